@@ -1,0 +1,195 @@
+/*
+ * vrenb200.h — C ABI of the B200-native replacement for vren's data-parallel compute core.
+ *
+ * Every entry point is what a binding from the reference (loryruta/vren, C++/Vulkan) would call in
+ * place of recording Vulkan dispatches.  All `*_run`-style calls are:
+ *   - asynchronous on the given CUDA stream (the analogue of "record into a VkCommandBuffer"),
+ *   - allocation-free and host-sync-free (caller owns inputs, outputs and scratch),
+ *   - re-entrant: no global mutable state.
+ * Pointers are raw device pointers unless the name ends in `_host`.  Lengths are ELEMENTS,
+ * sizes are BYTES.  Return value: 0 on success, one of VRENB200_E* otherwise.
+ *
+ * Reference interface each group replaces (paths relative to the reference checkout):
+ *   helpers   vren/vren/base/base.hpp:32-79
+ *   reduce    vren/vren/primitives/reduce.hpp:28-46, reduce.cpp:33-128, shaders/reduce.comp:50-87
+ *   scan      vren/vren/primitives/blelloch_scan.hpp:31-48, blelloch_scan.cpp:57-166
+ *   radix     vren/vren/primitives/radix_sort.hpp:42-52, radix_sort.cpp:124-337
+ *   bucket    vren/vren/primitives/bucket_sort.hpp:33-44, bucket_sort.cpp:62-161
+ *   bvh       vren/vren/primitives/build_bvh.hpp:8-56, build_bvh.cpp:38-136
+ *   lights    vren/vren/pipeline/clustered_shading.hpp:19-108, clustered_shading.cpp:29-690
+ */
+#ifndef VRENB200_H_
+#define VRENB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cudaStream_t without dragging cuda_runtime.h into C callers */
+typedef struct CUstream_st* vrenb200_stream_t;
+
+enum {
+    VRENB200_OK = 0,
+    VRENB200_EINVAL_LENGTH = 1,   /* length precondition violated (e.g. radix_sort compat: n>=1024 && pow2) */
+    VRENB200_EALIGN = 2,          /* pointer / offset alignment violated */
+    VRENB200_ESCRATCH = 3,        /* scratch buffer missing or too small */
+    VRENB200_ECUDA = 4,           /* a CUDA runtime call failed; see vrenb200_last_cuda_error() */
+    VRENB200_EINVAL_ARG = 5,      /* null pointer / bad enum */
+    VRENB200_ELIMIT = 6           /* exceeds an implementation limit (documented per call) */
+};
+
+/* element types of vren::reduce<T,op> (reduce.cpp:130-135) + scalar f32 as an extension */
+enum { VRENB200_U32 = 0, VRENB200_VEC4 = 1, VRENB200_F32 = 2 };
+/* vren::reduce_operation (reduce.hpp:8-13) */
+enum { VRENB200_ADD = 0, VRENB200_MIN = 1, VRENB200_MAX = 2 };
+/* output layout of reduce: TREE = full Blelloch up-sweep tree in out[0..P) (what the reference writes,
+ * reduce.comp:83-86); FINAL = only out[P-1] is written (what every in-repo caller consumes) */
+enum { VRENB200_REDUCE_TREE = 0, VRENB200_REDUCE_FINAL = 1 };
+
+const char* vrenb200_version(void);
+const char* vrenb200_status_string(int status);
+/* last cudaError_t seen by this thread inside the library (0 if none) */
+int vrenb200_last_cuda_error(void);
+
+/* ---- a10: integer helpers (base/base.hpp:32-79), restated in pure integer arithmetic ---------- */
+int      vrenb200_is_power_of_2(uint32_t v);
+uint32_t vrenb200_round_to_next_power_of_2(uint32_t v);
+uint64_t vrenb200_round_to_next_multiple_of(uint64_t v, uint64_t multiple);
+uint32_t vrenb200_divide_and_ceil(uint32_t v, uint32_t d);
+int      vrenb200_is_power_of(uint32_t n, uint32_t base);
+uint32_t vrenb200_round_to_next_power_of(uint32_t n, uint32_t base);
+
+/* ---- a1: reduce ------------------------------------------------------------------------------- */
+/* calc_reduce_output_buffer_length (reduce.cpp:137-140) */
+uint32_t vrenb200_calc_reduce_output_buffer_length(uint32_t count);
+/* scratch needed by FINAL mode (TREE mode needs none: partials live in the tree itself) */
+size_t vrenb200_reduce_scratch_bytes(int dtype, int mode, uint32_t n, uint32_t blocks);
+/* rows: in + y*n, out + y*P  (reduce.comp:52-53); `out` may alias `in` (reduce.cpp:117-128) */
+int vrenb200_reduce(vrenb200_stream_t stream, int dtype, int op, int mode,
+                    const void* in, uint32_t n, void* out, uint32_t blocks,
+                    void* scratch, size_t scratch_bytes);
+
+/* ---- a2: exclusive add-scan of uint32 ---------------------------------------------------------- */
+size_t vrenb200_scan_scratch_bytes(uint32_t n);
+/* in-place when out==in; any n>=1 (reference requires pow2: blelloch_scan.cpp:67) */
+int vrenb200_exclusive_scan_u32(vrenb200_stream_t stream, const uint32_t* in, uint32_t* out, uint32_t n,
+                                void* scratch, size_t scratch_bytes);
+/* blelloch_scan::downsweep (blelloch_scan.cpp:57-139): turns `blocks` up-sweep trees of pow2 length n
+ * into exclusive scans (+root when clear_last==0), in place */
+int vrenb200_blelloch_downsweep_u32(vrenb200_stream_t stream, uint32_t* buf, uint32_t n, uint32_t blocks,
+                                    int clear_last);
+
+/* ---- a3: radix sort ---------------------------------------------------------------------------- */
+/* one scratch blob holds the ping-pong buffers, digit histograms and look-back state. n < 2^30 */
+size_t vrenb200_radix_sort_scratch_bytes(uint32_t n, int with_values);
+/* ascending sort of uint32 keys, result in `keys` (radix_sort.cpp:149-337 semantics, any n>=0) */
+int vrenb200_radix_sort_keys(vrenb200_stream_t stream, uint32_t* keys, uint32_t n,
+                             void* scratch, size_t scratch_bytes);
+/* key-value extension: stable ascending by key, result in keys/values */
+int vrenb200_radix_sort_pairs(vrenb200_stream_t stream, uint32_t* keys, uint32_t* values, uint32_t n,
+                              void* scratch, size_t scratch_bytes);
+/* sizes of the two scratch buffers of the reference-shaped call (radix_sort.cpp:124-147 are SMALLER;
+ * the facade's create_scratch_buffer_1/2 use these) */
+size_t vrenb200_radix_sort_scratch_buffer_1_bytes(uint32_t n);
+size_t vrenb200_radix_sort_scratch_buffer_2_bytes(uint32_t n);
+/* reference-shaped call: two separate scratch buffers, enforces n>=1024 && pow2 (radix_sort.cpp:158-161) */
+int vrenb200_radix_sort_compat(vrenb200_stream_t stream, uint32_t* keys, uint32_t n,
+                               void* scratch_1, size_t scratch_1_bytes,
+                               void* scratch_2, size_t scratch_2_bytes);
+/* end-to-end variant with HOST buffers: H2D, sort, D2H on `stream`, then stream sync.
+ * `dev_work` must hold 8n (keys-only: 4n) bytes + scratch; used by bench.py's e2e leg */
+size_t vrenb200_radix_sort_host_work_bytes(uint32_t n, int with_values);
+int vrenb200_radix_sort_pairs_host(vrenb200_stream_t stream, uint32_t* keys_host, uint32_t* values_host,
+                                   uint32_t n, void* dev_work, size_t dev_work_bytes);
+
+/* tuning / measurement hooks (not part of the reference surface) */
+int vrenb200_radix_sort_set_variant(int variant);
+int vrenb200_radix_sort_num_variants(void);
+const char* vrenb200_radix_sort_variant_name(int variant);
+typedef struct vrenb200_sort_profile vrenb200_sort_profile;   /* CUDA events around every kernel of one sort */
+vrenb200_sort_profile* vrenb200_sort_profile_create(void);
+void vrenb200_sort_profile_destroy(vrenb200_sort_profile* p);
+/* values may be NULL (keys only). ms_out[6] = {histogram, histogram-scan, pass0..pass3}, read after stream sync */
+int vrenb200_radix_sort_pairs_profiled(vrenb200_stream_t stream, uint32_t* keys, uint32_t* values, uint32_t n,
+                                       void* scratch, size_t scratch_bytes, vrenb200_sort_profile* prof);
+int vrenb200_sort_profile_read(vrenb200_sort_profile* p, float* ms_out);
+
+/* ---- a4: bucket sort (16-bit key counting sort of uvec2) --------------------------------------- */
+/* bucket_sort::get_required_output_buffer_size (bucket_sort.cpp:67-70) */
+size_t vrenb200_bucket_sort_output_bytes(uint32_t n);
+size_t vrenb200_bucket_sort_scratch_bytes(uint32_t n);
+/* out: sorted uvec2[n], then at round_up(8n,256) 65536 counters holding bucket END offsets
+ * (bucket_sort.cpp:86, bucket_sort_write.comp:32). Ties keep input order (canonical choice). */
+int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pairs, uint32_t n, void* out,
+                         void* scratch, size_t scratch_bytes);
+
+/* ---- a5: 32-ary implicit BVH ------------------------------------------------------------------- */
+typedef struct vrenb200_bvh_node {   /* == vren::bvh_node (build_bvh.hpp:8-18), 32 bytes */
+    float min[3]; uint32_t next;
+    float max[3]; uint32_t _pad;
+} vrenb200_bvh_node;
+#define VRENB200_BVH_LEAF_NODE    0xFFFFFFFFu
+#define VRENB200_BVH_INVALID_NODE 0xFFFFFFFEu
+
+uint32_t vrenb200_calc_bvh_padded_leaf_count(uint32_t leaf_count);  /* build_bvh.cpp:99-104 */
+uint32_t vrenb200_calc_bvh_buffer_length(uint32_t leaf_count);      /* build_bvh.cpp:106-118 */
+size_t   vrenb200_calc_bvh_buffer_size(uint32_t leaf_count);        /* build_bvh.cpp:120-124 */
+uint32_t vrenb200_calc_bvh_root_index(uint32_t leaf_count);         /* build_bvh.cpp:126-130 */
+uint32_t vrenb200_calc_bvh_level_count(uint32_t leaf_count);        /* build_bvh.cpp:132-136 */
+/* leaves pre-filled in nodes[0..padded); builds every upper level (build_bvh.cpp:38-97) */
+int vrenb200_build_bvh(vrenb200_stream_t stream, vrenb200_bvh_node* nodes, uint32_t padded_leaf_count);
+
+/* ---- a6: construct_point_light_bvh ------------------------------------------------------------- */
+size_t vrenb200_light_bvh_buffer_bytes(uint32_t light_count);        /* clustered_shading.cpp:34-47 */
+size_t vrenb200_light_index_buffer_bytes(uint32_t light_count);      /* clustered_shading.cpp:54-58 (+ bucket-sort counters) */
+size_t vrenb200_light_bvh_scratch_bytes(uint32_t light_count);
+/* positions: vec4[L] world space; lights: point_light{vec3 color; float intensity}[L];
+ * view: column-major mat4 (glm layout). Outputs: view_pos vec4[L]; bvh nodes at offset 0 of bvh_buffer;
+ * sorted uvec2{morton, light_idx}[L] at offset 0 of index_buffer (clustered_shading.cpp:60-346) */
+int vrenb200_construct_point_light_bvh(vrenb200_stream_t stream,
+                                       const float* positions, const float* lights, uint32_t light_count,
+                                       const float* view_col_major,
+                                       float* view_pos, void* bvh_buffer, void* index_buffer,
+                                       void* scratch, size_t scratch_bytes);
+
+/* ---- a7/a8: cluster keys and light assignment --------------------------------------------------- */
+typedef struct vrenb200_camera {    /* vren::camera projection inputs (camera.hpp:14-23, camera.cpp:40-50) */
+    float fov_y, aspect_ratio, near_plane, far_plane;
+} vrenb200_camera;
+
+typedef struct vrenb200_cluster_limits {   /* config.hpp:23-24 made runtime */
+    uint32_t max_unique_cluster_keys;      /* default 1<<17 */
+    uint32_t max_assigned_lights;          /* default 1<<23 */
+} vrenb200_cluster_limits;
+
+size_t vrenb200_find_unique_clusters_scratch_bytes(uint32_t width, uint32_t height);
+/* depth: float[W*H] (D32 aspect); normals: half4[W*H] (RGBA16F) or NULL (=all-zero normals).
+ * keys_out uint[max_keys]; dispatch_params uvec4 {count,1,1,overflow_flag}; cluster_ref uint[W*H]
+ * (find_unique_clusters.comp:46-121). Emits the canonical tile-major order. */
+int vrenb200_find_unique_clusters(vrenb200_stream_t stream,
+                                  const float* depth, const void* normals_rgba16f,
+                                  uint32_t width, uint32_t height, const vrenb200_camera* camera,
+                                  uint32_t* keys_out, uint32_t max_keys, uint32_t* dispatch_params,
+                                  uint32_t* cluster_ref,
+                                  void* scratch, size_t scratch_bytes);
+
+size_t vrenb200_assign_lights_scratch_bytes(uint32_t max_keys);
+/* counts/offsets: uint[max_keys]; indices: uint[max_assigned] (assign_lights.comp:121-241,
+ * clustered_shading.cpp:473-690). status_out (device uint[4], may be NULL):
+ * {total_assigned, overflow_flag, node_visits, leaf_tests} */
+int vrenb200_assign_lights(vrenb200_stream_t stream,
+                           uint32_t width, uint32_t height, const vrenb200_camera* camera,
+                           const uint32_t* cluster_keys, const uint32_t* dispatch_params, uint32_t max_keys,
+                           const void* bvh_buffer, uint32_t bvh_root_index, uint32_t light_count,
+                           const void* light_index_buffer, const float* view_pos,
+                           uint32_t* indices_out, uint32_t max_assigned,
+                           uint32_t* counts_out, uint32_t* offsets_out, uint32_t* status_out,
+                           void* scratch, size_t scratch_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRENB200_H_ */

@@ -1,0 +1,249 @@
+"""GPU parity: CUDA kernels (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Sizes and input patterns mirror the reference's own tests (vren_test/vren_test/primitives/*.cpp); the
+BASELINE.json full sizes are covered through size-independent properties (sortedness + permutation checksum,
+closed-form scans).  Integer results are compared bit-exactly; fp32 results bit-exactly as well (same tree).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import splitmix64
+
+pytestmark = pytest.mark.gpu
+
+
+def dev_u32(arr):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(arr, dtype=np.uint32).view(np.int32)).cuda()
+
+
+def host_u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def rand_u32(seed, n):
+    return (splitmix64(seed, n) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
+# ---- a1 reduce --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("op", ["add", "min", "max"])
+@pytest.mark.parametrize("n", [1, 10, 100, 1000, 4096, 10000, 100000, (1 << 20) + 17])
+def test_reduce_u32_tree_and_final(vren, op, n):
+    x = np.ones(n, np.uint32) if op == "add" and n <= 100000 else (rand_u32(3, n) % np.uint32(100)).astype(np.uint32)
+    want = oracle.reduce(x, n, "u32", op)
+    got = host_u32(vren.reduce(dev_u32(x), n, "u32", op, mode="tree"))
+    assert np.array_equal(got, want)                 # the whole padded tree, like the reference test
+    P = oracle.next_pow2(n)
+    fin = host_u32(vren.reduce(dev_u32(x), n, "u32", op, mode="final"))
+    assert fin[P - 1] == want[P - 1]
+
+
+@pytest.mark.parametrize("op", ["add", "min", "max"])
+@pytest.mark.parametrize("n", [1, 7, 1000, 1024, 10000, 70001])
+def test_reduce_vec4_bit_exact(vren, op, n):
+    import torch
+
+    # TEST(reduce, type_vec4): rand()%100 as float; plus non-integers so the add order matters
+    x = (rand_u32(5, 4 * n) % np.uint32(100)).astype(np.float32) + (rand_u32(6, 4 * n) >> np.uint32(8)).astype(np.float32) / np.float32(1 << 24)
+    want = oracle.reduce(x, n, "vec4", op)
+    got = vren.reduce(torch.from_numpy(x).cuda(), n, "vec4", op, mode="tree").cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    P = oracle.next_pow2(n)
+    fin = vren.reduce(torch.from_numpy(x).cuda(), n, "vec4", op, mode="final").cpu().numpy()
+    assert np.array_equal(fin.reshape(-1, 4)[P - 1].view(np.uint32), want.reshape(-1, 4)[P - 1].view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [5, 4096, 5000, 1 << 16, 300001])
+def test_reduce_f32_add_tree_order(vren, n):
+    import torch
+
+    x = (rand_u32(9, n) >> np.uint32(8)).astype(np.float32) / np.float32(1 << 24)   # U[0,1)
+    want = oracle.reduce(x, n, "f32", "add")
+    got = vren.reduce(torch.from_numpy(x).cuda(), n, "f32", "add", mode="tree").cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    P = oracle.next_pow2(n)
+    fin = vren.reduce(torch.from_numpy(x).cuda(), n, "f32", "add", mode="final").cpu().numpy()
+    assert fin.view(np.uint32)[P - 1] == want.view(np.uint32)[P - 1]
+    # north-star tolerance for fp32 reduce: 1e-6 relative vs an fp64 sum
+    assert abs(float(fin[P - 1]) - float(x.astype(np.float64).sum())) <= 1e-6 * float(x.astype(np.float64).sum()) + 1e-6
+
+
+def test_reduce_rows_and_in_place(vren):
+    n, blocks = 2048, 16   # the shape radix_sort.cpp:230 uses (blocks = 16 digit rows)
+    x = (rand_u32(10, n * blocks) % np.uint32(1000)).astype(np.uint32)
+    want = oracle.reduce(x, n, "u32", "add", blocks=blocks)
+    d = dev_u32(x)
+    got = host_u32(vren.reduce(d, n, "u32", "add", mode="tree", blocks=blocks, out=d))   # in place (reduce.cpp:117-128)
+    assert np.array_equal(got, want)
+    n = 300                   # non-pow2 rows: in stride n, out stride P
+    x = (rand_u32(11, n * 3) % np.uint32(1000)).astype(np.uint32)
+    want = oracle.reduce(x, n, "u32", "max", blocks=3)
+    assert np.array_equal(host_u32(vren.reduce(dev_u32(x), n, "u32", "max", mode="tree", blocks=3)), want)
+    fin = host_u32(vren.reduce(dev_u32(x), n, "u32", "max", mode="final", blocks=3))
+    assert np.array_equal(fin[511::512], want[511::512])
+
+
+def test_reduce_full_size_c2(vren):
+    import torch
+
+    n = 1 << 28   # BASELINE C2
+    x = torch.ones(n, dtype=torch.int32, device="cuda")
+    fin = vren.reduce(x, n, "u32", "add", mode="final")
+    assert int(fin[n - 1].item()) == n
+    x = torch.arange(n, dtype=torch.int32, device="cuda")
+    assert int(vren.reduce(x, n, "u32", "max", mode="final")[n - 1].item()) == n - 1
+    tree = vren.reduce(x, n, "u32", "add", mode="tree")
+    # closed form for slots: sum over the aligned block ending at i
+    for i in (0, 1, 3, 4095, 4096 * 7 - 1, (1 << 22) - 1, n - 1, n // 2 - 1):
+        size = ((i + 1) & -(i + 1))
+        lo = i - size + 1
+        want = (size * (lo + i) // 2) & 0xFFFFFFFF
+        assert (int(tree[i].item()) & 0xFFFFFFFF) == want
+    f = torch.full((n,), 0.25, dtype=torch.float32, device="cuda")
+    assert float(vren.reduce(f, n, "f32", "add", mode="final")[n - 1].item()) == n * 0.25
+
+
+# ---- a2 scan ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log2n", range(0, 20))
+def test_scan_all_ones_pow2(vren, log2n):
+    n = 1 << log2n   # TEST(blelloch_scan, main)
+    x = np.ones(n, np.uint32)
+    got = host_u32(vren.exclusive_scan(dev_u32(x)))
+    assert np.array_equal(got, oracle.exclusive_scan(x))
+
+
+@pytest.mark.parametrize("n", [3, 1000, 4096, 4097, 123457, (1 << 21) + 5])
+def test_scan_random_wraparound_any_length(vren, n):
+    x = rand_u32(13, n)
+    want = oracle.exclusive_scan(x)
+    assert np.array_equal(host_u32(vren.exclusive_scan(dev_u32(x))), want)          # in place
+    import torch
+
+    src = dev_u32(x)
+    dst = torch.zeros_like(src)
+    vren.exclusive_scan(src, out=dst)                                                # out of place
+    assert np.array_equal(host_u32(dst), want) and np.array_equal(host_u32(src), x)
+
+
+def test_scan_full_size_c2(vren):
+    import torch
+
+    n = 1 << 28
+    x = torch.ones(n, dtype=torch.int32, device="cuda")
+    vren.exclusive_scan(x)
+    assert torch.equal(x, torch.arange(n, dtype=torch.int32, device="cuda"))
+    y = torch.full((n,), 0x01000193, dtype=torch.int32, device="cuda")   # wraps many times
+    vren.exclusive_scan(y)
+    idx = torch.tensor([0, 1, 4095, 4096, n // 3, n - 1], device="cuda")
+    want = [(i * 0x01000193) & 0xFFFFFFFF for i in idx.tolist()]
+    assert [v & 0xFFFFFFFF for v in y[idx].tolist()] == want
+
+
+@pytest.mark.parametrize("n,blocks,clear", [(1, 1, True), (256, 1, False), (1024, 1, True), (2048, 3, True),
+                                             (1 << 15, 16, True), (1 << 15, 2, False), (1 << 21, 1, True)])
+def test_downsweep_matches_reference_levels(vren, n, blocks, clear):
+    x = (rand_u32(15, n * blocks) % np.uint32(1000)).astype(np.uint32)
+    tree = oracle.reduce(x, n, "u32", "add", blocks=blocks)
+    want = oracle.downsweep(tree, n, blocks, clear)
+    got = host_u32(vren.downsweep(dev_u32(tree), n, blocks, clear))
+    assert np.array_equal(got, want)
+    if clear:
+        for y in range(blocks):
+            assert np.array_equal(got[y * n:(y + 1) * n], oracle.exclusive_scan(x[y * n:(y + 1) * n]))
+
+
+# ---- a3 radix sort ----------------------------------------------------------------------------------------------
+def test_radix_reference_case_reversed_iota_1024(vren):
+    n = 1 << 10   # TEST(radix_sort, main)
+    x = np.arange(n, dtype=np.uint32)[::-1].copy()
+    assert np.array_equal(host_u32(vren.radix_sort_keys(dev_u32(x))), oracle.sort_keys(x))
+
+
+@pytest.mark.parametrize("pattern", ["uniform", "reversed", "mod100", "equal", "top_digit_only"])
+@pytest.mark.parametrize("n", [1, 2, 31, 1000, 6144, 6145, 1 << 16, (1 << 20), (1 << 20) + 4097])
+def test_radix_keys_vs_std_sort(vren, pattern, n):
+    if pattern == "uniform":
+        x = rand_u32(1, n)
+    elif pattern == "reversed":
+        x = np.arange(n, dtype=np.uint32)[::-1].copy()
+    elif pattern == "mod100":
+        x = (rand_u32(2, n) % np.uint32(100)).astype(np.uint32)
+    elif pattern == "equal":
+        x = np.full(n, 0xFFFFFFFF, np.uint32)
+    else:
+        x = (rand_u32(4, n) & np.uint32(0xFF000000)).astype(np.uint32)
+    assert np.array_equal(host_u32(vren.radix_sort_keys(dev_u32(x))), oracle.sort_keys(x))
+
+
+@pytest.mark.parametrize("n", [1, 77, 6144, 1 << 14, (1 << 20), (1 << 20) + 1234])
+def test_radix_pairs_stable(vren, n):
+    # few distinct keys -> stability is observable through the values
+    k = (rand_u32(21, n) % np.uint32(1000) * np.uint32(0x00410041)).astype(np.uint32)
+    v = np.arange(n, dtype=np.uint32)
+    wk, wv = oracle.sort_pairs(k, v)
+    gk, gv = vren.radix_sort_pairs(dev_u32(k), dev_u32(v))
+    assert np.array_equal(host_u32(gk), wk) and np.array_equal(host_u32(gv), wv)
+    k = rand_u32(22, n)
+    wk, wv = oracle.sort_pairs(k, v)
+    gk, gv = vren.radix_sort_pairs(dev_u32(k), dev_u32(v))
+    assert np.array_equal(host_u32(gk), wk) and np.array_equal(host_u32(gv), wv)
+
+
+def test_radix_all_variants_agree(vren):
+    lib = vren.load()
+    n = (1 << 18) + 333
+    k = rand_u32(23, n)
+    v = np.arange(n, dtype=np.uint32)
+    wk, wv = oracle.sort_pairs(k, v)
+    try:
+        for var in range(lib.vrenb200_radix_sort_num_variants()):
+            assert lib.vrenb200_radix_sort_set_variant(var) == 0
+            gk, gv = vren.radix_sort_pairs(dev_u32(k), dev_u32(v))
+            assert np.array_equal(host_u32(gk), wk), lib.vrenb200_radix_sort_variant_name(var)
+            assert np.array_equal(host_u32(gv), wv), lib.vrenb200_radix_sort_variant_name(var)
+            assert np.array_equal(host_u32(vren.radix_sort_keys(dev_u32(k))), wk)
+    finally:
+        lib.vrenb200_radix_sort_set_variant(0)
+
+
+def test_radix_compat_preconditions(vren):
+    import torch
+
+    lib = vren.load()
+    buf = torch.zeros(4096, dtype=torch.int32, device="cuda")
+    s1 = torch.zeros(lib.vrenb200_radix_sort_scratch_buffer_1_bytes(4096), dtype=torch.uint8, device="cuda")
+    s2 = torch.zeros(lib.vrenb200_radix_sort_scratch_buffer_2_bytes(4096), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    # radix_sort.cpp:158-161 -> std::invalid_argument
+    for bad in (0, 512, 1000, 3000):
+        assert lib.vrenb200_radix_sort_compat(st, buf.data_ptr(), bad, s1.data_ptr(), s1.numel(), s2.data_ptr(), s2.numel()) == 1
+    x = np.arange(4096, dtype=np.uint32)[::-1].copy()
+    d = dev_u32(x)
+    assert lib.vrenb200_radix_sort_compat(st, d.data_ptr(), 4096, s1.data_ptr(), s1.numel(), s2.data_ptr(), s2.numel()) == 0
+    assert np.array_equal(host_u32(d), np.arange(4096, dtype=np.uint32))
+    assert lib.vrenb200_radix_sort_compat(st, d.data_ptr(), 4096, s1.data_ptr(), 16, s2.data_ptr(), s2.numel()) == 3
+
+
+def test_radix_pairs_full_size_headline(vren):
+    """2^28 pairs (BASELINE metric size): sortedness, permutation, key/value consistency, stability."""
+    import torch
+
+    n = 1 << 28
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234)
+    keys = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
+    vals = torch.arange(n, dtype=torch.int32, device="cuda")
+    orig = keys.clone()
+    vren.radix_sort_pairs(keys, vals)
+    torch.cuda.synchronize()
+    # unsigned order == signed order after flipping the sign bit
+    flipped = keys ^ torch.tensor(-(1 << 31), dtype=torch.int32, device="cuda")
+    assert bool((flipped[1:] >= flipped[:-1]).all())
+    assert torch.equal(orig[vals.long()], keys)                      # every pair kept together
+    marks = torch.zeros(n, dtype=torch.bool, device="cuda")
+    marks[vals.long()] = True
+    assert bool(marks.all())                                          # values are a permutation
+    ties = flipped[1:] == flipped[:-1]
+    assert bool((vals[1:][ties] > vals[:-1][ties]).all())             # stable

@@ -1,0 +1,240 @@
+// a2 — vren::blelloch_scan (reference: vren/vren/primitives/blelloch_scan.{hpp,cpp},
+// shaders/blelloch_scan_downsweep.comp:34-125).
+//
+// operator(): exclusive add-scan of uint32 (mod 2^32).  The reference runs reduce (up-sweep) + one strided
+// dispatch per level above 2^10 + a workgroup pass (~22 dispatches and ~3 round trips over the data at 2^28).
+// Here: ONE single-pass chained scan with decoupled look-back: each CTA scans a 4096-element tile held in
+// registers (128-bit loads, warp-shuffle scans), publishes {aggregate | inclusive prefix} in a 64-bit
+// status word, and a warp-wide look-back window resolves its exclusive prefix.  8 B/elt of HBM traffic.
+//
+// downsweep(): kept for API parity (radix_sort.cpp:281-289 calls it directly): takes an up-sweep TREE and
+// turns it into the scan, 10 levels per launch in shared memory, top-down.
+#include "common.cuh"
+
+namespace vrenb200 {
+
+namespace {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanVecs = 4;                                        // uint4 per thread
+constexpr uint32_t kScanTile = kScanThreads * kScanVecs * 4;        // 4096 elements
+constexpr uint32_t kWarpChunk = 32 * kScanVecs * 4;                 // 512 contiguous elements per warp
+
+constexpr uint64_t kFlagAggregate = 1ull << 32;
+constexpr uint64_t kFlagInclusive = 2ull << 32;
+
+struct scan_state
+{
+    uint32_t ticket;      // dynamic tile id: guarantees a tile only waits on tiles that already started
+    uint32_t _pad[63];
+    uint64_t status[1];   // [tiles]
+};
+
+__global__ void __launch_bounds__(kScanThreads)
+exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_state* state)
+{
+    __shared__ uint32_t s_warp_total[kScanWarps];
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile_prefix;
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(&state->ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t warp_base = (uint64_t) tile * kScanTile + warp * kWarpChunk;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+
+    uint4 x[kScanVecs];
+#pragma unroll
+    for (int v = 0; v < kScanVecs; v++)
+    {
+        const uint64_t idx = warp_base + v * 128 + lane * 4;
+        if (vec_ok && idx + 4 <= n)
+            x[v] = ldg_stream_u4(reinterpret_cast<const uint4*>(in + idx));
+        else
+        {
+            x[v].x = idx + 0 < n ? in[idx + 0] : 0u;
+            x[v].y = idx + 1 < n ? in[idx + 1] : 0u;
+            x[v].z = idx + 2 < n ? in[idx + 2] : 0u;
+            x[v].w = idx + 3 < n ? in[idx + 3] : 0u;
+        }
+    }
+
+    // in-thread exclusive scan of each vector + warp scan of the vector totals, carried across v
+    uint32_t carry = 0;
+#pragma unroll
+    for (int v = 0; v < kScanVecs; v++)
+    {
+        const uint32_t a = x[v].x, b = x[v].y, c = x[v].z, d = x[v].w;
+        const uint32_t total = a + b + c + d;
+        uint32_t inc = total;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(kFullMask, inc, s);
+            if (lane >= (unsigned) s) inc += t;
+        }
+        const uint32_t base = carry + inc - total;
+        carry += __shfl_sync(kFullMask, inc, 31);
+        x[v].x = base;
+        x[v].y = base + a;
+        x[v].z = base + a + b;
+        x[v].w = base + a + b + c;
+    }
+    if (lane == 31) s_warp_total[warp] = carry;
+    __syncthreads();
+
+    uint32_t warp_prefix = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kScanWarps; w++)
+    {
+        const uint32_t t = s_warp_total[w];
+        if (w < (int) warp) warp_prefix += t;
+        tile_total += t;
+    }
+
+    // decoupled look-back, one warp, 32 predecessors per probe
+    if (warp == 0)
+    {
+        uint64_t* status = state->status;
+        if (lane == 0)
+            st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | tile_total);
+        uint32_t exclusive = 0;
+        if (tile > 0)
+        {
+            int64_t base = (int64_t) tile - 1;
+            while (true)
+            {
+                const int64_t t = base - lane;
+                uint64_t s = kFlagInclusive; // virtual tile before tile 0: inclusive prefix 0
+                if (t >= 0)
+                {
+                    do { s = ld_relaxed_u64(&status[t]); } while ((s >> 32) == 0);
+                }
+                const unsigned incl = __ballot_sync(kFullMask, (s >> 32) == 2);
+                uint32_t val = (uint32_t) s;
+                if (incl != 0)
+                {
+                    const unsigned first = __ffs(incl) - 1;
+                    if (lane > first) val = 0;
+                }
+                val = __reduce_add_sync(kFullMask, val);
+                exclusive += val;
+                if (incl != 0) break;
+                base -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (exclusive + tile_total));
+        }
+        if (lane == 0) s_tile_prefix = exclusive;
+    }
+    __syncthreads();
+    const uint32_t prefix = s_tile_prefix + warp_prefix;
+
+#pragma unroll
+    for (int v = 0; v < kScanVecs; v++)
+    {
+        const uint64_t idx = warp_base + v * 128 + lane * 4;
+        x[v].x += prefix; x[v].y += prefix; x[v].z += prefix; x[v].w += prefix;
+        if (vec_ok && idx + 4 <= n)
+            *reinterpret_cast<uint4*>(out + idx) = x[v];
+        else
+        {
+            if (idx + 0 < n) out[idx + 0] = x[v].x;
+            if (idx + 1 < n) out[idx + 1] = x[v].y;
+            if (idx + 2 < n) out[idx + 2] = x[v].z;
+            if (idx + 3 < n) out[idx + 3] = x[v].w;
+        }
+    }
+}
+
+// blelloch_scan_downsweep.comp:59-125 generalised to a strided logical array: logical element i lives at
+// buf[(i+1)*stride-1]; `levels` = min(10, log2(count)) down-sweep levels in shared memory.
+__global__ void __launch_bounds__(1024)
+downsweep_strided_kernel(uint32_t* buf, uint32_t count, uint64_t stride, uint64_t row_stride,
+                         int clear_last, int levels)
+{
+    __shared__ uint32_t s_data[1024];
+    uint32_t* row = buf + blockIdx.y * row_stride;
+    const uint32_t gi = blockIdx.x * 1024u + threadIdx.x;
+    const uint64_t idx = ((uint64_t) gi + 1) * stride - 1;
+    uint32_t v = gi < count ? row[idx] : 0u;
+    if (clear_last && gi == count - 1) v = 0u;
+    s_data[threadIdx.x] = v;
+    __syncthreads();
+    for (int level = levels - 1; level >= 0; level--)
+    {
+        const uint32_t m = (1u << (level + 1)) - 1;
+        if ((threadIdx.x & m) == m)
+        {
+            const uint32_t a = threadIdx.x - (1u << level);
+            const uint32_t t = s_data[threadIdx.x];
+            s_data[threadIdx.x] = s_data[a] + t;
+            s_data[a] = t;
+        }
+        __syncthreads();
+    }
+    if (gi < count) row[idx] = s_data[threadIdx.x];
+}
+
+inline int ilog2(uint32_t v) { int r = 0; while (v >>= 1) r++; return r; }
+
+} // namespace
+} // namespace vrenb200
+
+using namespace vrenb200;
+
+extern "C" size_t vrenb200_scan_scratch_bytes(uint32_t n)
+{
+    const size_t tiles = ((size_t) n + kScanTile - 1) / kScanTile;
+    return align_up(offsetof(scan_state, status) + (tiles > 0 ? tiles : 1) * sizeof(uint64_t), 256);
+}
+
+extern "C" int vrenb200_exclusive_scan_u32(vrenb200_stream_t stream, const uint32_t* in, uint32_t* out, uint32_t n,
+                                           void* scratch, size_t scratch_bytes)
+{
+    if (in == nullptr || out == nullptr) return VRENB200_EINVAL_ARG;
+    if (n == 0) return VRENB200_EINVAL_LENGTH;
+    const size_t need = vrenb200_scan_scratch_bytes(n);
+    if (scratch == nullptr || scratch_bytes < need) return VRENB200_ESCRATCH;
+    if ((reinterpret_cast<uintptr_t>(scratch) & 7) != 0) return VRENB200_EALIGN;
+    cudaStream_t s = as_stream(stream);
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, need, s)));
+    const uint32_t tiles = (uint32_t) (((size_t) n + kScanTile - 1) / kScanTile);
+    exclusive_scan_u32_kernel<<<tiles, kScanThreads, 0, s>>>(in, out, n, static_cast<scan_state*>(scratch));
+    return check_launch();
+}
+
+extern "C" int vrenb200_blelloch_downsweep_u32(vrenb200_stream_t stream, uint32_t* buf, uint32_t n, uint32_t blocks,
+                                               int clear_last)
+{
+    if (buf == nullptr) return VRENB200_EINVAL_ARG;
+    if (n == 0 || (n & (n - 1)) != 0 || blocks == 0 || blocks > 65535) return VRENB200_EINVAL_LENGTH;
+    cudaStream_t s = as_stream(stream);
+    // n < 1024: the reference's zero-filled 1024-wide tile swallows the root, i.e. behaves as clear_last
+    // (blelloch_scan_downsweep.comp:68-75,83-97)
+    if (n < 1024) clear_last = 1;
+    const int total_levels = ilog2(n);
+    // top-down groups of <=10 levels; the top group takes the remainder so lower groups are full 1024-blocks
+    int top_levels = total_levels % 10;
+    int done = 0;
+    bool first = true;
+    if (total_levels == 0)
+    {
+        downsweep_strided_kernel<<<dim3(1, blocks), 1024, 0, s>>>(buf, 1, 1, n, clear_last, 0);
+        return check_launch();
+    }
+    while (done < total_levels)
+    {
+        const int levels = (first && top_levels != 0) ? top_levels : 10;
+        const int remaining_below = total_levels - done - levels;     // levels handled by later launches
+        const uint64_t stride = 1ull << remaining_below;
+        const uint32_t count = (uint32_t) ((uint64_t) n >> remaining_below);
+        const dim3 grid((count + 1023) / 1024, blocks);
+        downsweep_strided_kernel<<<grid, 1024, 0, s>>>(buf, count, stride, n, first ? clear_last : 0, levels);
+        VRENB200_TRY(check_launch());
+        done += levels;
+        first = false;
+    }
+    return VRENB200_OK;
+}

@@ -1,0 +1,198 @@
+"""ctypes binding of libvrenb200.so (the C ABI declared in include/vrenb200.h).
+
+PyTorch is used only as the owner of device memory and streams; every compute call goes through the C ABI.
+There is NO CPU fallback: if the shared library is missing the import of the symbols fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB_PATH = Path(__file__).resolve().parent / "libvrenb200.so"
+HEADER = ROOT / "include" / "vrenb200.h"
+
+OK = 0
+STATUS_NAMES = {0: "OK", 1: "EINVAL_LENGTH", 2: "EALIGN", 3: "ESCRATCH", 4: "ECUDA", 5: "EINVAL_ARG", 6: "ELIMIT"}
+U32, VEC4, F32 = 0, 1, 2
+ADD, MIN, MAX = 0, 1, 2
+REDUCE_TREE, REDUCE_FINAL = 0, 1
+BVH_LEAF_NODE = 0xFFFFFFFF
+BVH_INVALID_NODE = 0xFFFFFFFE
+
+
+class VrenError(RuntimeError):
+    def __init__(self, status: int, what: str):
+        self.status = status
+        super().__init__(f"{what}: status {status} ({STATUS_NAMES.get(status, '?')})")
+
+
+class Camera(C.Structure):
+    _fields_ = [("fov_y", C.c_float), ("aspect_ratio", C.c_float), ("near_plane", C.c_float), ("far_plane", C.c_float)]
+
+
+def declared_symbols() -> list[str]:
+    """every function name include/vrenb200.h declares (used by the CPU-side export test)"""
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vrenb200_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m vren_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback for the vren_b200 compute path."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    vp, u32, u64, sz, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_int
+
+    def sig(name, res, *args):
+        f = getattr(lib, name)
+        f.restype = res
+        f.argtypes = list(args)
+
+    sig("vrenb200_version", C.c_char_p)
+    sig("vrenb200_status_string", C.c_char_p, i32)
+    sig("vrenb200_last_cuda_error", i32)
+    sig("vrenb200_is_power_of_2", i32, u32)
+    sig("vrenb200_round_to_next_power_of_2", u32, u32)
+    sig("vrenb200_round_to_next_multiple_of", u64, u64, u64)
+    sig("vrenb200_divide_and_ceil", u32, u32, u32)
+    sig("vrenb200_is_power_of", i32, u32, u32)
+    sig("vrenb200_round_to_next_power_of", u32, u32, u32)
+    sig("vrenb200_calc_reduce_output_buffer_length", u32, u32)
+    sig("vrenb200_reduce_scratch_bytes", sz, i32, i32, u32, u32)
+    sig("vrenb200_reduce", i32, vp, i32, i32, i32, vp, u32, vp, u32, vp, sz)
+    sig("vrenb200_scan_scratch_bytes", sz, u32)
+    sig("vrenb200_exclusive_scan_u32", i32, vp, vp, vp, u32, vp, sz)
+    sig("vrenb200_blelloch_downsweep_u32", i32, vp, vp, u32, u32, i32)
+    sig("vrenb200_radix_sort_scratch_bytes", sz, u32, i32)
+    sig("vrenb200_radix_sort_keys", i32, vp, vp, u32, vp, sz)
+    sig("vrenb200_radix_sort_pairs", i32, vp, vp, vp, u32, vp, sz)
+    sig("vrenb200_radix_sort_scratch_buffer_1_bytes", sz, u32)
+    sig("vrenb200_radix_sort_scratch_buffer_2_bytes", sz, u32)
+    sig("vrenb200_radix_sort_compat", i32, vp, vp, u32, vp, sz, vp, sz)
+    sig("vrenb200_radix_sort_host_work_bytes", sz, u32, i32)
+    sig("vrenb200_radix_sort_pairs_host", i32, vp, vp, vp, u32, vp, sz)
+    sig("vrenb200_radix_sort_set_variant", i32, i32)
+    sig("vrenb200_radix_sort_num_variants", i32)
+    sig("vrenb200_radix_sort_variant_name", C.c_char_p, i32)
+    sig("vrenb200_sort_profile_create", vp)
+    sig("vrenb200_sort_profile_destroy", None, vp)
+    sig("vrenb200_sort_profile_read", i32, vp, C.POINTER(C.c_float))
+    sig("vrenb200_radix_sort_pairs_profiled", i32, vp, vp, vp, u32, vp, sz, vp)
+    for name, res, args in _LATE_SIGS:
+        if hasattr(lib, name):
+            sig(name, res, *args)
+    _lib = lib
+    return lib
+
+
+_vp, _u32, _sz, _i32 = C.c_void_p, C.c_uint32, C.c_size_t, C.c_int
+_LATE_SIGS = [
+    ("vrenb200_bucket_sort_output_bytes", _sz, (_u32,)),
+    ("vrenb200_bucket_sort_scratch_bytes", _sz, (_u32,)),
+    ("vrenb200_bucket_sort", _i32, (_vp, _vp, _u32, _vp, _vp, _sz)),
+    ("vrenb200_calc_bvh_padded_leaf_count", _u32, (_u32,)),
+    ("vrenb200_calc_bvh_buffer_length", _u32, (_u32,)),
+    ("vrenb200_calc_bvh_buffer_size", _sz, (_u32,)),
+    ("vrenb200_calc_bvh_root_index", _u32, (_u32,)),
+    ("vrenb200_calc_bvh_level_count", _u32, (_u32,)),
+    ("vrenb200_build_bvh", _i32, (_vp, _vp, _u32)),
+    ("vrenb200_light_bvh_buffer_bytes", _sz, (_u32,)),
+    ("vrenb200_light_index_buffer_bytes", _sz, (_u32,)),
+    ("vrenb200_light_bvh_scratch_bytes", _sz, (_u32,)),
+    ("vrenb200_construct_point_light_bvh", _i32, (_vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _sz)),
+    ("vrenb200_find_unique_clusters_scratch_bytes", _sz, (_u32, _u32)),
+    ("vrenb200_find_unique_clusters", _i32,
+     (_vp, _vp, _vp, _u32, _u32, C.POINTER(Camera), _vp, _u32, _vp, _vp, _vp, _sz)),
+    ("vrenb200_assign_lights_scratch_bytes", _sz, (_u32,)),
+    ("vrenb200_assign_lights", _i32,
+     (_vp, _u32, _u32, C.POINTER(Camera), _vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _sz)),
+]
+
+
+def check(status: int, what: str) -> None:
+    if status != OK:
+        raise VrenError(status, what)
+
+
+# ---- torch-tensor convenience layer (tests / bench); torch imported lazily -----------------------------------
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _scratch(nbytes: int):
+    import torch
+
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device="cuda")
+
+
+_DT = {"u32": U32, "vec4": VEC4, "f32": F32}
+_OP = {"add": ADD, "min": MIN, "max": MAX}
+
+
+def reduce(inp, n: int, dtype: str, op: str, mode: str = "tree", blocks: int = 1, out=None):
+    """vren::reduce<T,op>. inp: device tensor (int32 storage for u32, float32 for f32/vec4 [n,4])."""
+    import torch
+
+    lib = load()
+    P = lib.vrenb200_round_to_next_power_of_2(n)
+    comps = 4 if dtype == "vec4" else 1
+    if out is None:
+        out = torch.zeros(blocks * P * comps, dtype=inp.dtype, device=inp.device)
+    m = REDUCE_TREE if mode == "tree" else REDUCE_FINAL
+    sb = lib.vrenb200_reduce_scratch_bytes(_DT[dtype], m, n, blocks)
+    scratch = _scratch(sb)
+    check(lib.vrenb200_reduce(_stream(), _DT[dtype], _OP[op], m, _ptr(inp), n, _ptr(out), blocks, _ptr(scratch), sb),
+          "vrenb200_reduce")
+    return out
+
+
+def exclusive_scan(inp, out=None, n: int | None = None):
+    lib = load()
+    n = inp.numel() if n is None else n
+    out = inp if out is None else out
+    sb = lib.vrenb200_scan_scratch_bytes(n)
+    scratch = _scratch(sb)
+    check(lib.vrenb200_exclusive_scan_u32(_stream(), _ptr(inp), _ptr(out), n, _ptr(scratch), sb), "vrenb200_exclusive_scan_u32")
+    return out
+
+
+def downsweep(buf, n: int, blocks: int = 1, clear_last: bool = True):
+    lib = load()
+    check(lib.vrenb200_blelloch_downsweep_u32(_stream(), _ptr(buf), n, blocks, int(clear_last)), "vrenb200_blelloch_downsweep_u32")
+    return buf
+
+
+def radix_sort_keys(keys, n: int | None = None):
+    lib = load()
+    n = keys.numel() if n is None else n
+    sb = lib.vrenb200_radix_sort_scratch_bytes(n, 0)
+    scratch = _scratch(sb)
+    check(lib.vrenb200_radix_sort_keys(_stream(), _ptr(keys), n, _ptr(scratch), sb), "vrenb200_radix_sort_keys")
+    return keys
+
+
+def radix_sort_pairs(keys, vals, n: int | None = None, scratch=None):
+    lib = load()
+    n = keys.numel() if n is None else n
+    sb = lib.vrenb200_radix_sort_scratch_bytes(n, 1)
+    if scratch is None:
+        scratch = _scratch(sb)
+    check(lib.vrenb200_radix_sort_pairs(_stream(), _ptr(keys), _ptr(vals), n, _ptr(scratch), sb), "vrenb200_radix_sort_pairs")
+    return keys, vals
