@@ -80,7 +80,72 @@ def load() -> C.CDLL:
     return lib
 
 
-_LATE: list = []
+class Camera(C.Structure):
+    _fields_ = [("fov_y", C.c_float), ("aspect_ratio", C.c_float), ("near_plane", C.c_float), ("far_plane", C.c_float)]
+
+
+_LATE: list = [
+    ("oracle_construct_point_light_bvh", None, (f32p, f32p, C.c_uint32, f32p, f32p, voidp, u32p)),
+    ("oracle_find_unique_clusters", C.c_uint32, (f32p, voidp, C.c_uint32, C.c_uint32, C.POINTER(Camera), u32p, u32p)),
+    ("oracle_assign_lights", C.c_uint64,
+     (C.c_uint32, C.c_uint32, C.POINTER(Camera), u32p, C.c_uint32, C.c_uint32, voidp, C.c_uint32, C.c_uint32, u32p, f32p,
+      u32p, C.c_uint64, u32p, u32p)),
+]
+
+
+def default_camera(width: int, height: int, fov_deg: float = 45.0, near: float = 0.01, far: float = 1000.0) -> Camera:
+    """vren::camera defaults (camera.hpp:20-23) with the screen's aspect ratio"""
+    import math
+
+    return Camera(np.float32(math.radians(fov_deg)), np.float32(width / height), np.float32(near), np.float32(far))
+
+
+def construct_point_light_bvh(positions: np.ndarray, lights: np.ndarray, view: np.ndarray):
+    """positions [L,4] f32, lights [L,4] f32 (rgb, intensity), view: 16 floats column-major.
+    Returns (view_pos [L,4], nodes BVH_NODE[len], sorted_pairs [L,2])"""
+    lib = load()
+    L = positions.shape[0]
+    positions = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1)
+    lights = np.ascontiguousarray(lights, dtype=np.float32).reshape(-1)
+    view = np.ascontiguousarray(view, dtype=np.float32).reshape(-1)
+    view_pos = np.zeros(L * 4, np.float32)
+    nodes = np.zeros(int(lib.oracle_calc_bvh_buffer_length(L)), dtype=BVH_NODE)
+    pairs = np.zeros(L * 2, np.uint32)
+    lib.oracle_construct_point_light_bvh(positions, lights, L, view, view_pos, nodes.ctypes.data, pairs)
+    return view_pos.reshape(L, 4), nodes, pairs.reshape(L, 2)
+
+
+def find_unique_clusters(depth: np.ndarray, normals, cam: Camera):
+    """depth [H,W] f32, normals [H,W,4] float16 or None -> (keys[count], cluster_ref [H,W])"""
+    lib = load()
+    H, W = depth.shape
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    tiles = ((W + 31) // 32) * ((H + 31) // 32)
+    keys = np.zeros(tiles * 1024, np.uint32)
+    ref = np.zeros(H * W, np.uint32)
+    nptr = None
+    if normals is not None:
+        normals = np.ascontiguousarray(normals, dtype=np.float16)
+        nptr = normals.ctypes.data
+    count = lib.oracle_find_unique_clusters(depth.reshape(-1), nptr, W, H, C.byref(cam), keys, ref)
+    return keys[:count].copy(), ref.reshape(H, W)
+
+
+def assign_lights(W, H, cam: Camera, keys: np.ndarray, max_keys: int, nodes: np.ndarray, light_count: int,
+                  sorted_pairs: np.ndarray, view_pos: np.ndarray, max_assigned: int):
+    """-> (counts[max_keys], offsets[max_keys], indices[max_assigned], total)"""
+    lib = load()
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    counts = np.zeros(max_keys, np.uint32)
+    offsets = np.zeros(max_keys, np.uint32)
+    indices = np.zeros(max_assigned, np.uint32)
+    nodes = np.ascontiguousarray(nodes)
+    root = int(lib.oracle_calc_bvh_root_index(light_count))
+    total = lib.oracle_assign_lights(W, H, C.byref(cam), keys, keys.size, max_keys, nodes.ctypes.data, root, light_count,
+                                     np.ascontiguousarray(sorted_pairs, dtype=np.uint32).reshape(-1),
+                                     np.ascontiguousarray(view_pos, dtype=np.float32).reshape(-1),
+                                     indices, max_assigned, counts, offsets)
+    return counts, offsets, indices, int(total)
 
 
 def load_ref():

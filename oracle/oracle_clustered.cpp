@@ -1,0 +1,385 @@
+// TEST INFRASTRUCTURE — CPU restatement ("oracle") of vren's light-clustering pass (a6, a7, a8).
+//
+// PARITY UNPINNED UPSTREAM: the reference has no test, golden vector or CPU implementation for clustered shading
+// (SURVEY 4, 8c), and it cannot be built here (no Vulkan/glslc).  This file restates the shaders line by line and
+// fixes the choices the reference leaves open (SURVEY 8c i-vii); each is marked CANONICAL below.
+//
+// fp32 contract (CANONICAL vii): every operation is a separately rounded IEEE fp32 op in GLSL source order (this
+// file is compiled with -ffp-contract=off); mat4*vec4 = ((m0*x + m1*y) + (m2*z + m3*w)); normalize(v) = v / sqrt(dot);
+// dot(v,v) = (x*x + y*y) + z*z.  Transcendentals (tan, pow, log) are evaluated once on the host:
+//   a        = 1.0f + (2.0f * tanf(fov_y / 2.0f)) / (float) Ty                (find_unique_clusters.comp:65)
+//   slice k  = floor(log(z / near) / log(a)) evaluated in DOUBLE from the fp32 z, near, a; negative -> 0
+//   near_k   = near * powf(a, (float) k)                                       (clustered_shading.glsl:97-98)
+//   inverse(projection) in closed form: i00 = 1/m00, i11 = 1/m11, row3 = (0, 0, 1/m32, -m22/m32), row2 = (0,0,0,1)
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <vector>
+
+extern "C" {
+void oracle_reduce(int dtype, int op, const void* in, uint32_t n, void* out, uint32_t blocks);
+void oracle_bucket_sort(const uint32_t* in_pairs, uint32_t n, uint32_t* out_pairs, uint32_t* counters);
+uint32_t oracle_calc_bvh_padded_leaf_count(uint32_t leaf_count);
+uint32_t oracle_calc_bvh_buffer_length(uint32_t leaf_count);
+uint32_t oracle_calc_bvh_level_count(uint32_t leaf_count);
+uint32_t oracle_round_to_next_power_of_2(uint32_t v);
+void oracle_build_bvh(void* nodes, uint32_t padded_leaf_count);
+}
+
+namespace {
+
+struct bvh_node { float mn[3]; uint32_t next; float mx[3]; uint32_t pad; };
+const uint32_t LEAF = 0xFFFFFFFFu, INVALID = 0xFFFFFFFEu;
+
+struct camera_t { float fov_y, aspect, near_plane, far_plane; };
+
+// camera.cpp:40-50 (glm column-major: m[col][row])
+struct proj_t
+{
+    float m00, m11, m22, m32;      // m23 = 1
+    float i00, i11, iB, nAB;       // closed-form inverse entries (CANONICAL vii)
+    float tan_half;
+};
+
+proj_t make_projection(const camera_t& c)
+{
+    proj_t p;
+    p.tan_half = tanf(c.fov_y / 2.0f);
+    p.m00 = 1.0f / (p.tan_half * c.aspect);
+    p.m11 = 1.0f / p.tan_half;
+    p.m22 = c.far_plane / (c.far_plane - c.near_plane);
+    p.m32 = -(c.far_plane * c.near_plane) / (c.far_plane - c.near_plane);
+    p.i00 = 1.0f / p.m00;
+    p.i11 = 1.0f / p.m11;
+    p.iB = 1.0f / p.m32;
+    p.nAB = (-p.m22) / p.m32;
+    return p;
+}
+
+float slice_base(const proj_t& p, uint32_t tiles_y)
+{
+    return 1.0f + (2.0f * p.tan_half) / (float) tiles_y;
+}
+
+uint32_t slice_of(float z, float near_plane, float a)
+{
+    const double k = std::floor(std::log((double) z / (double) near_plane) / std::log((double) a));
+    if (!(k >= 0.0)) return 0u;                 // CANONICAL: uint(negative or NaN) -> 0
+    if (k > 4294967295.0) return 0xFFFFFFFFu;
+    return (uint32_t) k;
+}
+
+float half_to_float(uint16_t h)
+{
+    const uint32_t s = (h >> 15) & 1u, e = (h >> 10) & 31u, m = h & 1023u;
+    uint32_t u;
+    if (e == 0)
+    {
+        if (m == 0) u = s << 31;
+        else
+        {
+            int ee = -1;
+            uint32_t mm = m;
+            do { ee++; mm <<= 1; } while ((mm & 1024u) == 0);
+            u = (s << 31) | ((uint32_t) (127 - 15 - ee) << 23) | ((mm & 1023u) << 13);
+        }
+    }
+    else if (e == 31) u = (s << 31) | 0x7F800000u | (m << 13);
+    else u = (s << 31) | ((e + 112u) << 23) | (m << 13);
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+// clustered_shading.glsl:7-43
+uint32_t discretize_normal(float nx, float ny, float nz)
+{
+    if (nx == 0.0f && ny == 0.0f && nz == 0.0f) return 0xFFFFFFFFu;
+    const float n[3] = {nx, ny, nz};
+    float min_t = 1e35f;
+    uint32_t axis = 0, face_idx = 0; // CANONICAL: defined start values (the shader leaves them uninitialised)
+    for (uint32_t i = 0; i < 3; i++)
+    {
+        const float sg = n[i] > 0.0f ? 1.0f : (n[i] < 0.0f ? -1.0f : 0.0f);
+        const float t = sg / n[i];
+        if (t < min_t)
+        {
+            min_t = t;
+            axis = i;
+            face_idx = (n[i] > 0.0f ? 1u : 0u) * 3u + i;
+        }
+    }
+    const float p[3] = {n[0] * min_t, n[1] * min_t, n[2] * min_t};
+    const float uvx = p[(axis + 1) % 3], uvy = p[(axis + 2) % 3];
+    const float fx = std::floor((uvx + 1.0f) / 2.0f * 3.0f), fy = std::floor((uvy + 1.0f) / 2.0f * 3.0f);
+    const uint32_t dx = fx >= 0.0f ? (uint32_t) fx : 0u, dy = fy >= 0.0f ? (uint32_t) fy : 0u;
+    return (face_idx * 9u + dx * 3u + dy) & 0x3Fu;
+}
+
+} // namespace
+
+extern "C" {
+
+// ---- a6 ------------------------------------------------------------------------------------------------------------
+// positions vec4[L], lights {vec3 color; float intensity}[L], view = column-major mat4.
+// Outputs: view_pos vec4[L], nodes[calc_bvh_buffer_length(L)], sorted uvec2[L].
+void oracle_construct_point_light_bvh(const float* positions, const float* lights, uint32_t L, const float* view,
+                                      float* view_pos, bvh_node* nodes, uint32_t* sorted_pairs)
+{
+    // K9: point_light_position_to_view_space.comp:30
+    for (uint32_t i = 0; i < L; i++)
+    {
+        const float x = positions[4 * i], y = positions[4 * i + 1], z = positions[4 * i + 2];
+        for (int c = 0; c < 4; c++)
+        {
+            const float a = view[0 + c] * x + view[4 + c] * y;
+            const float b = view[8 + c] * z + view[12 + c] * 1.0f;
+            view_pos[4 * i + c] = a + b;
+        }
+    }
+    // clustered_shading.cpp:141-178: reduce<vec4,max>, reduce<vec4,min> over next_pow2(L) slots, result = last slot
+    const uint32_t P = oracle_round_to_next_power_of_2(L);
+    std::vector<float> tree((size_t) P * 4);
+    float mx[4], mn[4];
+    oracle_reduce(1, 2, view_pos, L, tree.data(), 1);
+    std::memcpy(mx, &tree[(size_t) (P - 1) * 4], 16);
+    oracle_reduce(1, 1, view_pos, L, tree.data(), 1);
+    std::memcpy(mn, &tree[(size_t) (P - 1) * 4], 16);
+    // K10: discretize_point_light_positions.comp:26-43
+    std::vector<uint32_t> pairs((size_t) L * 2);
+    for (uint32_t i = 0; i < L; i++)
+    {
+        uint32_t q[3];
+        for (int c = 0; c < 3; c++)
+        {
+            const float t = (view_pos[4 * i + c] - mn[c]) / (mx[c] - mn[c]) * 32.0f;
+            const float f = std::floor(t);
+            q[c] = f >= 0.0f ? (uint32_t) f : 0u; // CANONICAL v: NaN (max == min) -> bin 0
+        }
+        uint32_t code = 0;
+        for (uint32_t b = 0; b < 5; b++)
+        {
+            code |= ((q[0] >> b) & 1u) << (b * 3);
+            code |= ((q[1] >> b) & 1u) << (b * 3 + 1);
+            code |= ((q[2] >> b) & 1u) << (b * 3 + 2);
+        }
+        pairs[2 * (size_t) i] = code;
+        pairs[2 * (size_t) i + 1] = i;
+    }
+    // bucket sort (CANONICAL i: ties keep input order)
+    std::vector<uint32_t> counters(65536);
+    oracle_bucket_sort(pairs.data(), L, sorted_pairs, counters.data());
+    // K11: init_light_array_bvh.comp:42-65 (CANONICAL iii: invalid leaves get the empty box, _pad = 0)
+    const uint32_t padded = oracle_calc_bvh_padded_leaf_count(L);
+    for (uint32_t i = 0; i < padded; i++)
+    {
+        bvh_node& nd = nodes[i];
+        nd.pad = 0;
+        if (i < L)
+        {
+            const uint32_t l = sorted_pairs[2 * (size_t) i + 1];
+            const float r = lights[4 * (size_t) l + 3];
+            for (int c = 0; c < 3; c++)
+            {
+                nd.mn[c] = view_pos[4 * (size_t) l + c] - r;
+                nd.mx[c] = view_pos[4 * (size_t) l + c] + r;
+            }
+            nd.next = LEAF;
+        }
+        else
+        {
+            for (int c = 0; c < 3; c++) { nd.mn[c] = 1e35f; nd.mx[c] = -1e35f; }
+            nd.next = INVALID;
+        }
+    }
+    oracle_build_bvh(nodes, padded);
+}
+
+// ---- a7 ------------------------------------------------------------------------------------------------------------
+// find_unique_clusters.comp:46-121.  depth float[W*H]; normals = RGBA16F as uint16[W*H*4] or NULL (all-zero).
+// keys_out must hold Tx*Ty*1024 entries at worst; cluster_ref uint[W*H].
+// CANONICAL ii: tiles visited in tile-major order (j*Tx + i), ascending key inside a tile.
+// CANONICAL vi: pixels of partial tiles wrap (sampler REPEAT), nearest texel.
+// Returns the number of unique cluster keys (dispatch_params.x).
+uint32_t oracle_find_unique_clusters(const float* depth, const uint16_t* normals, uint32_t W, uint32_t H,
+                                     const camera_t* cam, uint32_t* keys_out, uint32_t* cluster_ref)
+{
+    const proj_t pr = make_projection(*cam);
+    const uint32_t Tx = (W + 31) / 32, Ty = (H + 31) / 32;
+    const float a = slice_base(pr, Ty);
+    uint32_t count = 0;
+    std::vector<uint32_t> keys(1024);
+    for (uint32_t j = 0; j < Ty; j++)
+        for (uint32_t i = 0; i < Tx; i++)
+        {
+            for (uint32_t t = 0; t < 1024; t++)
+            {
+                const uint32_t x = ((i << 5) + (t & 31)) % W, y = ((j << 5) + (t >> 5)) % H;
+                const float d = depth[(size_t) y * W + x];
+                // frag_pos = inverse(P) * (., ., d, 1); frag_pos /= frag_pos.w -> z = 1 / w'
+                const float w = d * pr.iB + 1.0f * pr.nAB;
+                const float z = 1.0f / w;
+                const uint32_t k = slice_of(z, cam->near_plane, a);
+                uint32_t nb = 0xFFFFFFFFu;
+                if (normals)
+                {
+                    const uint16_t* h = normals + ((size_t) y * W + x) * 4;
+                    nb = discretize_normal(half_to_float(h[0]), half_to_float(h[1]), half_to_float(h[2]));
+                }
+                keys[t] = (i & 0xFFu) | ((j & 0xFFu) << 8) | ((k & 0x3FFu) << 16) | (nb << 26);
+            }
+            std::vector<uint32_t> uniq(keys);
+            std::sort(uniq.begin(), uniq.end());
+            uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+            for (uint32_t t = 0; t < 1024; t++)
+            {
+                const uint32_t x = (i << 5) + (t & 31), y = (j << 5) + (t >> 5);
+                if (x < W && y < H)
+                    cluster_ref[(size_t) y * W + x] =
+                        count + (uint32_t) (std::lower_bound(uniq.begin(), uniq.end(), keys[t]) - uniq.begin());
+            }
+            for (uint32_t u : uniq) keys_out[count++] = u;
+        }
+    return count;
+}
+
+// ---- a8 ------------------------------------------------------------------------------------------------------------
+// clustered_shading.glsl:72-110 — cluster "min/max" corners exactly as written (NOT component-wise ordered)
+static void cluster_aabb(uint32_t ci, uint32_t cj, uint32_t ck, uint32_t Tx, uint32_t Ty, const camera_t& cam,
+                         const proj_t& pr, float a, float* cmin, float* cmax)
+{
+    const float tx = (float) Tx, ty = (float) Ty;
+    float p0x = (float) ci / tx, p0y = (float) cj / ty;
+    p0x = p0x * 2.0f - 1.0f;
+    p0y = (1.0f - p0y) * 2.0f - 1.0f;
+    float p1x = (float) (ci + 1) / tx, p1y = (float) (cj + 1) / ty;
+    p1x = p1x * 2.0f - 1.0f;
+    p1y = (1.0f - p1y) * 2.0f - 1.0f;
+    // inverse(proj) * (px, py, 0, 1): x' = i00*px, y' = i11*py, z' = 1, w' = (iB*0 + nAB*1)
+    const float w = 0.0f * pr.iB + 1.0f * pr.nAB;
+    const float v0[3] = {(pr.i00 * p0x) / w, (pr.i11 * p0y) / w, 1.0f / w};
+    const float v1[3] = {(pr.i00 * p1x) / w, (pr.i11 * p1y) / w, 1.0f / w};
+    const float near_k = cam.near_plane * powf(a, (float) ck);
+    const float far_k = near_k * a;
+    const float l0 = std::sqrt((v0[0] * v0[0] + v0[1] * v0[1]) + v0[2] * v0[2]);
+    const float l1 = std::sqrt((v1[0] * v1[0] + v1[1] * v1[1]) + v1[2] * v1[2]);
+    const float d0[3] = {v0[0] / l0, v0[1] / l0, v0[2] / l0};
+    const float d1[3] = {v1[0] / l1, v1[1] / l1, v1[2] / l1};
+    const float s0 = near_k / d0[2], s1 = far_k / d1[2];
+    for (int c = 0; c < 3; c++) { cmin[c] = s0 * d0[c]; cmax[c] = s1 * d1[c]; }
+}
+
+// assign_lights.comp:121-241 + clustered_shading.cpp:473-690.
+// counts/offsets: uint[max_keys] (offsets = exclusive scan of counts over all max_keys slots);
+// indices: hits in traversal order, within a leaf group in DESCENDING lane order (:229-232).
+// CANONICAL iii/iv: INVALID nodes and padding leaves never overlap.
+// Returns the total number of assigned lights (indices beyond max_assigned are counted but not written).
+uint64_t oracle_assign_lights(uint32_t W, uint32_t H, const camera_t* cam, const uint32_t* cluster_keys, uint32_t key_count,
+                              uint32_t max_keys, const bvh_node* bvh, uint32_t bvh_root_index, uint32_t light_count,
+                              const uint32_t* sorted_pairs, const float* view_pos,
+                              uint32_t* indices, uint64_t max_assigned, uint32_t* counts, uint32_t* offsets)
+{
+    std::fill(counts, counts + max_keys, 0u);                     // vkCmdFillBuffer, clustered_shading.cpp:492
+    if (light_count == 0) return 0;                                // :494-496 nothing else is touched
+    const proj_t pr = make_projection(*cam);
+    const uint32_t Tx = (W + 31) / 32, Ty = (H + 31) / 32;
+    const float a = 2.0f * pr.tan_half / (float) Ty + 1.0f;        // clustered_shading.glsl:96
+    const uint32_t levels = oracle_calc_bvh_level_count(light_count);
+    std::vector<std::vector<uint32_t>> lists(key_count);
+    for (uint32_t c = 0; c < key_count; c++)
+    {
+        const uint32_t key = cluster_keys[c];
+        float cmin[3], cmax[3];
+        cluster_aabb(key & 0xFFu, (key >> 8) & 0xFFu, (key >> 16) & 0x3FFu, Tx, Ty, *cam, pr, a, cmin, cmax);
+        // the state machine of assign_lights.comp:133-239 is a depth-first walk, lowest set bit first
+        uint32_t overlaps[8] = {0};
+        auto node_address = [&](uint32_t level) {
+            // get_node_address, assign_lights.comp:108-119
+            int64_t sum = 0, p32 = 1;
+            for (uint32_t e = 0; e <= level + 1; e++) { sum += p32; p32 *= 32; }
+            int64_t addr = (int64_t) bvh_root_index - (sum - 1);
+            for (uint32_t i = 0; i < level; i++)
+            {
+                int64_t w = 1;
+                for (uint32_t e = 0; e < level - i; e++) w *= 32;
+                addr += w * (int64_t) __builtin_ctz(overlaps[i]);
+            }
+            return (uint32_t) addr;
+        };
+        uint32_t level = 0;
+        int state = 2;
+        std::vector<uint32_t>& out = lists[c];
+        while (true)
+        {
+            if (state == 0)
+            {
+                overlaps[level] &= ~(1u << __builtin_ctz(overlaps[level]));
+                if (overlaps[level] == 0) state = 1;
+                else { level++; state = 2; }
+            }
+            else if (state == 1)
+            {
+                if (level > 0) { level--; state = 0; }
+                else break;
+            }
+            else
+            {
+                const uint32_t addr = node_address(level);
+                if (level < levels - 1)
+                {
+                    uint32_t mask = 0;
+                    for (uint32_t t = 0; t < 32; t++)
+                    {
+                        const bvh_node& n = bvh[addr + t];
+                        if (n.next == INVALID) continue;
+                        const bool ov = cmax[0] >= n.mn[0] && cmin[0] <= n.mx[0] && cmax[1] >= n.mn[1] && cmin[1] <= n.mx[1] &&
+                                        cmax[2] >= n.mn[2] && cmin[2] <= n.mx[2];
+                        if (ov) mask |= 1u << t;
+                    }
+                    overlaps[level] = mask;
+                    if (mask == 0) state = 1;
+                    else level++;
+                }
+                else
+                {
+                    uint32_t mask = 0;
+                    for (uint32_t t = 0; t < 32; t++)
+                    {
+                        if (addr + t >= light_count) continue;
+                        const bvh_node& n = bvh[addr + t];
+                        const uint32_t l = sorted_pairs[2 * (size_t) (addr + t) + 1];
+                        const float* o = view_pos + 4 * (size_t) l;
+                        const float r = (n.mx[0] - n.mn[0]) / 2.0f;
+                        float q[3];
+                        for (int k = 0; k < 3; k++)
+                        {
+                            const float m = cmax[k] < o[k] ? cmax[k] : o[k];      // min(o, cmax)
+                            q[k] = cmin[k] < m ? m : cmin[k];                     // max(cmin, .)
+                            q[k] = q[k] - o[k];
+                        }
+                        const float d = std::sqrt((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]);
+                        if (d < r) mask |= 1u << t;
+                    }
+                    for (int t = 31; t >= 0; t--)
+                        if (mask & (1u << t)) out.push_back(sorted_pairs[2 * (size_t) (addr + t) + 1]);
+                    state = 1;
+                }
+            }
+        }
+        counts[c] = (uint32_t) out.size();
+    }
+    uint32_t acc = 0;
+    for (uint32_t c = 0; c < max_keys; c++) { offsets[c] = acc; acc += counts[c]; }  // blelloch_scan over max_keys
+    uint64_t total = 0;
+    for (uint32_t c = 0; c < key_count; c++)
+    {
+        for (size_t r = 0; r < lists[c].size(); r++)
+            if ((uint64_t) offsets[c] + r < max_assigned) indices[offsets[c] + r] = lists[c][r];
+        total += lists[c].size();
+    }
+    return total;
+}
+
+} // extern "C"

@@ -339,6 +339,13 @@ void oracle_bucket_sort(const uint32_t* in_pairs, uint32_t n, uint32_t* out_pair
 struct bvh_node { float mn[3]; uint32_t next; float mx[3]; uint32_t pad; };
 static const uint32_t LEAF = 0xFFFFFFFFu, INVALID = 0xFFFFFFFEu;
 
+static uint32_t ford(float f)
+{
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
 // build_bvh.cpp:69-94 + build_bvh.comp:32-55. Canonical choices where the reference is undefined
 // (SURVEY 8c-iii): an all-invalid parent gets min=+1e35, max=-1e35 (never overlaps), _pad = 0.
 void oracle_build_bvh(bvh_node* nodes, uint32_t padded_leaf_count)
@@ -360,8 +367,9 @@ void oracle_build_bvh(bvh_node* nodes, uint32_t padded_leaf_count)
                 any = true;
                 for (int c = 0; c < 3; c++)
                 {
-                    p.mn[c] = ch.mn[c] < p.mn[c] ? ch.mn[c] : p.mn[c];
-                    p.mx[c] = p.mx[c] < ch.mx[c] ? ch.mx[c] : p.mx[c];
+                    // total order with -0 < +0 so that the result does not depend on the visiting order
+                    p.mn[c] = ford(ch.mn[c]) < ford(p.mn[c]) ? ch.mn[c] : p.mn[c];
+                    p.mx[c] = ford(p.mx[c]) < ford(ch.mx[c]) ? ch.mx[c] : p.mx[c];
                 }
             }
             p.next = any ? src + 32 * j : INVALID;

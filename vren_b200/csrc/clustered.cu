@@ -1,0 +1,675 @@
+// a7 — clustered_shading::find_unique_cluster_list (reference: vren/vren/pipeline/clustered_shading.cpp:363-448,
+//      shaders/clustered_shading/find_unique_clusters.comp:46-121, clustered_shading.glsl:7-43)
+// a8 — clustered_shading::assign_lights (reference: clustered_shading.cpp:473-690, assign_lights.comp:77-241,
+//      clustered_shading.glsl:58-110)
+//
+// a7, reference: one 32x32 workgroup per tile, 1024-wide bitonic sort (55 barrier stages) + workgroup scan + one
+// global atomicAdd per tile -> list order depends on atomic arrival order.
+// a7, here: one CTA per tile; the 32x32 depth (and RGBA16F normal) tile is staged with a 2-D TMA tensor copy
+// (cp.async.bulk.tensor.2d + mbarrier).  All keys of a tile share (i, j), so the 16 remaining key bits index a
+// 65536-bit shared-memory bitmap: set bit = key present, rank = popcount prefix -> sorted unique list without a sort.
+// Tile bases come from a decoupled look-back over tiles in tile-major order, which makes the list order
+// deterministic (the canonical order of the oracle).  One launch, 4 B/px read (+8 B/px normals) + 4 B/px written.
+//
+// a8: one warp per unique cluster walks the 32-ary light BVH with a per-level overlap bitmask (lane t tests child
+// t, lowest set bit first), leaf level = sphere vs box.  Count pass -> exclusive scan -> write pass, as the
+// reference, but with persistent warps and the single-pass scan; light order inside a list follows
+// assign_lights.comp:229-232 (descending lane inside a leaf group).
+//
+// fp32 contract: every op is an explicitly rounded _rn intrinsic in GLSL source order; tan/pow/log are evaluated
+// on the host once per camera (tables below) with the formulas stated in oracle/oracle_clustered.cpp.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vrenb200 {
+
+namespace {
+
+constexpr uint32_t kInvalid = VRENB200_BVH_INVALID_NODE;
+constexpr int kMaxBvhLevels = 6;
+
+// ---- host-side camera constants (camera.cpp:40-50) -----------------------------------------------------------
+struct proj_consts
+{
+    float i00, i11, iB, nAB;   // closed-form inverse(projection) entries
+    float tan_half;
+};
+
+proj_consts make_proj(const vrenb200_camera& c)
+{
+    proj_consts p;
+    p.tan_half = tanf(c.fov_y / 2.0f);
+    const float m00 = 1.0f / (p.tan_half * c.aspect_ratio);
+    const float m11 = 1.0f / p.tan_half;
+    const float m22 = c.far_plane / (c.far_plane - c.near_plane);
+    const float m32 = -(c.far_plane * c.near_plane) / (c.far_plane - c.near_plane);
+    p.i00 = 1.0f / m00;
+    p.i11 = 1.0f / m11;
+    p.iB = 1.0f / m32;
+    p.nAB = (-m22) / m32;
+    return p;
+}
+
+// slice index of a view-space depth: floor(log(z/near)/log(a)) in double (find_unique_clusters.comp:65)
+uint32_t slice_of(float z, float near_plane, float a)
+{
+    const double k = std::floor(std::log((double) z / (double) near_plane) / std::log((double) a));
+    if (!(k >= 0.0)) return 0u;
+    if (k > 4294967295.0) return 0xFFFFFFFFu;
+    return (uint32_t) k;
+}
+
+// thresholds[k] = smallest positive float z whose slice is >= k (k >= 1); the device finds the slice by comparing
+// against this table, so it agrees with the double-precision formula for every float z by construction.
+constexpr uint32_t kMaxSlices = 16384;
+
+struct slice_table
+{
+    float near_plane = 0, a = 0;
+    std::vector<float> thresholds; // [0] = 0 (unused), [1..count)
+};
+
+const slice_table& get_slice_table(float near_plane, float a)
+{
+    static thread_local slice_table tab;
+    if (tab.near_plane == near_plane && tab.a == a && !tab.thresholds.empty()) return tab;
+    tab.near_plane = near_plane;
+    tab.a = a;
+    tab.thresholds.clear();
+    tab.thresholds.push_back(0.0f);
+    const uint32_t kmax = std::min<uint32_t>(slice_of(3.4028234e38f, near_plane, a), kMaxSlices - 2);
+    for (uint32_t k = 1; k <= kmax; k++)
+    {
+        float c = (float) ((double) near_plane * std::pow((double) a, (double) k));
+        while (slice_of(c, near_plane, a) < k) c = std::nextafterf(c, INFINITY);
+        while (slice_of(std::nextafterf(c, 0.0f), near_plane, a) >= k) c = std::nextafterf(c, 0.0f);
+        tab.thresholds.push_back(c);
+    }
+    return tab;
+}
+
+// ---- mbarrier / TMA wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int x, int y, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- a7 kernel ----------------------------------------------------------------------------------------------------
+struct cluster_key_params
+{
+    uint32_t width, height, tiles_x, tiles_y;
+    float iB, nAB;              // w' = d*iB + nAB ; z = 1/w'
+    float inv_near, inv_log2a;  // first guess of the slice
+    uint32_t table_len;
+    uint32_t max_keys;
+    int use_tma, has_normals;
+};
+
+struct cluster_scan_state
+{
+    uint32_t ticket;
+    uint32_t _pad[63];
+    uint64_t status[1]; // [tiles] flag<<32 | value
+};
+
+constexpr uint64_t kFlagAggregate = 1ull << 32;
+constexpr uint64_t kFlagInclusive = 2ull << 32;
+
+// clustered_shading.glsl:7-43
+__device__ __forceinline__ uint32_t discretize_normal(float nx, float ny, float nz)
+{
+    if (nx == 0.0f && ny == 0.0f && nz == 0.0f) return 0xFFFFFFFFu;
+    const float n[3] = {nx, ny, nz};
+    float min_t = 1e35f;
+    uint32_t axis = 0, face_idx = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 3; i++)
+    {
+        const float sg = n[i] > 0.0f ? 1.0f : (n[i] < 0.0f ? -1.0f : 0.0f);
+        const float t = __fdiv_rn(sg, n[i]);
+        if (t < min_t)
+        {
+            min_t = t;
+            axis = i;
+            face_idx = (n[i] > 0.0f ? 1u : 0u) * 3u + i;
+        }
+    }
+    const float p0 = __fmul_rn(n[0], min_t), p1 = __fmul_rn(n[1], min_t), p2 = __fmul_rn(n[2], min_t);
+    const float uvx = axis == 0 ? p1 : (axis == 1 ? p2 : p0);
+    const float uvy = axis == 0 ? p2 : (axis == 1 ? p0 : p1);
+    const float fx = floorf(__fmul_rn(__fdiv_rn(__fadd_rn(uvx, 1.0f), 2.0f), 3.0f));
+    const float fy = floorf(__fmul_rn(__fdiv_rn(__fadd_rn(uvy, 1.0f), 2.0f), 3.0f));
+    const uint32_t dx = fx >= 0.0f ? (uint32_t) fx : 0u, dy = fy >= 0.0f ? (uint32_t) fy : 0u;
+    return (face_idx * 9u + dx * 3u + dy) & 0x3Fu;
+}
+
+__global__ void __launch_bounds__(1024)
+find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const __grid_constant__ CUtensorMap normal_map,
+                            const float* __restrict__ depth, const uint2* __restrict__ normals,
+                            const float* __restrict__ thresholds, cluster_key_params prm,
+                            cluster_scan_state* state, uint32_t* keys_out, uint32_t* dispatch_params, uint32_t* cluster_ref)
+{
+    __shared__ alignas(128) float s_depth[32 * 32];
+    __shared__ alignas(128) uint2 s_normal[32 * 32];
+    __shared__ uint32_t s_bitmap[2048];
+    __shared__ uint32_t s_prefix[2048];
+    __shared__ uint32_t s_warp[32];
+    __shared__ alignas(8) uint64_t s_bar;
+    __shared__ uint32_t s_tile, s_base;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0)
+    {
+        s_tile = atomicAdd(&state->ticket, 1u);
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+    }
+    s_bitmap[tid] = 0;
+    s_bitmap[tid + 1024] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t ti = tile % prm.tiles_x, tj = tile / prm.tiles_x;   // canonical tile-major order
+    const uint32_t x = (ti << 5) + lane, y = (tj << 5) + warp;         // local invocation (lane, warp)
+    const bool interior = (ti << 5) + 32 <= prm.width && (tj << 5) + 32 <= prm.height;
+
+    float d;
+    uint2 nraw = make_uint2(0u, 0u);
+    if (prm.use_tma && interior)
+    {
+        if (tid == 0)
+        {
+            mbar_arrive_expect_tx(&s_bar, 32 * 32 * 4 + (prm.has_normals ? 32 * 32 * 8 : 0));
+            tma_load_2d(s_depth, &depth_map, (int) (ti << 5), (int) (tj << 5), &s_bar);
+            if (prm.has_normals) tma_load_2d(s_normal, &normal_map, (int) (ti << 5), (int) (tj << 5), &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+        d = s_depth[tid];
+        if (prm.has_normals) nraw = s_normal[tid];
+    }
+    else
+    {
+        // partial tiles wrap like the reference's REPEAT sampler (gbuffer.cpp:28-34)
+        const uint32_t sx = x % prm.width, sy = y % prm.height;
+        d = depth[(size_t) sy * prm.width + sx];
+        if (prm.has_normals) nraw = normals[(size_t) sy * prm.width + sx];
+    }
+
+    // view-space depth and slice (find_unique_clusters.comp:48-65)
+    const float w = __fadd_rn(__fmul_rn(d, prm.iB), __fmul_rn(1.0f, prm.nAB));
+    const float z = __fdiv_rn(1.0f, w);
+    uint32_t k = 0;
+    if (z > 0.0f)
+    {
+        const float zc = fminf(z, 3.4028234e38f);
+        int g = (int) (__log2f(zc * prm.inv_near) * prm.inv_log2a);
+        g = max(0, min(g, (int) prm.table_len - 1));
+        while (g > 0 && zc < thresholds[g]) g--;
+        while (g + 1 < (int) prm.table_len && zc >= thresholds[g + 1]) g++;
+        k = (uint32_t) g;
+    }
+    uint32_t nb = 0xFFFFFFFFu;
+    if (prm.has_normals)
+    {
+        const __half2 h01 = *reinterpret_cast<const __half2*>(&nraw.x);
+        const __half2 h23 = *reinterpret_cast<const __half2*>(&nraw.y);
+        nb = discretize_normal(__low2float(h01), __high2float(h01), __low2float(h23));
+    }
+    const uint32_t sub = ((nb & 0x3Fu) << 10) | (k & 0x3FFu);   // key bits 16..31
+    atomicOr(&s_bitmap[sub >> 5], 1u << (sub & 31));
+    __syncthreads();
+
+    // popcount prefix over the 2048 bitmap words: thread t owns words 2t, 2t+1
+    const uint32_t w0 = s_bitmap[2 * tid], w1 = s_bitmap[2 * tid + 1];
+    const uint32_t c0 = __popc(w0), c01 = c0 + __popc(w1);
+    uint32_t inc = c01;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(kFullMask, inc, s);
+        if (lane >= (unsigned) s) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        uint32_t v = s_warp[lane];
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(kFullMask, v, s);
+            if (lane >= (unsigned) s) v += t;
+        }
+        s_warp[lane] = v; // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t excl = inc - c01 + (warp > 0 ? s_warp[warp - 1] : 0u);
+    s_prefix[2 * tid] = excl;
+    s_prefix[2 * tid + 1] = excl + c0;
+    const uint32_t unique = s_warp[31];
+
+    // decoupled look-back across tiles (tile-major order)
+    if (warp == 0)
+    {
+        uint64_t* status = state->status;
+        if (lane == 0) st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | unique);
+        uint32_t exclusive = 0;
+        if (tile > 0)
+        {
+            int64_t base = (int64_t) tile - 1;
+            while (true)
+            {
+                const int64_t t = base - lane;
+                uint64_t s = kFlagInclusive;
+                if (t >= 0)
+                {
+                    do { s = ld_relaxed_u64(&status[t]); } while ((s >> 32) == 0);
+                }
+                const unsigned incl = __ballot_sync(kFullMask, (s >> 32) == 2);
+                uint32_t val = (uint32_t) s;
+                if (incl != 0 && lane > (unsigned) (__ffs(incl) - 1)) val = 0;
+                exclusive += __reduce_add_sync(kFullMask, val);
+                if (incl != 0) break;
+                base -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (exclusive + unique));
+        }
+        if (lane == 0)
+        {
+            s_base = exclusive;
+            if (exclusive + unique > prm.max_keys) atomicOr(&dispatch_params[3], 1u);   // overflow, detected not silent
+            if (tile == prm.tiles_x * prm.tiles_y - 1)
+            {
+                // indirect-dispatch block of the reference: {count, 1, 1, _} (clustered_shading.cpp:386-394)
+                dispatch_params[0] = min(exclusive + unique, prm.max_keys);
+                dispatch_params[1] = 1;
+                dispatch_params[2] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+
+    // per-pixel cluster reference (imageStore, find_unique_clusters.comp:113-120); out-of-image pixels are dropped
+    const uint32_t word = s_bitmap[sub >> 5];
+    const uint32_t r = base + s_prefix[sub >> 5] + __popc(word & ((1u << (sub & 31)) - 1u));
+    if (x < prm.width && y < prm.height) cluster_ref[(size_t) y * prm.width + x] = r;
+
+    // unique keys, ascending inside the tile
+    const uint32_t tile_bits = (ti & 0xFFu) | ((tj & 0xFFu) << 8);
+    uint32_t out = base + excl;
+    uint32_t bits = w0;
+    while (bits)
+    {
+        const uint32_t b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (out < prm.max_keys) keys_out[out] = tile_bits | (((2 * tid) * 32 + b) << 16);
+        out++;
+    }
+    bits = w1;
+    while (bits)
+    {
+        const uint32_t b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (out < prm.max_keys) keys_out[out] = tile_bits | (((2 * tid + 1) * 32 + b) << 16);
+        out++;
+    }
+}
+
+// ---- a8 kernel ----------------------------------------------------------------------------------------------------
+struct assign_params
+{
+    uint32_t tiles_x, tiles_y;
+    float i00, i11, nAB;
+    float near_plane, a;
+    uint32_t bvh_root, levels, light_count;
+    uint32_t max_keys, max_assigned;
+};
+
+struct float3x { float v[3]; };
+
+// clustered_shading.glsl:72-110, exactly as written (corners are NOT re-ordered component-wise)
+__device__ __forceinline__ void cluster_aabb(uint32_t key, const assign_params& prm, const float* __restrict__ near_table,
+                                             float3x& cmin, float3x& cmax)
+{
+    const uint32_t ci = key & 0xFFu, cj = (key >> 8) & 0xFFu, ck = (key >> 16) & 0x3FFu;
+    const float tx = (float) prm.tiles_x, ty = (float) prm.tiles_y;
+    float p0x = __fdiv_rn((float) ci, tx), p0y = __fdiv_rn((float) cj, ty);
+    p0x = __fsub_rn(__fmul_rn(p0x, 2.0f), 1.0f);
+    p0y = __fsub_rn(__fmul_rn(__fsub_rn(1.0f, p0y), 2.0f), 1.0f);
+    float p1x = __fdiv_rn((float) (ci + 1), tx), p1y = __fdiv_rn((float) (cj + 1), ty);
+    p1x = __fsub_rn(__fmul_rn(p1x, 2.0f), 1.0f);
+    p1y = __fsub_rn(__fmul_rn(__fsub_rn(1.0f, p1y), 2.0f), 1.0f);
+    const float w = prm.nAB; // (0*iB) + (1*nAB)
+    const float v0x = __fdiv_rn(__fmul_rn(prm.i00, p0x), w), v0y = __fdiv_rn(__fmul_rn(prm.i11, p0y), w), vz = __fdiv_rn(1.0f, w);
+    const float v1x = __fdiv_rn(__fmul_rn(prm.i00, p1x), w), v1y = __fdiv_rn(__fmul_rn(prm.i11, p1y), w);
+    const float near_k = near_table[ck];
+    const float far_k = __fmul_rn(near_k, prm.a);
+    const float l0 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v0x, v0x), __fmul_rn(v0y, v0y)), __fmul_rn(vz, vz)));
+    const float l1 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v1x, v1x), __fmul_rn(v1y, v1y)), __fmul_rn(vz, vz)));
+    const float d0[3] = {__fdiv_rn(v0x, l0), __fdiv_rn(v0y, l0), __fdiv_rn(vz, l0)};
+    const float d1[3] = {__fdiv_rn(v1x, l1), __fdiv_rn(v1y, l1), __fdiv_rn(vz, l1)};
+    const float s0 = __fdiv_rn(near_k, d0[2]), s1 = __fdiv_rn(far_k, d1[2]);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+    {
+        cmin.v[c] = __fmul_rn(s0, d0[c]);
+        cmax.v[c] = __fmul_rn(s1, d1[c]);
+    }
+}
+
+constexpr int kAssignThreads = 256;
+constexpr int kAssignWarps = kAssignThreads / 32;
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kAssignThreads)
+assign_lights_kernel(const uint32_t* __restrict__ cluster_keys, const uint32_t* __restrict__ dispatch_params,
+                     const float4* __restrict__ bvh, const uint2* __restrict__ sorted_pairs,
+                     const float4* __restrict__ view_pos, const float* __restrict__ near_table, assign_params prm,
+                     uint32_t* counts, const uint32_t* __restrict__ offsets, uint32_t* indices, uint32_t* status_out)
+{
+    __shared__ uint32_t s_overlaps[kAssignWarps][kMaxBvhLevels];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t count = min(dispatch_params[0], prm.max_keys);
+    const uint32_t total_warps = gridDim.x * kAssignWarps;
+    uint32_t* ov = s_overlaps[warp];
+    const unsigned ge = lanemask_ge();
+
+    // level_base[l] = address of the first node of traversal level l (0 = children of the root)
+    uint32_t level_base[kMaxBvhLevels];
+    {
+        uint32_t acc = 0, p = 1;
+#pragma unroll
+        for (int l = 0; l < kMaxBvhLevels; l++)
+        {
+            p *= 32;
+            acc += p;
+            level_base[l] = prm.bvh_root - acc;
+        }
+    }
+    uint32_t stat_nodes = 0, stat_leaves = 0, stat_total = 0;
+
+    for (uint32_t c = blockIdx.x * kAssignWarps + warp; c < count; c += total_warps)
+    {
+        float3x cmin, cmax;
+        cluster_aabb(cluster_keys[c], prm, near_table, cmin, cmax);
+        const uint32_t out_base = WRITE ? offsets[c] : 0u;
+        uint32_t running = 0;
+
+        uint32_t level = 0, idx = 0; // idx = index of the current 32-group inside its level
+        bool enter = true;
+        while (true)
+        {
+            if (enter)
+            {
+                uint32_t lb = level_base[0];
+#pragma unroll
+                for (int l = 1; l < kMaxBvhLevels; l++)
+                    if ((int) level == l) lb = level_base[l];
+                const uint32_t addr = lb + idx * 32 + lane;
+                const float4 lo = bvh[2 * (size_t) addr], hi = bvh[2 * (size_t) addr + 1];
+                if (level + 1 < prm.levels)
+                {
+                    // test_aabb_aabb(cluster_min, cluster_max, node.min, node.max), assign_lights.comp:84-94
+                    const bool valid = __float_as_uint(lo.w) != kInvalid;
+                    const bool overlap = valid && cmax.v[0] >= lo.x && cmin.v[0] <= hi.x && cmax.v[1] >= lo.y &&
+                                         cmin.v[1] <= hi.y && cmax.v[2] >= lo.z && cmin.v[2] <= hi.z;
+                    const unsigned mask = __ballot_sync(kFullMask, overlap);
+                    stat_nodes += 32;
+                    if (mask == 0) enter = false; // POP
+                    else
+                    {
+                        if (lane == 0) ov[level] = mask;
+                        __syncwarp();
+                        idx = idx * 32 + (__ffs(mask) - 1);
+                        level++;
+                    }
+                }
+                else
+                {
+                    // leaf group: sphere (light) vs cluster box, assign_lights.comp:97-102,209-214
+                    bool hit = false;
+                    uint32_t light = 0;
+                    if (addr < prm.light_count)
+                    {
+                        light = sorted_pairs[addr].y;
+                        const float4 o = view_pos[light];
+                        const float r = __fdiv_rn(__fsub_rn(hi.x, lo.x), 2.0f);
+                        const float oc[3] = {o.x, o.y, o.z};
+                        float q[3];
+#pragma unroll
+                        for (int k = 0; k < 3; k++)
+                        {
+                            const float m = cmax.v[k] < oc[k] ? cmax.v[k] : oc[k];     // min(o, cmax)
+                            const float t = cmin.v[k] < m ? m : cmin.v[k];             // max(cmin, .)
+                            q[k] = __fsub_rn(t, oc[k]);
+                        }
+                        const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q[0], q[0]), __fmul_rn(q[1], q[1])), __fmul_rn(q[2], q[2])));
+                        hit = dist < r;
+                    }
+                    const unsigned mask = __ballot_sync(kFullMask, hit);
+                    stat_leaves += 32;
+                    if (WRITE && hit)
+                    {
+                        const uint32_t slot = out_base + running + (__popc(mask & ge) - 1);   // descending lane order
+                        if (slot < prm.max_assigned) indices[slot] = light;
+                    }
+                    running += __popc(mask);
+                    enter = false; // POP
+                }
+            }
+            else
+            {
+                // POP then ADVANCE (assign_lights.comp:137-166): clear the lowest set bit of the parent level
+                if (level == 0) break;
+                level--;
+                idx >>= 5;
+                uint32_t m = ov[level];
+                m &= m - 1;
+                if (m != 0)
+                {
+                    __syncwarp();
+                    if (lane == 0) ov[level] = m;
+                    __syncwarp();
+                    idx = idx * 32 + (__ffs(m) - 1);
+                    level++;
+                    enter = true;
+                }
+            }
+        }
+        if (!WRITE && lane == 0) counts[c] = running;
+        stat_total += running;
+    }
+    if (!WRITE && status_out != nullptr && lane == 0)
+    {
+        if (stat_total) atomicAdd(&status_out[0], stat_total);
+        if (stat_nodes) atomicAdd(&status_out[2], stat_nodes);
+        if (stat_leaves) atomicAdd(&status_out[3], stat_leaves);
+    }
+}
+
+// overflow flag of the assigned-light list: total > max_assigned (reference overruns silently, config.hpp:24)
+__global__ void assign_overflow_kernel(uint32_t* status_out, uint32_t max_assigned)
+{
+    if (status_out[0] > max_assigned) status_out[1] = 1;
+}
+
+// ---- tensor maps ----------------------------------------------------------------------------------------------------
+using encode_fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_fn get_encode_fn()
+{
+    static encode_fn fn = []() -> encode_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<encode_fn>(p);
+    }();
+    return fn;
+}
+
+bool make_tile_map(CUtensorMap* map, const void* base, uint32_t width, uint32_t height, uint32_t elem_bytes)
+{
+    encode_fn enc = get_encode_fn();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || ((uint64_t) width * elem_bytes) % 16 != 0) return false;
+    const cuuint64_t dims[2] = {width, height};
+    const cuuint64_t strides[1] = {(cuuint64_t) width * elem_bytes};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+    return enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+} // namespace
+} // namespace vrenb200
+
+using namespace vrenb200;
+
+extern "C" size_t vrenb200_find_unique_clusters_scratch_bytes(uint32_t width, uint32_t height)
+{
+    const size_t tiles = (size_t) ((width + 31) / 32) * ((height + 31) / 32);
+    return align_up(offsetof(cluster_scan_state, status) + std::max<size_t>(tiles, 1) * 8, 256) + kMaxSlices * sizeof(float);
+}
+
+extern "C" int vrenb200_find_unique_clusters(vrenb200_stream_t stream,
+                                             const float* depth, const void* normals_rgba16f,
+                                             uint32_t width, uint32_t height, const vrenb200_camera* camera,
+                                             uint32_t* keys_out, uint32_t max_keys, uint32_t* dispatch_params,
+                                             uint32_t* cluster_ref, void* scratch, size_t scratch_bytes)
+{
+    if (!depth || !camera || !keys_out || !dispatch_params || !cluster_ref) return VRENB200_EINVAL_ARG;
+    if (width == 0 || height == 0) return VRENB200_EINVAL_LENGTH;
+    const uint32_t tiles_x = (width + 31) / 32, tiles_y = (height + 31) / 32;
+    if (tiles_x > 256 || tiles_y > 256) return VRENB200_ELIMIT;      // 8-bit tile fields of the key (find_unique_clusters.comp:72-76)
+    if (scratch == nullptr || scratch_bytes < vrenb200_find_unique_clusters_scratch_bytes(width, height)) return VRENB200_ESCRATCH;
+    if (reinterpret_cast<uintptr_t>(scratch) & 255) return VRENB200_EALIGN;
+    cudaStream_t s = as_stream(stream);
+
+    const proj_consts pc = make_proj(*camera);
+    const float a = 1.0f + (2.0f * pc.tan_half) / (float) tiles_y;
+    const slice_table& tab = get_slice_table(camera->near_plane, a);
+
+    const size_t state_bytes = align_up(offsetof(cluster_scan_state, status) + (size_t) tiles_x * tiles_y * 8, 256);
+    cluster_scan_state* state = static_cast<cluster_scan_state*>(scratch);
+    float* thresholds = reinterpret_cast<float*>(static_cast<char*>(scratch) + state_bytes);
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, state_bytes, s)));
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(dispatch_params, 0, 16, s)));                  // vkCmdUpdateBuffer {0,1,1}
+    VRENB200_TRY(check_cuda(cudaMemcpyAsync(thresholds, tab.thresholds.data(), tab.thresholds.size() * sizeof(float),
+                                            cudaMemcpyHostToDevice, s)));
+
+    cluster_key_params prm{};
+    prm.width = width; prm.height = height; prm.tiles_x = tiles_x; prm.tiles_y = tiles_y;
+    prm.iB = pc.iB; prm.nAB = pc.nAB;
+    prm.inv_near = 1.0f / camera->near_plane;
+    prm.inv_log2a = (float) (1.0 / std::log2((double) a));
+    prm.table_len = (uint32_t) tab.thresholds.size();
+    prm.max_keys = max_keys;
+    prm.has_normals = normals_rgba16f != nullptr;
+    CUtensorMap dmap, nmap;
+    std::memset(&dmap, 0, sizeof(dmap));
+    std::memset(&nmap, 0, sizeof(nmap));
+    prm.use_tma = make_tile_map(&dmap, depth, width, height, 4) &&
+                  (!prm.has_normals || make_tile_map(&nmap, normals_rgba16f, width, height, 8));
+    find_unique_clusters_kernel<<<tiles_x * tiles_y, 1024, 0, s>>>(dmap, nmap, depth, static_cast<const uint2*>(normals_rgba16f),
+                                                                 thresholds, prm, state, keys_out, dispatch_params, cluster_ref);
+    return check_launch();
+}
+
+extern "C" size_t vrenb200_assign_lights_scratch_bytes(uint32_t max_keys)
+{
+    return 1024 * sizeof(float) + vrenb200_scan_scratch_bytes(max_keys) + 256;
+}
+
+extern "C" int vrenb200_assign_lights(vrenb200_stream_t stream,
+                                      uint32_t width, uint32_t height, const vrenb200_camera* camera,
+                                      const uint32_t* cluster_keys, const uint32_t* dispatch_params, uint32_t max_keys,
+                                      const void* bvh_buffer, uint32_t bvh_root_index, uint32_t light_count,
+                                      const void* light_index_buffer, const float* view_pos,
+                                      uint32_t* indices_out, uint32_t max_assigned,
+                                      uint32_t* counts_out, uint32_t* offsets_out, uint32_t* status_out,
+                                      void* scratch, size_t scratch_bytes)
+{
+    if (!camera || !cluster_keys || !dispatch_params || !counts_out || !offsets_out || !indices_out) return VRENB200_EINVAL_ARG;
+    if (max_keys == 0) return VRENB200_EINVAL_LENGTH;
+    cudaStream_t s = as_stream(stream);
+    // vkCmdFillBuffer(counts, 0) — the only effect when there are no lights (clustered_shading.cpp:492-496)
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(counts_out, 0, (size_t) max_keys * 4, s)));
+    if (status_out) VRENB200_TRY(check_cuda(cudaMemsetAsync(status_out, 0, 16, s)));
+    if (light_count == 0) return VRENB200_OK;
+    if (!bvh_buffer || !light_index_buffer || !view_pos) return VRENB200_EINVAL_ARG;
+    if (scratch == nullptr || scratch_bytes < vrenb200_assign_lights_scratch_bytes(max_keys)) return VRENB200_ESCRATCH;
+    if (reinterpret_cast<uintptr_t>(scratch) & 255) return VRENB200_EALIGN;
+    const uint32_t levels = vrenb200_calc_bvh_level_count(light_count);
+    if (levels > (uint32_t) kMaxBvhLevels) return VRENB200_ELIMIT;
+
+    const uint32_t tiles_x = (width + 31) / 32, tiles_y = (height + 31) / 32;
+    const proj_consts pc = make_proj(*camera);
+    assign_params prm{};
+    prm.tiles_x = tiles_x; prm.tiles_y = tiles_y;
+    prm.i00 = pc.i00; prm.i11 = pc.i11; prm.nAB = pc.nAB;
+    prm.near_plane = camera->near_plane;
+    prm.a = 2.0f * pc.tan_half / (float) tiles_y + 1.0f;            // clustered_shading.glsl:96
+    prm.bvh_root = bvh_root_index; prm.levels = levels; prm.light_count = light_count;
+    prm.max_keys = max_keys; prm.max_assigned = max_assigned;
+
+    // near_k = near * pow(a, k), k < 1024 (clustered_shading.glsl:97) evaluated on the host with powf
+    float near_host[1024];
+    for (int k = 0; k < 1024; k++) near_host[k] = camera->near_plane * powf(prm.a, (float) k);
+    float* near_table = static_cast<float*>(scratch);
+    void* scan_scratch = static_cast<char*>(scratch) + 1024 * sizeof(float);
+    const size_t scan_bytes = vrenb200_scan_scratch_bytes(max_keys);
+    VRENB200_TRY(check_cuda(cudaMemcpyAsync(near_table, near_host, sizeof(near_host), cudaMemcpyHostToDevice, s)));
+
+    const float4* bvh = static_cast<const float4*>(bvh_buffer);
+    const uint2* pairs = static_cast<const uint2*>(light_index_buffer);
+    const float4* vp = reinterpret_cast<const float4*>(view_pos);
+    const int grid = kNumSMs * 8;
+    assign_lights_kernel<false><<<grid, kAssignThreads, 0, s>>>(cluster_keys, dispatch_params, bvh, pairs, vp, near_table, prm,
+                                                               counts_out, nullptr, nullptr, status_out);
+    VRENB200_TRY(check_launch());
+    // copy counts -> offsets + blelloch_scan over all max_keys slots (clustered_shading.cpp:586-619), one pass here
+    VRENB200_TRY(vrenb200_exclusive_scan_u32(stream, counts_out, offsets_out, max_keys, scan_scratch, scan_bytes));
+    assign_lights_kernel<true><<<grid, kAssignThreads, 0, s>>>(cluster_keys, dispatch_params, bvh, pairs, vp, near_table, prm,
+                                                              counts_out, offsets_out, indices_out, status_out);
+    VRENB200_TRY(check_launch());
+    if (status_out)
+    {
+        assign_overflow_kernel<<<1, 1, 0, s>>>(status_out, max_assigned);
+        VRENB200_TRY(check_launch());
+    }
+    return VRENB200_OK;
+}

@@ -1,19 +1,24 @@
-// a3 — vren::radix_sort (reference: vren/vren/primitives/radix_sort.{hpp,cpp}, shaders/radix_sort_*.comp).
+// a3 — vren::radix_sort   (reference: vren/vren/primitives/radix_sort.{hpp,cpp}, shaders/radix_sort_*.comp)
+// a4 — vren::bucket_sort  (reference: vren/vren/primitives/bucket_sort.{hpp,cpp}, shaders/bucket_sort_*.comp)
 //
-// Reference: LSD, 4-bit digits, 8 passes, each pass = fill + local_count + reduce + global_offset + downsweep
-// + reorder (~14 dispatches, 12n bytes of key traffic per pass, one key per thread, n pow2 >= 1024).
+// Reference radix sort: LSD, 4-bit digits, 8 passes, each pass = fill + local_count + reduce + global_offset +
+// downsweep + reorder (~14 dispatches, 12n bytes of key traffic per pass, one key per thread, n pow2 >= 1024).
+// Reference bucket sort: global atomics on 65536 counters (count), blelloch scan, atomics again (write): unstable.
 //
-// Here (B200-first): "onesweep" — 8-bit digits, 4 passes.
-//   1. ONE histogram kernel reads the keys once (128-bit loads) and builds all four 256-bin digit histograms.
+// Here (B200-first): "onesweep" — 8-bit digits, one fused kernel per digit.
+//   1. ONE histogram kernel reads the keys once (128-bit loads) and builds every 256-bin digit histogram.
 //   2. One tiny kernel turns them into exclusive digit offsets.
-//   3. Per pass ONE fused kernel.  A CTA takes a tile (dynamic ticket), stages keys (and values) into shared
+//   3. Per digit ONE fused kernel.  A CTA takes a tile (dynamic ticket), stages keys (and values) into shared
 //      memory with a single-thread TMA bulk copy (cp.async.bulk + mbarrier: no register staging, values land
 //      while keys are being ranked), ranks keys stably with warp-ballot digit matching against warp-private
 //      histograms, resolves the tile's global digit offsets with a decoupled look-back over a flag|count word
 //      per (tile, digit), regroups keys/values by digit in shared memory and writes them out coalesced.
-// HBM traffic: 4n (histogram) + 4 passes x 8n (keys) [+ 4 x 8n values] = 36 B/key, 68 B/pair.
-// Stability: warp-striped order (warp, item, lane) == element order, so equal keys keep input order (needed
-// by LSD passes, and it is the pairs contract).
+// Radix sort = 4 digits: 4n (histogram) + 4 x 8n keys [+ 4 x 8n values] = 36 B/key, 68 B/pair of HBM traffic.
+// Bucket sort = the same kernel over interleaved uvec2 pairs with 2 digits (16-bit key): 8n + 2 x 16n = 40 B/pair,
+// deterministic and stable (the canonical tie-break), bucket END offsets from a fused 65536-bin count.
+// Stability: warp-striped order (warp, item, lane) == element order, so equal keys keep input order.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vrenb200 {
@@ -28,13 +33,15 @@ constexpr uint32_t kLbFlagAggregate = 1u << 30;
 constexpr uint32_t kLbFlagInclusive = 2u << 30;
 constexpr uint32_t kLbValueMask = (1u << 30) - 1;
 
+constexpr uint32_t kBucketKeys = 1u << 16; // bucket_sort.hpp:15-16
+
 // ---- control block carved from scratch ----------------------------------------------------------------------
 struct sort_control
 {
     uint32_t tickets[kPasses];            // dynamic tile ids per pass
     uint32_t _pad[60];
     uint32_t hist[kPasses][kRadix];       // global digit counts, then exclusive offsets
-    // followed by look-back words: [kPasses][tiles][kRadix]
+    // followed by look-back words: [passes][tiles][kRadix]
 };
 
 // ---- mbarrier / bulk-copy (TMA 1D) wrappers --------------------------------------------------------------
@@ -70,7 +77,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// ---- 1. histogram of all four digits in one read of the keys ----------------------------------------------
+// ---- 1. histograms in one read of the keys -------------------------------------------------------------------
 constexpr int kHistThreads = 512;
 
 __global__ void __launch_bounds__(kHistThreads)
@@ -113,7 +120,85 @@ radix_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, sort_contr
     }
 }
 
-// ---- 2. exclusive scan of each 256-bin histogram (grid = kPasses, block = 256) ---------------------------
+// bucket sort: uvec2 pairs, key = x & 0xFFFF -> two digit histograms + the 65536 bucket counters
+// (bucket_sort_count.comp:27-34) in the same read
+__global__ void __launch_bounds__(kHistThreads)
+bucket_histogram_kernel(const uint2* __restrict__ pairs, uint32_t n, sort_control* ctl, uint32_t* bucket_counters)
+{
+    __shared__ uint32_t s_hist[2][kRadix];
+    for (int i = threadIdx.x; i < 2 * kRadix; i += kHistThreads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t n2 = n / 2;
+    const uint4* pairs2 = reinterpret_cast<const uint4*>(pairs);
+    auto count = [&](uint32_t x) {
+        atomicAdd(&s_hist[0][x & 0xFF], 1u);
+        atomicAdd(&s_hist[1][(x >> 8) & 0xFF], 1u);
+        atomicAdd(&bucket_counters[x & (kBucketKeys - 1)], 1u);
+    };
+    for (uint32_t i = blockIdx.x * kHistThreads + threadIdx.x; i < n2; i += gridDim.x * kHistThreads)
+    {
+        const uint4 a = ldg_stream_u4(pairs2 + i);
+        count(a.x); count(a.z);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) count(pairs[n - 1].x);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * kRadix; t += kHistThreads)
+    {
+        const uint32_t c = (&s_hist[0][0])[t];
+        if (c != 0) atomicAdd(&(&ctl->hist[0][0])[t], c);
+    }
+}
+
+// counts -> bucket END offsets (inclusive prefix): what bucket_sort_write.comp:32 leaves behind. One CTA.
+__global__ void __launch_bounds__(1024)
+bucket_end_offsets_kernel(uint32_t* counters)
+{
+    __shared__ uint32_t s_warp[32];
+    constexpr int PER = kBucketKeys / 1024; // 64 consecutive counters per thread
+    uint4* mine = reinterpret_cast<uint4*>(counters + threadIdx.x * PER);
+    uint4 v[PER / 4];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER / 4; i++)
+    {
+        v[i] = mine[i];
+        sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(kFullMask, inc, s);
+        if (lane >= (unsigned) s) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(kFullMask, w, s);
+            if (lane >= (unsigned) s) w += t;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    uint32_t run = inc - sum + (warp > 0 ? s_warp[warp - 1] : 0u);
+#pragma unroll
+    for (int i = 0; i < PER / 4; i++)
+    {
+        run += v[i].x; v[i].x = run;
+        run += v[i].y; v[i].y = run;
+        run += v[i].z; v[i].z = run;
+        run += v[i].w; v[i].w = run;
+        mine[i] = v[i];
+    }
+}
+
+// ---- 2. exclusive scan of each 256-bin histogram (grid = passes, block = 256) ----------------------------
 __global__ void __launch_bounds__(kRadix)
 radix_scan_histograms_kernel(sort_control* ctl)
 {
@@ -138,13 +223,16 @@ radix_scan_histograms_kernel(sort_control* ctl)
 }
 
 // ---- 3. the fused onesweep pass ------------------------------------------------------------------------------
-template <int THREADS, int ITEMS, bool KV>
+enum { LAYOUT_KEYS = 0, LAYOUT_SOA = 1, LAYOUT_AOS = 2 };
+
+template <int THREADS, int ITEMS, int LAYOUT>
 struct onesweep_smem
 {
     static constexpr int WARPS = THREADS / 32;
     static constexpr int TILE = THREADS * ITEMS;
-    alignas(128) uint32_t keys[TILE];
-    alignas(128) uint32_t vals[KV ? TILE : 4];
+    static constexpr int KV_WORDS = LAYOUT == LAYOUT_KEYS ? TILE : 2 * TILE;
+    // KEYS: keys[TILE] | SOA: keys[TILE] then values[TILE] | AOS: uint2[TILE]
+    alignas(128) uint32_t kv[KV_WORDS];
     uint32_t warp_hist[WARPS][kRadix];
     uint32_t digit_base[kRadix];
     uint32_t scan_warp[kRadix / 32];
@@ -153,18 +241,34 @@ struct onesweep_smem
     uint32_t tile;
 };
 
-enum { MATCH_BALLOT = 0, MATCH_HW = 1 };
+enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1 };
 
+// lanes of the warp holding the same 8-bit digit.
+// MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
+// MATCH_BALLOT_C: the plain C++ form (the compiler spends 6 per bit), kept for A/B runs.
 template <int MATCH>
 __device__ __forceinline__ unsigned match_digit(uint32_t d)
 {
-    if (MATCH == MATCH_HW)
+    unsigned mask = kFullMask;
+    if (MATCH == MATCH_BALLOT)
     {
-        return __match_any_sync(kFullMask, d);
+#pragma unroll
+        for (int b = 0; b < kRadixBits; b++)
+        {
+            asm("{\n"
+                ".reg .pred p;\n"
+                ".reg .b32 t, bal;\n"
+                "and.b32 t, %1, %2;\n"
+                "setp.ne.u32 p, t, 0;\n"
+                "vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+                "@p and.b32 %0, %0, bal;\n"
+                "@!p lop3.b32 %0, %0, bal, 0, 0x30;\n"   // mask & ~bal
+                "}\n"
+                : "+r"(mask) : "r"(d), "r"(1u << b));
+        }
     }
     else
     {
-        unsigned mask = kFullMask;
 #pragma unroll
         for (int b = 0; b < kRadixBits; b++)
         {
@@ -172,19 +276,23 @@ __device__ __forceinline__ unsigned match_digit(uint32_t d)
             const unsigned bal = __ballot_sync(kFullMask, bit);
             mask &= bit ? bal : ~bal;
         }
-        return mask;
     }
+    return mask;
 }
 
-template <int THREADS, int ITEMS, bool KV, int MATCH, int MIN_BLOCKS>
+template <int THREADS, int ITEMS, int LAYOUT, int MATCH, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                      uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t num_tiles)
 {
-    using smem_t = onesweep_smem<THREADS, ITEMS, KV>;
+    using smem_t = onesweep_smem<THREADS, ITEMS, LAYOUT>;
     constexpr int WARPS = smem_t::WARPS;
     constexpr int TILE = smem_t::TILE;
+    constexpr bool HAS_VALUES = LAYOUT != LAYOUT_KEYS;
+    constexpr int KSTRIDE = LAYOUT == LAYOUT_AOS ? 2 : 1;       // words between consecutive staged keys
+    constexpr int VOFF = LAYOUT == LAYOUT_AOS ? 1 : TILE;       // word offset key -> its value
+    constexpr uint32_t ELEM_BYTES = LAYOUT == LAYOUT_AOS ? 8 : 4;
     static_assert(THREADS >= kRadix, "one thread per digit needed");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     smem_t& sm = *reinterpret_cast<smem_t*>(smem_raw);
@@ -213,12 +321,12 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     {
         if (tid == 0)
         {
-            mbar_arrive_expect_tx(&sm.bar_keys, TILE * 4);
-            bulk_copy_g2s(sm.keys, keys_in + tile_base, TILE * 4, &sm.bar_keys);
-            if (KV)
+            mbar_arrive_expect_tx(&sm.bar_keys, TILE * ELEM_BYTES);
+            bulk_copy_g2s(sm.kv, keys_in + tile_base * KSTRIDE, TILE * ELEM_BYTES, &sm.bar_keys);
+            if (LAYOUT == LAYOUT_SOA)
             {
                 mbar_arrive_expect_tx(&sm.bar_vals, TILE * 4);
-                bulk_copy_g2s(sm.vals, vals_in + tile_base, TILE * 4, &sm.bar_vals);
+                bulk_copy_g2s(sm.kv + TILE, vals_in + tile_base, TILE * 4, &sm.bar_vals);
             }
         }
         mbar_wait(&sm.bar_keys, 0);
@@ -228,8 +336,10 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
         // ragged last tile: guarded loads, padding keys 0xFFFFFFFF sort behind every real key of the tile
         for (uint32_t i = tid; i < (uint32_t) TILE; i += THREADS)
         {
-            sm.keys[i] = i < valid ? keys_in[tile_base + i] : 0xFFFFFFFFu;
-            if (KV) sm.vals[i] = i < valid ? vals_in[tile_base + i] : 0u;
+            const bool in = i < valid;
+            sm.kv[i * KSTRIDE] = in ? keys_in[(tile_base + i) * KSTRIDE] : 0xFFFFFFFFu;
+            if (LAYOUT == LAYOUT_SOA) sm.kv[TILE + i] = in ? vals_in[tile_base + i] : 0u;
+            if (LAYOUT == LAYOUT_AOS) sm.kv[i * 2 + 1] = in ? keys_in[(tile_base + i) * 2 + 1] : 0u;
         }
         __syncthreads();
     }
@@ -238,25 +348,22 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     const uint32_t warp_off = warp * (ITEMS * 32) + lane;
     uint32_t key[ITEMS];
 #pragma unroll
-    for (int j = 0; j < ITEMS; j++) key[j] = sm.keys[warp_off + j * 32];
+    for (int j = 0; j < ITEMS; j++) key[j] = sm.kv[(warp_off + j * 32) * KSTRIDE];
 
-    // stable in-warp ranking: ballot match + warp-private running digit counters
+    // stable in-warp ranking: ballot match + warp-private running digit counters.  Every lane of a match group
+    // reads the counter, then every lane writes back the same new value (no leader election, no divergence).
     uint32_t rank[ITEMS];
     uint32_t* my_hist = sm.warp_hist[warp];
+    const unsigned lt = lanemask_lt();
 #pragma unroll
     for (int j = 0; j < ITEMS; j++)
     {
         const uint32_t d = (key[j] >> shift) & 0xFFu;
         const unsigned mask = match_digit<MATCH>(d);
-        const unsigned leader = 31 - __clz(mask);
-        uint32_t prior = 0;
-        if (lane == leader)
-        {
-            prior = my_hist[d];
-            my_hist[d] = prior + __popc(mask);
-        }
-        prior = __shfl_sync(kFullMask, prior, leader);
-        rank[j] = prior + __popc(mask & lanemask_lt());
+        const uint32_t prior = my_hist[d];
+        rank[j] = prior + __popc(mask & lt);
+        __syncwarp();
+        my_hist[d] = prior + __popc(mask);
         __syncwarp();
     }
     __syncthreads();
@@ -302,20 +409,25 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     // in-tile destination of every item; fetch the staged values with the same striping
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) rank[j] += my_hist[(key[j] >> shift) & 0xFFu];
-    uint32_t val[KV ? ITEMS : 1];
-    if (KV)
+    uint32_t val[HAS_VALUES ? ITEMS : 1];
+    if (HAS_VALUES)
     {
-        if (full) mbar_wait(&sm.bar_vals, 0);
+        if (LAYOUT == LAYOUT_SOA && full) mbar_wait(&sm.bar_vals, 0);
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) val[j] = sm.vals[warp_off + j * 32];
+        for (int j = 0; j < ITEMS; j++) val[j] = sm.kv[(warp_off + j * 32) * KSTRIDE + VOFF];
     }
     __syncthreads(); // every warp has consumed the staged inputs: the buffers become the regroup area
 
 #pragma unroll
     for (int j = 0; j < ITEMS; j++)
     {
-        sm.keys[rank[j]] = key[j];
-        if (KV) sm.vals[rank[j]] = val[j];
+        if (LAYOUT == LAYOUT_AOS)
+            reinterpret_cast<uint2*>(sm.kv)[rank[j]] = make_uint2(key[j], val[j]);
+        else
+        {
+            sm.kv[rank[j]] = key[j];
+            if (HAS_VALUES) sm.kv[TILE + rank[j]] = val[j];
+        }
     }
 
     // decoupled look-back, one thread per digit
@@ -339,60 +451,88 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     __syncthreads();
 
     // coalesced write-out: in-tile position p -> digit run -> global slot
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++)
+    if (full)
     {
-        const uint32_t p = j * THREADS + tid;
-        if (full || p < valid)
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++)
         {
-            const uint32_t k = sm.keys[p];
+            const uint32_t p = j * THREADS + tid;
+            if (LAYOUT == LAYOUT_AOS)
+            {
+                const uint2 e = reinterpret_cast<const uint2*>(sm.kv)[p];
+                const uint32_t g = sm.digit_base[(e.x >> shift) & 0xFFu] + p;
+                reinterpret_cast<uint2*>(keys_out)[g] = e;
+            }
+            else
+            {
+                const uint32_t k = sm.kv[p];
+                const uint32_t g = sm.digit_base[(k >> shift) & 0xFFu] + p;
+                keys_out[g] = k;
+                if (HAS_VALUES) vals_out[g] = sm.kv[TILE + p];
+            }
+        }
+    }
+    else
+    {
+        for (uint32_t p = tid; p < valid; p += THREADS)
+        {
+            const uint32_t k = sm.kv[p * KSTRIDE];
             const uint32_t g = sm.digit_base[(k >> shift) & 0xFFu] + p;
-            keys_out[g] = k;
-            if (KV) vals_out[g] = sm.vals[p];
+            if (LAYOUT == LAYOUT_AOS)
+                reinterpret_cast<uint2*>(keys_out)[g] = make_uint2(k, sm.kv[p * 2 + 1]);
+            else
+            {
+                keys_out[g] = k;
+                if (HAS_VALUES) vals_out[g] = sm.kv[TILE + p];
+            }
         }
     }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
+using launch_fn = int (*)(cudaStream_t, const uint32_t*, uint32_t*, const uint32_t*, uint32_t*, uint32_t, int,
+                          sort_control*, uint32_t*, uint32_t, int);
+
 struct sort_variant
 {
     const char* name;
     uint32_t tile;
-    int (*launch)(cudaStream_t, const uint32_t*, uint32_t*, const uint32_t*, uint32_t*, uint32_t, int,
-                  sort_control*, uint32_t*, uint32_t, bool);
+    launch_fn launch;
 };
+
+template <int THREADS, int ITEMS, int LAYOUT, int MATCH, int MIN_BLOCKS>
+int launch_one(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout,
+               uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t tiles)
+{
+    auto kern = onesweep_pass_kernel<THREADS, ITEMS, LAYOUT, MATCH, MIN_BLOCKS>;
+    constexpr size_t smem = sizeof(onesweep_smem<THREADS, ITEMS, LAYOUT>);
+    VRENB200_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)));
+    kern<<<tiles, THREADS, smem, s>>>(kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    return check_launch();
+}
 
 template <int THREADS, int ITEMS, int MATCH, int MIN_BLOCKS>
 int launch_onesweep(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout,
-                    uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t tiles, bool kv)
+                    uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t tiles, int layout)
 {
-    if (kv)
+    switch (layout)
     {
-        auto kern = onesweep_pass_kernel<THREADS, ITEMS, true, MATCH, MIN_BLOCKS>;
-        constexpr size_t smem = sizeof(onesweep_smem<THREADS, ITEMS, true>);
-        VRENB200_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)));
-        kern<<<tiles, THREADS, smem, s>>>(kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    case LAYOUT_KEYS: return launch_one<THREADS, ITEMS, LAYOUT_KEYS, MATCH, MIN_BLOCKS>(s, kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    case LAYOUT_SOA:  return launch_one<THREADS, ITEMS, LAYOUT_SOA, MATCH, MIN_BLOCKS>(s, kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    default:          return launch_one<THREADS, ITEMS, LAYOUT_AOS, MATCH, MIN_BLOCKS>(s, kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
     }
-    else
-    {
-        auto kern = onesweep_pass_kernel<THREADS, ITEMS, false, MATCH, MIN_BLOCKS>;
-        constexpr size_t smem = sizeof(onesweep_smem<THREADS, ITEMS, false>);
-        VRENB200_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)));
-        kern<<<tiles, THREADS, smem, s>>>(kin, kout, nullptr, nullptr, n, pass, ctl, lookback, tiles);
-    }
-    return check_launch();
 }
 
 #define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B> }
 const sort_variant g_variants[] = {
-    VARIANT(384, 16, MATCH_BALLOT, 2),   // 0: default
+    VARIANT(512, 16, MATCH_BALLOT, 2),   // 0: default
+    VARIANT(512, 16, MATCH_BALLOT_C, 2),
+    VARIANT(384, 16, MATCH_BALLOT, 2),
     VARIANT(256, 16, MATCH_BALLOT, 3),
-    VARIANT(512, 16, MATCH_BALLOT, 2),
+    VARIANT(256, 16, MATCH_BALLOT, 4),
+    VARIANT(384, 12, MATCH_BALLOT, 3),
     VARIANT(512, 12, MATCH_BALLOT, 2),
-    VARIANT(384, 16, MATCH_HW, 2),
-    VARIANT(256, 16, MATCH_HW, 3),
-    VARIANT(512, 16, MATCH_HW, 2),
-    VARIANT(256, 24, MATCH_BALLOT, 2),
+    VARIANT(1024, 8, MATCH_BALLOT, 1),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
@@ -433,7 +573,7 @@ int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, 
          reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(alt_vals) |
          reinterpret_cast<uintptr_t>(ctl_mem)) & 15)
         return VRENB200_EALIGN;
-    const bool kv = vals != nullptr;
+    const int layout = vals != nullptr ? LAYOUT_SOA : LAYOUT_KEYS;
     const sort_variant& var = g_variants[g_variant];
     const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
     sort_control* ctl = static_cast<sort_control*>(ctl_mem);
@@ -452,7 +592,7 @@ int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, 
     {
         const bool even = (pass & 1) == 0;
         VRENB200_TRY(var.launch(s, even ? keys : alt_keys, even ? alt_keys : keys, even ? vals : alt_vals,
-                                even ? alt_vals : vals, n, pass, ctl, lookback, tiles, kv));
+                                even ? alt_vals : vals, n, pass, ctl, lookback, tiles, layout));
         if (prof) cudaEventRecord(prof->ev[3 + pass], s);
     }
     return VRENB200_OK;
@@ -582,4 +722,48 @@ extern "C" int vrenb200_radix_sort_pairs_host(vrenb200_stream_t stream, uint32_t
     VRENB200_TRY(check_cuda(cudaMemcpyAsync(keys_host, dk, (size_t) n * 4, cudaMemcpyDeviceToHost, s)));
     if (kv) VRENB200_TRY(check_cuda(cudaMemcpyAsync(values_host, dv, (size_t) n * 4, cudaMemcpyDeviceToHost, s)));
     return check_cuda(cudaStreamSynchronize(s));
+}
+
+// ---- a4: bucket sort ------------------------------------------------------------------------------------------
+extern "C" size_t vrenb200_bucket_sort_output_bytes(uint32_t n)
+{
+    // bucket_sort.cpp:67-70
+    return align_up((size_t) n * 8, 256) + (size_t) kBucketKeys * sizeof(uint32_t);
+}
+
+extern "C" size_t vrenb200_bucket_sort_scratch_bytes(uint32_t n)
+{
+    return align_up((size_t) n * 8, 256) + control_bytes(n);
+}
+
+extern "C" int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pairs, uint32_t n, void* out,
+                                    void* scratch, size_t scratch_bytes)
+{
+    if (out == nullptr || (n > 0 && in_pairs == nullptr)) return VRENB200_EINVAL_ARG;
+    if (n >= (1u << 30)) return VRENB200_ELIMIT;
+    if ((reinterpret_cast<uintptr_t>(in_pairs) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(scratch)) & 15)
+        return VRENB200_EALIGN;
+    cudaStream_t s = as_stream(stream);
+    uint32_t* counters = reinterpret_cast<uint32_t*>(static_cast<char*>(out) + align_up((size_t) n * 8, 256)); // bucket_sort.cpp:86
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(counters, 0, kBucketKeys * sizeof(uint32_t), s)));                 // bucket_sort.cpp:104
+    if (n == 0) return VRENB200_OK;
+    if (scratch == nullptr || scratch_bytes < vrenb200_bucket_sort_scratch_bytes(n)) return VRENB200_ESCRATCH;
+    char* p = static_cast<char*>(scratch);
+    uint32_t* tmp = reinterpret_cast<uint32_t*>(p);
+    void* ctl_mem = p + align_up((size_t) n * 8, 256);
+    const sort_variant& var = g_variants[g_variant];
+    const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
+    sort_control* ctl = static_cast<sort_control*>(ctl_mem);
+    uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
+    const size_t clear = sizeof(sort_control) + (size_t) 2 * tiles * kRadix * sizeof(uint32_t);
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(ctl_mem, 0, clear, s)));
+    const uint32_t hist_grid = (uint32_t) std::min<size_t>(kNumSMs * 2, ((size_t) n / 2 + kHistThreads - 1) / kHistThreads + 1);
+    bucket_histogram_kernel<<<hist_grid, kHistThreads, 0, s>>>(static_cast<const uint2*>(in_pairs), n, ctl, counters);
+    VRENB200_TRY(check_launch());
+    radix_scan_histograms_kernel<<<2, kRadix, 0, s>>>(ctl);
+    VRENB200_TRY(check_launch());
+    VRENB200_TRY(var.launch(s, static_cast<const uint32_t*>(in_pairs), tmp, nullptr, nullptr, n, 0, ctl, lookback, tiles, LAYOUT_AOS));
+    VRENB200_TRY(var.launch(s, tmp, static_cast<uint32_t*>(out), nullptr, nullptr, n, 1, ctl, lookback, tiles, LAYOUT_AOS));
+    bucket_end_offsets_kernel<<<1, 1024, 0, s>>>(counters);
+    return check_launch();
 }

@@ -196,3 +196,50 @@ def radix_sort_pairs(keys, vals, n: int | None = None, scratch=None):
         scratch = _scratch(sb)
     check(lib.vrenb200_radix_sort_pairs(_stream(), _ptr(keys), _ptr(vals), n, _ptr(scratch), sb), "vrenb200_radix_sort_pairs")
     return keys, vals
+
+
+def bucket_sort(pairs, n: int | None = None):
+    """vren::bucket_sort over uvec2 pairs [n,2] (int32 storage). Returns (out_buffer_u8, sorted_view [n,2], counters_view [65536])"""
+    import torch
+
+    lib = load()
+    n = pairs.shape[0] if n is None else n
+    ob = lib.vrenb200_bucket_sort_output_bytes(n)
+    out = torch.zeros(ob, dtype=torch.uint8, device=pairs.device)
+    sb = lib.vrenb200_bucket_sort_scratch_bytes(n)
+    scratch = _scratch(sb)
+    check(lib.vrenb200_bucket_sort(_stream(), _ptr(pairs), n, _ptr(out), _ptr(scratch), sb), "vrenb200_bucket_sort")
+    sorted_view = out[: n * 8].view(torch.int32).view(n, 2)
+    coff = (n * 8 + 255) // 256 * 256
+    counters = out[coff: coff + 65536 * 4].view(torch.int32)
+    return out, sorted_view, counters
+
+
+def build_bvh(nodes_u8, padded_leaf_count: int):
+    """nodes_u8: uint8 device tensor holding calc_bvh_buffer_length(padded) 32-byte nodes, leaves pre-filled"""
+    lib = load()
+    check(lib.vrenb200_build_bvh(_stream(), _ptr(nodes_u8), padded_leaf_count), "vrenb200_build_bvh")
+    return nodes_u8
+
+
+def construct_point_light_bvh(positions, lights, view16, external_scratch: bool = True):
+    """positions/lights: float32 [L,4] device tensors; view16: 16 python floats (column-major).
+    Returns (view_pos [L,4], bvh_u8, index_u8)"""
+    import torch
+
+    lib = load()
+    L = positions.shape[0]
+    view_pos = torch.zeros(L, 4, dtype=torch.float32, device=positions.device)
+    bvh = torch.zeros(lib.vrenb200_light_bvh_buffer_bytes(L), dtype=torch.uint8, device=positions.device)
+    idx = torch.zeros(lib.vrenb200_light_index_buffer_bytes(L), dtype=torch.uint8, device=positions.device)
+    view = (C.c_float * 16)(*[float(v) for v in view16])
+    if external_scratch:
+        sb = lib.vrenb200_light_bvh_scratch_bytes(L)
+        scratch = _scratch(sb)
+        sp = _ptr(scratch)
+    else:
+        sb, sp = 0, 0
+    check(lib.vrenb200_construct_point_light_bvh(_stream(), _ptr(positions), _ptr(lights), L, C.cast(view, C.c_void_p),
+                                                 _ptr(view_pos), _ptr(bvh), _ptr(idx), sp, sb),
+          "vrenb200_construct_point_light_bvh")
+    return view_pos, bvh, idx
