@@ -1,0 +1,133 @@
+"""GPU parity for a7 (unique cluster keys) and a8 (light assignment) vs the oracle, and the a6->a7->a8 chain (a9).
+
+The reference has no test for this pass (parity unpinned upstream); the oracle restates the shaders with the
+canonical choices of SURVEY 8c.  The CUDA path emits the canonical tile-major order itself, so keys, per-pixel
+references, counts, offsets and light index lists are all compared bit-exactly, plus the order-free properties the
+reference guarantees (keys[ref(x,y)] == key(x,y); per-key light sets).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from vren_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    import torch
+
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint32:
+        return torch.from_numpy(a.view(np.int32)).cuda()
+    return torch.from_numpy(a).cuda()
+
+
+def host_u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def both_cameras(vren, w, h, **kw):
+    oc = oracle.default_camera(w, h, **kw)
+    vc = vren.Camera(oc.fov_y, oc.aspect_ratio, oc.near_plane, oc.far_plane)
+    return oc, vc
+
+
+@pytest.mark.parametrize("size", [(32, 32), (64, 48), (256, 144), (640, 360), (1000, 700), (1920, 1080)])
+@pytest.mark.parametrize("with_normals", [False, True])
+def test_find_unique_clusters_matches_oracle(vren, size, with_normals):
+    w, h = size
+    depth = synthetic.depth_buffer(w, h, seed=w + h)
+    normals = synthetic.normal_buffer(w, h, seed=w) if with_normals else None
+    oc, vc = both_cameras(vren, w, h)
+    want_keys, want_ref = oracle.find_unique_clusters(depth, normals, oc)
+    keys, disp, ref = vren.find_unique_clusters(dev(depth), None if normals is None else dev(normals), vc)
+    disp = host_u32(disp)
+    assert disp[0] == want_keys.size and disp[1] == 1 and disp[2] == 1 and disp[3] == 0
+    got_keys = host_u32(keys)[: disp[0]]
+    assert np.array_equal(got_keys, want_keys)                       # canonical tile-major order, ascending per tile
+    got_ref = host_u32(ref).reshape(h, w)
+    assert np.array_equal(got_ref, want_ref)
+    # order-free contract of the reference: the key a pixel references is the pixel's own key
+    px_keys = got_keys[got_ref]
+    ys, xs = np.mgrid[0:h, 0:w]
+    assert np.array_equal(px_keys & 0xFF, (xs >> 5) & 0xFF) and np.array_equal((px_keys >> 8) & 0xFF, (ys >> 5) & 0xFF)
+    if not with_normals:
+        assert np.all(px_keys >> 26 == 63)                           # zero normal -> all-ones field
+
+
+def test_find_unique_clusters_background_and_overflow(vren):
+    w, h = 256, 128
+    depth = np.ones((h, w), np.float32)                              # cleared depth buffer: every pixel at the far plane
+    oc, vc = both_cameras(vren, w, h)
+    want_keys, want_ref = oracle.find_unique_clusters(depth, None, oc)
+    keys, disp, ref = vren.find_unique_clusters(dev(depth), None, vc)
+    assert host_u32(disp)[0] == want_keys.size == (w // 32) * (h // 32)
+    assert np.array_equal(host_u32(keys)[: want_keys.size], want_keys)
+    # overflow of the key list is detected (the reference silently overruns config.hpp:23)
+    depth = synthetic.depth_buffer(w, h, seed=9)
+    want_keys, _ = oracle.find_unique_clusters(depth, None, oc)
+    cap = want_keys.size // 2
+    keys, disp, ref = vren.find_unique_clusters(dev(depth), None, vc, max_keys=cap)
+    disp = host_u32(disp)
+    assert disp[3] == 1 and disp[0] == cap
+    assert np.array_equal(host_u32(keys)[:cap], want_keys[:cap])
+
+
+def run_chain(vren, w, h, L, seed, intensity=(1.0, 1.0), max_keys=1 << 17, max_assigned=1 << 23, yaw=0.0):
+    depth = synthetic.depth_buffer(w, h, seed=seed)
+    pos, lights = synthetic.point_lights(L, seed=seed + 1, aspect=w / h, intensity=intensity)
+    view = synthetic.view_matrix(yaw, 0.0, (0.0, 0.0, 0.0))
+    oc, vc = both_cameras(vren, w, h)
+    # oracle chain
+    wvp, wnodes, wpairs = oracle.construct_point_light_bvh(pos, lights, view)
+    wkeys, wref = oracle.find_unique_clusters(depth, None, oc)
+    wcounts, woffsets, windices, wtotal = oracle.assign_lights(w, h, oc, wkeys, max_keys, wnodes, L, wpairs, wvp, max_assigned)
+    # CUDA chain (a9 order: a6 -> a7 -> a8)
+    vp, bvh, idx = vren.construct_point_light_bvh(dev(pos), dev(lights), view.tolist())
+    keys, disp, ref = vren.find_unique_clusters(dev(depth), None, vc, max_keys=max_keys)
+    counts, offsets, indices, status = vren.assign_lights(w, h, vc, keys, disp, bvh, L, idx, vp, max_keys=max_keys, max_assigned=max_assigned)
+    return (wkeys, wcounts, woffsets, windices, wtotal), (host_u32(keys), host_u32(counts), host_u32(offsets), host_u32(indices), host_u32(status))
+
+
+@pytest.mark.parametrize("w,h,L", [(64, 64, 1), (64, 64, 40), (256, 144, 1000), (640, 360, 5000), (1280, 720, 33000), (1920, 1080, 65536)])
+def test_assign_lights_chain_matches_oracle(vren, w, h, L):
+    (wkeys, wcounts, woffsets, windices, wtotal), (keys, counts, offsets, indices, status) = run_chain(vren, w, h, L, seed=w + L, intensity=(0.5, 3.0))
+    assert np.array_equal(counts, wcounts)
+    assert np.array_equal(offsets, woffsets)                          # exclusive scan over all 2^17 slots
+    assert status[0] == wtotal and status[1] == 0
+    assert np.array_equal(indices[:wtotal], windices[:wtotal])        # light order inside every list is part of the contract
+    assert wtotal > 0 or L <= 40
+    # keyed view (what a non-canonical list order would still have to satisfy)
+    got = {int(k): indices[o:o + c].tolist() for k, o, c in zip(keys[: wkeys.size], offsets, counts)}
+    want = {int(k): windices[o:o + c].tolist() for k, o, c in zip(wkeys, woffsets, wcounts)}
+    assert got == want
+
+
+def test_assign_lights_no_lights_and_overflow(vren):
+    import torch
+
+    w, h = 128, 64
+    oc, vc = both_cameras(vren, w, h)
+    depth = synthetic.depth_buffer(w, h, seed=5)
+    keys, disp, ref = vren.find_unique_clusters(dev(depth), None, vc)
+    # L == 0: counts zero-filled, nothing else touched (clustered_shading.cpp:494-496)
+    dummy = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    counts, offsets, indices, status = vren.assign_lights(w, h, vc, keys, disp, dummy, 0, dummy, dummy.view(torch.float32), max_assigned=1024)
+    assert int(counts.abs().sum()) == 0 and int(indices.abs().sum()) == 0
+    # indices overflow is detected and writes are clamped (reference overruns VREN_MAX_ASSIGNED_LIGHT_COUNT silently)
+    (wkeys, wcounts, woffsets, windices, wtotal), (keys, counts, offsets, indices, status) = run_chain(
+        vren, 256, 144, 3000, seed=11, intensity=(20.0, 20.0), max_assigned=4096)
+    assert wtotal > 4096 and status[0] == wtotal and status[1] == 1
+    assert np.array_equal(counts, wcounts) and np.array_equal(indices, windices)
+
+
+def test_cluster_chain_c5_full_size(vren):
+    """BASELINE C5: 3840x2160 depth, 65 536 lights (intensity 1.0), one view"""
+    (wkeys, wcounts, woffsets, windices, wtotal), (keys, counts, offsets, indices, status) = run_chain(vren, 3840, 2160, 65536, seed=2024)
+    assert np.array_equal(keys[: wkeys.size], wkeys)
+    assert np.array_equal(counts, wcounts) and np.array_equal(offsets, woffsets)
+    assert status[0] == wtotal and status[1] == 0
+    assert np.array_equal(indices[:wtotal], windices[:wtotal])

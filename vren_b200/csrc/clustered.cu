@@ -19,6 +19,7 @@
 // fp32 contract: every op is an explicitly rounded _rn intrinsic in GLSL source order; tan/pow/log are evaluated
 // on the host once per camera (tables below) with the formulas stated in oracle/oracle_clustered.cpp.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>

@@ -241,7 +241,7 @@ struct onesweep_smem
     uint32_t tile;
 };
 
-enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1 };
+enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2 }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -250,7 +250,7 @@ template <int MATCH>
 __device__ __forceinline__ unsigned match_digit(uint32_t d)
 {
     unsigned mask = kFullMask;
-    if (MATCH == MATCH_BALLOT)
+    if ((MATCH & MATCH_BALLOT_C) == 0)
     {
 #pragma unroll
         for (int b = 0; b < kRadixBits; b++)
@@ -302,7 +302,9 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 
     if (tid == 0)
     {
-        sm.tile = atomicAdd(&ctl->tickets[pass], 1u);
+        // tile id: dynamic ticket (a tile can only wait on tiles that already started), or the block index when the
+        // variant relies on in-order CTA dispatch (saves one L2 atomic round trip at the head of every tile)
+        sm.tile = (MATCH & TILE_BY_BLOCKIDX) ? blockIdx.x : atomicAdd(&ctl->tickets[pass], 1u);
         mbar_init(&sm.bar_keys, 1);
         mbar_init(&sm.bar_vals, 1);
         mbar_fence_init();
@@ -370,11 +372,16 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 
     // per digit: tile count, publish aggregate, tile-local exclusive offsets
     uint32_t cnt = 0, inc = 0, real_cnt = 0;
+    uint32_t per_warp[WARPS];
     uint32_t* lb = lookback + ((size_t) pass * num_tiles + tile) * kRadix;
     if (tid < kRadix)
     {
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) cnt += sm.warp_hist[w][tid];
+        for (int w = 0; w < WARPS; w++)
+        {
+            per_warp[w] = sm.warp_hist[w][tid];
+            cnt += per_warp[w];
+        }
         real_cnt = cnt - ((tid == kRadix - 1) ? (uint32_t) TILE - valid : 0u);
         st_relaxed_u32(&lb[tid], (tile == 0 ? kLbFlagInclusive : kLbFlagAggregate) | real_cnt);
         inc = cnt;
@@ -399,9 +406,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 #pragma unroll
         for (int w = 0; w < WARPS; w++)
         {
-            const uint32_t c = sm.warp_hist[w][tid];
             sm.warp_hist[w][tid] = run;
-            run += c;
+            run += per_warp[w];
         }
     }
     __syncthreads();
@@ -421,13 +427,11 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 #pragma unroll
     for (int j = 0; j < ITEMS; j++)
     {
-        if (LAYOUT == LAYOUT_AOS)
+        // pairs are regrouped interleaved (one 64-bit shared store / load per pair) whatever the global layout
+        if (HAS_VALUES)
             reinterpret_cast<uint2*>(sm.kv)[rank[j]] = make_uint2(key[j], val[j]);
         else
-        {
             sm.kv[rank[j]] = key[j];
-            if (HAS_VALUES) sm.kv[TILE + rank[j]] = val[j];
-        }
     }
 
     // decoupled look-back, one thread per digit
@@ -457,18 +461,22 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
         for (int j = 0; j < ITEMS; j++)
         {
             const uint32_t p = j * THREADS + tid;
-            if (LAYOUT == LAYOUT_AOS)
+            if (HAS_VALUES)
             {
                 const uint2 e = reinterpret_cast<const uint2*>(sm.kv)[p];
                 const uint32_t g = sm.digit_base[(e.x >> shift) & 0xFFu] + p;
-                reinterpret_cast<uint2*>(keys_out)[g] = e;
+                if (LAYOUT == LAYOUT_AOS)
+                    reinterpret_cast<uint2*>(keys_out)[g] = e;
+                else
+                {
+                    keys_out[g] = e.x;
+                    vals_out[g] = e.y;
+                }
             }
             else
             {
                 const uint32_t k = sm.kv[p];
-                const uint32_t g = sm.digit_base[(k >> shift) & 0xFFu] + p;
-                keys_out[g] = k;
-                if (HAS_VALUES) vals_out[g] = sm.kv[TILE + p];
+                keys_out[sm.digit_base[(k >> shift) & 0xFFu] + p] = k;
             }
         }
     }
@@ -476,14 +484,14 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     {
         for (uint32_t p = tid; p < valid; p += THREADS)
         {
-            const uint32_t k = sm.kv[p * KSTRIDE];
+            const uint32_t k = sm.kv[p * (HAS_VALUES ? 2 : 1)];
             const uint32_t g = sm.digit_base[(k >> shift) & 0xFFu] + p;
             if (LAYOUT == LAYOUT_AOS)
                 reinterpret_cast<uint2*>(keys_out)[g] = make_uint2(k, sm.kv[p * 2 + 1]);
             else
             {
                 keys_out[g] = k;
-                if (HAS_VALUES) vals_out[g] = sm.kv[TILE + p];
+                if (HAS_VALUES) vals_out[g] = sm.kv[p * 2 + 1];
             }
         }
     }
@@ -526,13 +534,13 @@ int launch_onesweep(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const u
 #define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B> }
 const sort_variant g_variants[] = {
     VARIANT(512, 16, MATCH_BALLOT, 2),   // 0: default
-    VARIANT(512, 16, MATCH_BALLOT_C, 2),
-    VARIANT(384, 16, MATCH_BALLOT, 2),
-    VARIANT(256, 16, MATCH_BALLOT, 3),
-    VARIANT(256, 16, MATCH_BALLOT, 4),
-    VARIANT(384, 12, MATCH_BALLOT, 3),
-    VARIANT(512, 12, MATCH_BALLOT, 2),
-    VARIANT(1024, 8, MATCH_BALLOT, 1),
+    VARIANT(512, 16, TILE_BY_BLOCKIDX, 2),
+    VARIANT(384, 16, TILE_BY_BLOCKIDX, 2),
+    VARIANT(256, 16, TILE_BY_BLOCKIDX, 3),
+    VARIANT(256, 16, TILE_BY_BLOCKIDX, 4),
+    VARIANT(384, 20, TILE_BY_BLOCKIDX, 2),
+    VARIANT(512, 20, TILE_BY_BLOCKIDX, 1),
+    VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile

@@ -243,3 +243,44 @@ def construct_point_light_bvh(positions, lights, view16, external_scratch: bool 
                                                  _ptr(view_pos), _ptr(bvh), _ptr(idx), sp, sb),
           "vrenb200_construct_point_light_bvh")
     return view_pos, bvh, idx
+
+
+DEFAULT_MAX_UNIQUE_CLUSTER_KEYS = 1 << 17     # VREN_MAX_UNIQUE_CLUSTER_KEY_COUNT, config.hpp:23
+DEFAULT_MAX_ASSIGNED_LIGHTS = 1 << 23         # VREN_MAX_ASSIGNED_LIGHT_COUNT, config.hpp:24
+
+
+def find_unique_clusters(depth, normals, camera: Camera, max_keys: int = DEFAULT_MAX_UNIQUE_CLUSTER_KEYS):
+    """depth: float32 [H,W] device tensor; normals: float16 [H,W,4] or None.
+    Returns (keys int32[max_keys], dispatch_params int32[4], cluster_ref int32 [H,W])"""
+    import torch
+
+    lib = load()
+    H, W = depth.shape
+    keys = torch.zeros(max_keys, dtype=torch.int32, device=depth.device)
+    disp = torch.zeros(4, dtype=torch.int32, device=depth.device)
+    ref = torch.zeros(H, W, dtype=torch.int32, device=depth.device)
+    sb = lib.vrenb200_find_unique_clusters_scratch_bytes(W, H)
+    scratch = _scratch(sb)
+    check(lib.vrenb200_find_unique_clusters(_stream(), _ptr(depth), _ptr(normals), W, H, C.byref(camera), _ptr(keys), max_keys,
+                                            _ptr(disp), _ptr(ref), _ptr(scratch), sb), "vrenb200_find_unique_clusters")
+    return keys, disp, ref
+
+
+def assign_lights(width: int, height: int, camera: Camera, keys, disp, bvh, light_count: int, index_buffer, view_pos,
+                  max_keys: int = DEFAULT_MAX_UNIQUE_CLUSTER_KEYS, max_assigned: int = DEFAULT_MAX_ASSIGNED_LIGHTS):
+    """Returns (counts[max_keys], offsets[max_keys], indices[max_assigned], status[4])"""
+    import torch
+
+    lib = load()
+    dev = keys.device
+    counts = torch.zeros(max_keys, dtype=torch.int32, device=dev)
+    offsets = torch.zeros(max_keys, dtype=torch.int32, device=dev)
+    indices = torch.zeros(max_assigned, dtype=torch.int32, device=dev)
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    sb = lib.vrenb200_assign_lights_scratch_bytes(max_keys)
+    scratch = _scratch(sb)
+    root = lib.vrenb200_calc_bvh_root_index(light_count)
+    check(lib.vrenb200_assign_lights(_stream(), width, height, C.byref(camera), _ptr(keys), _ptr(disp), max_keys, _ptr(bvh), root,
+                                     light_count, _ptr(index_buffer), _ptr(view_pos), _ptr(indices), max_assigned,
+                                     _ptr(counts), _ptr(offsets), _ptr(status), _ptr(scratch), sb), "vrenb200_assign_lights")
+    return counts, offsets, indices, status
