@@ -1,0 +1,88 @@
+"""CPU suite: the C-ABI library loads, exports every symbol include/vrenb200.h declares, and its pure-integer helpers
+agree with the oracle's restatement of the reference's double-precision formulas and with the reference KATs.
+No compute call is made here (no GPU needed)."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+import oracle
+from vren_b200 import build, lib
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def handle(built):
+    return lib.load()
+
+
+def test_every_declared_symbol_is_exported(handle):
+    declared = lib.declared_symbols()
+    assert len(declared) >= 45
+    missing = [s for s in declared if not hasattr(handle, s)]
+    assert not missing, f"libvrenb200.so does not export {missing}"
+    out = subprocess.run(["nm", "-D", "--defined-only", str(lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert set(declared) <= exported
+
+
+def test_version_and_status_strings(handle):
+    assert b"sm_100a" in handle.vrenb200_version()
+    assert handle.vrenb200_status_string(0) == b"ok"
+    assert handle.vrenb200_status_string(1) == b"invalid length"
+
+
+def test_integer_helpers_match_reference_formulas(handle):
+    orc = oracle.load()
+    for v in list(range(1, 70)) + [1000, 1023, 1024, 1025, 32767, 32768, 32769, 1 << 20, (1 << 20) + 1, 2193819, 1 << 25]:
+        assert handle.vrenb200_round_to_next_power_of_2(v) == orc.oracle_round_to_next_power_of_2(v)
+        assert handle.vrenb200_divide_and_ceil(v, 1024) == orc.oracle_divide_and_ceil(v, 1024)
+        assert handle.vrenb200_divide_and_ceil(v, 32) == orc.oracle_divide_and_ceil(v, 32)
+        assert bool(handle.vrenb200_is_power_of(v, 32)) == bool(orc.oracle_is_power_of(v, 32))
+        assert handle.vrenb200_round_to_next_power_of(v, 32) == orc.oracle_round_to_next_power_of(v, 32)
+        assert handle.vrenb200_calc_bvh_padded_leaf_count(v) == orc.oracle_calc_bvh_padded_leaf_count(v)
+        assert handle.vrenb200_calc_bvh_buffer_length(v) == orc.oracle_calc_bvh_buffer_length(v)
+        assert handle.vrenb200_calc_bvh_buffer_size(v) == orc.oracle_calc_bvh_buffer_size(v)
+        assert handle.vrenb200_calc_bvh_root_index(v) == orc.oracle_calc_bvh_root_index(v)
+        assert handle.vrenb200_calc_bvh_level_count(v) == orc.oracle_calc_bvh_level_count(v)
+    assert handle.vrenb200_round_to_next_multiple_of(10, 256) == 256
+    # TEST(build_bvh, utils) KATs (vren_test/vren_test/primitives/build_bvh.cpp:225-253) straight on the C ABI
+    assert [handle.vrenb200_calc_bvh_padded_leaf_count(x) for x in (0, 1, 17, 32, 129, 582, 1024, 2193819)] == [32, 32, 32, 32, 1024, 1024, 1024, 33554432]
+    assert handle.vrenb200_calc_bvh_buffer_length(2193819) == 32**5 + 32**4 + 32**3 + 32**2 + 32 + 1
+    assert [handle.vrenb200_calc_bvh_level_count(x) for x in (0, 1, 129, 582, 2193819)] == [1, 1, 2, 2, 5]
+
+
+def test_sizing_queries(handle):
+    assert handle.vrenb200_bucket_sort_output_bytes(100) == 1024 + 65536 * 4          # bucket_sort.cpp:67-70
+    assert handle.vrenb200_radix_sort_scratch_buffer_2_bytes(1 << 20) == 4 << 20       # radix_sort.cpp:139-147
+    assert handle.vrenb200_calc_reduce_output_buffer_length(10000) == 16384            # reduce.cpp:137-140
+    assert handle.vrenb200_light_bvh_buffer_bytes(65536) >= handle.vrenb200_calc_bvh_buffer_size(65536) == 34636832
+    assert handle.vrenb200_light_index_buffer_bytes(65536) >= handle.vrenb200_bucket_sort_output_bytes(65536)
+    assert handle.vrenb200_reduce_scratch_bytes(lib.U32, lib.REDUCE_TREE, 1 << 28, 1) == 0
+
+
+def test_product_path_never_touches_the_oracle():
+    """the shipped package must not import/execute anything under oracle/ (no CPU fallback)"""
+    files = list((ROOT / "vren_b200").rglob("*.py")) + list((ROOT / "vren_b200" / "csrc").glob("*")) + list((ROOT / "include").rglob("*.h*"))
+    for path in files:
+        if path.name == "build.py":      # builds the checker (allowed); it never loads it
+            continue
+        text = path.read_text(errors="ignore")
+        assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, path
+
+
+def test_facade_headers_compile(built):
+    """the C++ facade mirrors the reference's class names; it must at least compile and link on the CPU box"""
+    exe = build.build_facade_test(force=True)
+    assert exe.exists()
+
+
+@pytest.mark.gpu
+def test_facade_reference_style_tests(vren):
+    exe = build.build_facade_test()
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL PASS" in r.stdout

@@ -85,6 +85,24 @@ def build_oracle(force: bool = False) -> Path:
     return ORACLE_LIB
 
 
+FACADE_TEST = ROOT / "build" / "facade_test"
+
+
+def build_facade_test(force: bool = False) -> Path:
+    """tests/cpp/facade_test.cpp: the C++ facade (include/vren/) driven like the reference's own tests"""
+    src = ROOT / "tests" / "cpp" / "facade_test.cpp"
+    deps = [src, LIB] + sorted((ROOT / "include").rglob("*.h*"))
+    if not force and _newer(FACADE_TEST, deps):
+        return FACADE_TEST
+    FACADE_TEST.parent.mkdir(parents=True, exist_ok=True)
+    cuda_home = Path(_nvcc()).resolve().parent.parent
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", f"-I{ROOT / 'include'}", f"-I{cuda_home / 'include'}", str(src), "-o", str(FACADE_TEST),
+           f"-L{LIB.parent}", "-lvrenb200", f"-L{cuda_home / 'lib64'}", "-lcudart", f"-Wl,-rpath,{LIB.parent}",
+           f"-Wl,-rpath,{cuda_home / 'lib64'}"]
+    subprocess.run(cmd, check=True)
+    return FACADE_TEST
+
+
 def build_reference_extract(force: bool = False):
     """oracle/_ref: the few reference functions that compile standalone (see oracle/ref_extract.py)."""
     script = ORACLE_DIR / "ref_extract.py"

@@ -372,16 +372,11 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 
     // per digit: tile count, publish aggregate, tile-local exclusive offsets
     uint32_t cnt = 0, inc = 0, real_cnt = 0;
-    uint32_t per_warp[WARPS];
     uint32_t* lb = lookback + ((size_t) pass * num_tiles + tile) * kRadix;
     if (tid < kRadix)
     {
 #pragma unroll
-        for (int w = 0; w < WARPS; w++)
-        {
-            per_warp[w] = sm.warp_hist[w][tid];
-            cnt += per_warp[w];
-        }
+        for (int w = 0; w < WARPS; w++) cnt += sm.warp_hist[w][tid];
         real_cnt = cnt - ((tid == kRadix - 1) ? (uint32_t) TILE - valid : 0u);
         st_relaxed_u32(&lb[tid], (tile == 0 ? kLbFlagInclusive : kLbFlagAggregate) | real_cnt);
         inc = cnt;
@@ -406,8 +401,9 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 #pragma unroll
         for (int w = 0; w < WARPS; w++)
         {
+            const uint32_t c = sm.warp_hist[w][tid];
             sm.warp_hist[w][tid] = run;
-            run += per_warp[w];
+            run += c;
         }
     }
     __syncthreads();
