@@ -8,7 +8,8 @@ A "step" is one complete sort (histogram + 4 onesweep passes) of one batch of sy
   e2e          same metric through the host-buffer C-ABI call (H2D + sort + D2H inside the timed region)
   roofline     dominant kernel = onesweep pass: algorithmic 16 B/pair/launch over its CUDA-event duration
   cpu_baseline the oracle's restatement of the reference's CPU check (std::stable_sort by key) on a bounded sample
-N>1 (torchrun): every rank sorts its own shard of n pairs (weak scaling, no data-path collective).
+N>1 (torchrun): ONE global sort of N x 2^log2n pairs, 2^log2n per rank (weak scaling): top-digit histogram ->
+all_gather -> stable local partition -> NCCL all-to-all-v over NVLink -> local 4-pass onesweep (vren_b200/dist.py).
 """
 from __future__ import annotations
 
@@ -149,6 +150,79 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def secondary_metrics(lib, vlib, dev):
+    """the other BASELINE.json configs, each timed with CUDA events after 3 warm-ups (inputs larger than L2):
+    C2 scan + reduce over 2^28 u32, C4 BuildBVH over 2^20 leaves, C5 clustered light assignment at 4K / 65 536 lights"""
+    import math
+
+    import numpy as np
+    import torch
+
+    from vren_b200 import synthetic
+    from vren_b200.pipeline import ClusterAndShade
+
+    peak, _ = measured_peaks()
+    out = {}
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    n = 1 << 28
+    x = torch.ones(n, dtype=torch.int32, device=dev)
+    y = torch.empty_like(x)
+    sb = lib.vrenb200_scan_scratch_bytes(n)
+    scr = torch.empty(sb, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: vlib.check(lib.vrenb200_exclusive_scan_u32(stream, x.data_ptr(), y.data_ptr(), n, scr.data_ptr(), sb), "scan"))
+    out["scan_u32_2p28"] = {"ms": ms, "GB/s": 8 * n / ms / 1e6, "frac_hbm": 8 * n / ms / 1e6 / peak, "bytes_per_elt": 8}
+    rb = lib.vrenb200_reduce_scratch_bytes(vlib.U32, vlib.REDUCE_FINAL, n, 1)
+    rscr = torch.empty(max(rb, 256), dtype=torch.uint8, device=dev)
+    ms = timed(lambda: vlib.check(lib.vrenb200_reduce(stream, vlib.U32, vlib.ADD, vlib.REDUCE_FINAL, x.data_ptr(), n, y.data_ptr(), 1, rscr.data_ptr(), rb), "reduce"))
+    out["reduce_u32_add_final_2p28"] = {"ms": ms, "GB/s": 4 * n / ms / 1e6, "frac_hbm": 4 * n / ms / 1e6 / peak, "bytes_per_elt": 4}
+    xf = x.view(torch.float32)
+    ms = timed(lambda: vlib.check(lib.vrenb200_reduce(stream, vlib.F32, vlib.ADD, vlib.REDUCE_FINAL, xf.data_ptr(), n, y.data_ptr(), 1, rscr.data_ptr(), rb), "reduce"))
+    out["reduce_f32_add_final_2p28"] = {"ms": ms, "GB/s": 4 * n / ms / 1e6, "frac_hbm": 4 * n / ms / 1e6 / peak, "bytes_per_elt": 4}
+    ms = timed(lambda: vlib.check(lib.vrenb200_reduce(stream, vlib.U32, vlib.ADD, vlib.REDUCE_TREE, x.data_ptr(), n, y.data_ptr(), 1, 0, 0), "reduce"))
+    out["reduce_u32_add_tree_2p28"] = {"ms": ms, "GB/s": 8 * n / ms / 1e6, "frac_hbm": 8 * n / ms / 1e6 / peak, "bytes_per_elt": 8}
+    del x, y, xf, scr
+
+    # C4: BuildBVH over 2^20 pre-filled leaves (33 B/leaf)
+    leaves = 1 << 20
+    length = lib.vrenb200_calc_bvh_buffer_length(leaves)
+    nodes = torch.zeros(length * 8, dtype=torch.float32, device=dev)
+    nv = nodes.view(length, 8)
+    nv[:leaves, 0:3] = torch.rand(leaves, 3, device=dev) * 100
+    nv[:leaves, 4:7] = nv[:leaves, 0:3] + torch.rand(leaves, 3, device=dev) * 10
+    nodes.view(torch.int32).view(length, 8)[:leaves, 3] = -1
+    ms = timed(lambda: vlib.check(lib.vrenb200_build_bvh(stream, nodes.data_ptr(), leaves), "build_bvh"))
+    out["build_bvh_2p20_leaves"] = {"ms": ms, "GB/s": 33 * leaves / ms / 1e6, "frac_hbm": 33 * leaves / ms / 1e6 / peak, "bytes_per_leaf": 33,
+                                    "note": "34.6 MB problem: L2-resident and launch-bound, not HBM-bound"}
+    del nodes, nv
+
+    # C5: one view of the clustered light assignment
+    w, h, L = 3840, 2160, 65536
+    depth = torch.from_numpy(synthetic.depth_buffer(w, h, seed=2024)).to(dev)
+    pos, lights = synthetic.point_lights(L, seed=2025, aspect=w / h, intensity=(1.0, 1.0))
+    pos, lights = torch.from_numpy(pos).to(dev), torch.from_numpy(lights).to(dev)
+    view = synthetic.view_matrix(0.0, 0.0, (0, 0, 0)).tolist()
+    cam = vlib.Camera(np.float32(math.radians(45.0)), np.float32(w / h), np.float32(0.01), np.float32(1000.0))
+    cs = ClusterAndShade(w, h, max_point_lights=L)
+    ms = timed(lambda: cs(w, h, cam, view, depth, None, pos, lights, L), iters=20)
+    st = cs.status.cpu().numpy()
+    out["light_assign_4k_65536_lights"] = {"ms_per_view": ms, "target_ms": 0.5, "clusters": int(cs.dispatch_params[0]),
+                                           "assigned_lights": int(st[0]), "node_tests": int(st[2]), "leaf_tests": int(st[3]),
+                                           "stages": "construct_point_light_bvh + find_unique_cluster_list + assign_lights"}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -185,13 +259,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    dops = None
+    if world > 1:
+        from vren_b200 import dist as vdist
+
+        dops = vdist.CudaOps()
+    last = {}
+
     def one_step(profile):
         keys.copy_(keys0)      # restore the unsorted batch (untimed; 2 GiB of traffic also evicts L2)
         vals.copy_(vals0)
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        vlib.check(lib.vrenb200_radix_sort_pairs_profiled(stream, keys.data_ptr(), vals.data_ptr(), n, scratch.data_ptr(),
-                                                          sbytes, prof if profile else None), "radix_sort_pairs")
+        if world == 1:
+            vlib.check(lib.vrenb200_radix_sort_pairs_profiled(stream, keys.data_ptr(), vals.data_ptr(), n, scratch.data_ptr(),
+                                                              sbytes, prof if profile else None), "radix_sort_pairs")
+        else:
+            last["k"], last["v"], last["plan"] = vdist.sharded_sort_pairs(keys, vals, ops=dops)
         e1.record()
         return e0, e1
 
@@ -204,14 +290,36 @@ def run_ours(args):
             e0, e1 = one_step(True)
             e1.synchronize()
             step_ms.append(e0.elapsed_time(e1))
+            if world == 1:
+                vlib.check(lib.vrenb200_sort_profile_read(prof, kern_ms), "profile_read")
+                hist_ms.append(kern_ms[0])
+                pass_ms.extend(kern_ms[2:6])
+        barrier()
+    # correctness of the last step (cheap device-side property check; full parity lives in tests/)
+    sign = torch.tensor(-(1 << 31), dtype=torch.int32, device=dev)
+    if world == 1:
+        flipped = keys ^ sign
+        assert bool((flipped[1:] >= flipped[:-1]).all()), "bench: output not sorted"
+        assert torch.equal(keys0[vals.long()], keys), "bench: pairs broken"
+    else:
+        ok = last["k"] ^ sign
+        assert bool((ok[1:] >= ok[:-1]).all()), "bench: shard not sorted"
+        lo, hi = last["plan"].digit_lo[rank], last["plan"].digit_lo[rank + 1]
+        top = (last["k"].to(torch.int64) & 0xFFFFFFFF) >> 24
+        assert ok.numel() == 0 or (int(top.min()) >= lo and int(top.max()) < hi), "bench: shard outside its digit range"
+        cnt = torch.tensor([ok.numel()], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt)
+        assert int(cnt.item()) == world * n, "bench: pairs lost in the exchange"
+        # one profiled local sort for the roofline object (kernel timing does not depend on the exchange)
+        for _ in range(3):
+            keys.copy_(keys0); vals.copy_(vals0)
+            vlib.check(lib.vrenb200_radix_sort_pairs_profiled(stream, keys.data_ptr(), vals.data_ptr(), n, scratch.data_ptr(), sbytes, prof),
+                       "radix_sort_pairs")
+            torch.cuda.synchronize()
             vlib.check(lib.vrenb200_sort_profile_read(prof, kern_ms), "profile_read")
             hist_ms.append(kern_ms[0])
             pass_ms.extend(kern_ms[2:6])
-        barrier()
-    # correctness of the last step (cheap device-side property check; full parity lives in tests/)
-    flipped = keys ^ torch.tensor(-(1 << 31), dtype=torch.int32, device=dev)
-    assert bool((flipped[1:] >= flipped[:-1]).all()), "bench: output not sorted"
-    assert torch.equal(keys0[vals.long()], keys), "bench: pairs broken"
+        last.clear()
 
     ms = sum(step_ms) / len(step_ms)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -247,6 +355,11 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n / (float(te.item()) * 1e-3) / 1e9
 
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        del work
+        torch.cuda.empty_cache()
+        secondary = secondary_metrics(lib, vlib, dev)
     if rank == 0:
         peak, peak_src = measured_peaks()
         pass_avg_ms = sum(pass_ms) / len(pass_ms)
@@ -263,7 +376,8 @@ def run_ours(args):
             "config": {"workload": f"radix sort of 2^{args.log2n} uint32 key-value pairs per GPU (uniform keys, value=index)",
                        "l2": "inputs larger than L2 (2 GiB restored between steps)",
                        "variant": lib.vrenb200_radix_sort_variant_name(args.variant or 0).decode(),
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent shards, one per GPU"},
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"one global sort of {world}x2^{args.log2n} pairs: top-digit split + NCCL all-to-all-v + local onesweep"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "onesweep_pass_kernel", "peak_source": peak_src,
                          "kernel_ms": pass_avg_ms, "histogram_ms": sum(hist_ms) / len(hist_ms),
@@ -271,7 +385,8 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                     "ms_per_step": float(te.item())},
-            "gpu_launches": 6 * args.steps,
+            "gpu_launches": (6 if world == 1 else 1 + 1 + 2 + 6) * args.steps,
+            "secondary": secondary,
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
@@ -289,6 +404,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=28)
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -77,6 +77,9 @@ size_t vrenb200_scan_scratch_bytes(uint32_t n);
 /* in-place when out==in; any n>=1 (reference requires pow2: blelloch_scan.cpp:67) */
 int vrenb200_exclusive_scan_u32(vrenb200_stream_t stream, const uint32_t* in, uint32_t* out, uint32_t n,
                                 void* scratch, size_t scratch_bytes);
+/* out[i] = base + sum_{k<i} in[k]: local step of the sharded scan */
+int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const uint32_t* in, uint32_t* out, uint32_t n,
+                                     uint32_t base, void* scratch, size_t scratch_bytes);
 /* blelloch_scan::downsweep (blelloch_scan.cpp:57-139): turns `blocks` up-sweep trees of pow2 length n
  * into exclusive scans (+root when clear_last==0), in place */
 int vrenb200_blelloch_downsweep_u32(vrenb200_stream_t stream, uint32_t* buf, uint32_t n, uint32_t blocks,
@@ -104,6 +107,14 @@ int vrenb200_radix_sort_compat(vrenb200_stream_t stream, uint32_t* keys, uint32_
 size_t vrenb200_radix_sort_host_work_bytes(uint32_t n, int with_values);
 int vrenb200_radix_sort_pairs_host(vrenb200_stream_t stream, uint32_t* keys_host, uint32_t* values_host,
                                    uint32_t n, void* dev_work, size_t dev_work_bytes);
+
+/* building blocks of the multi-GPU sort: all four 256-bin digit histograms of the keys
+ * (hist_out: device uint32[4][256]) and a stable sort restricted to the digits [first_pass, first_pass+num_passes) */
+int vrenb200_radix_digit_histograms(vrenb200_stream_t stream, const uint32_t* keys, uint32_t n, uint32_t* hist_out);
+size_t vrenb200_radix_sort_range_scratch_bytes(uint32_t n);
+int vrenb200_radix_sort_pairs_range(vrenb200_stream_t stream, uint32_t* keys, uint32_t* values, uint32_t* alt_keys,
+                                    uint32_t* alt_values, uint32_t n, int first_pass, int num_passes,
+                                    void* scratch, size_t scratch_bytes, int* result_in_alt);
 
 /* tuning / measurement hooks (not part of the reference surface) */
 int vrenb200_radix_sort_set_variant(int variant);

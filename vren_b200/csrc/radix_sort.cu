@@ -569,7 +569,7 @@ namespace {
 
 // control + look-back live in `ctl_mem`; alt buffers given explicitly
 int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, uint32_t* alt_keys, uint32_t* alt_vals,
-                    void* ctl_mem, vrenb200_sort_profile* prof = nullptr)
+                    void* ctl_mem, vrenb200_sort_profile* prof = nullptr, int first_pass = 0, int num_passes = kPasses)
 {
     if (n == 0) return VRENB200_OK;
     if (n >= (1u << 30)) return VRENB200_ELIMIT;
@@ -592,12 +592,14 @@ int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, 
     radix_scan_histograms_kernel<<<kPasses, kRadix, 0, s>>>(ctl);
     VRENB200_TRY(check_launch());
     if (prof) cudaEventRecord(prof->ev[2], s);
-    for (int pass = 0; pass < kPasses; pass++)
+    // ping-pong: the i-th executed pass reads (keys, vals) when i is even; with 4 passes the result is back in `keys`
+    for (int i = 0; i < num_passes; i++)
     {
-        const bool even = (pass & 1) == 0;
+        const int pass = first_pass + i;
+        const bool even = (i & 1) == 0;
         VRENB200_TRY(var.launch(s, even ? keys : alt_keys, even ? alt_keys : keys, even ? vals : alt_vals,
                                 even ? alt_vals : vals, n, pass, ctl, lookback, tiles, layout));
-        if (prof) cudaEventRecord(prof->ev[3 + pass], s);
+        if (prof && num_passes == kPasses) cudaEventRecord(prof->ev[3 + pass], s);
     }
     return VRENB200_OK;
 }
@@ -681,6 +683,37 @@ extern "C" int vrenb200_radix_sort_pairs_profiled(vrenb200_stream_t stream, uint
     const size_t alt = align_up((size_t) n * 4, 256);
     return radix_sort_impl(as_stream(stream), keys, values, n, reinterpret_cast<uint32_t*>(p),
                            kv ? reinterpret_cast<uint32_t*>(p + alt) : nullptr, p + (kv ? 2 : 1) * alt, prof);
+}
+
+// ---- building blocks of the multi-GPU sort (vren_b200/dist.py): digit histograms and a digit-range sort --------
+// hist_out: device uint32[4][256], counts of every 8-bit digit of the keys (digit 3 = most significant byte)
+extern "C" int vrenb200_radix_digit_histograms(vrenb200_stream_t stream, const uint32_t* keys, uint32_t n, uint32_t* hist_out)
+{
+    if (hist_out == nullptr || (n > 0 && keys == nullptr)) return VRENB200_EINVAL_ARG;
+    if ((reinterpret_cast<uintptr_t>(keys) & 15) || (reinterpret_cast<uintptr_t>(hist_out) & 3)) return VRENB200_EALIGN;
+    cudaStream_t s = as_stream(stream);
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(hist_out, 0, sizeof(uint32_t) * kPasses * kRadix, s)));
+    if (n == 0) return VRENB200_OK;
+    // the kernel addresses its output through sort_control::hist
+    sort_control* fake = reinterpret_cast<sort_control*>(reinterpret_cast<char*>(hist_out) - offsetof(sort_control, hist));
+    radix_histogram_kernel<<<kNumSMs * 2, kHistThreads, 0, s>>>(keys, n, fake);
+    return check_launch();
+}
+
+extern "C" size_t vrenb200_radix_sort_range_scratch_bytes(uint32_t n) { return control_bytes(n); }
+
+// stable sort by the digits [first_pass, first_pass + num_passes) only (8 bits each, pass 0 = least significant).
+// Ping-pongs between (keys, values) and (alt_keys, alt_values); *result_in_alt = num_passes & 1. values may be NULL.
+extern "C" int vrenb200_radix_sort_pairs_range(vrenb200_stream_t stream, uint32_t* keys, uint32_t* values, uint32_t* alt_keys,
+                                               uint32_t* alt_values, uint32_t n, int first_pass, int num_passes,
+                                               void* scratch, size_t scratch_bytes, int* result_in_alt)
+{
+    if (first_pass < 0 || num_passes < 1 || first_pass + num_passes > kPasses) return VRENB200_EINVAL_ARG;
+    if (result_in_alt) *result_in_alt = num_passes & 1;
+    if (n == 0) return VRENB200_OK;
+    if (keys == nullptr || alt_keys == nullptr || ((values == nullptr) != (alt_values == nullptr))) return VRENB200_EINVAL_ARG;
+    if (scratch == nullptr || scratch_bytes < control_bytes(n)) return VRENB200_ESCRATCH;
+    return radix_sort_impl(as_stream(stream), keys, values, n, alt_keys, alt_values, scratch, nullptr, first_pass, num_passes);
 }
 
 extern "C" size_t vrenb200_radix_sort_scratch_buffer_1_bytes(uint32_t n) { return control_bytes(n); }

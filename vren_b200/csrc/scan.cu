@@ -32,7 +32,7 @@ struct scan_state
 };
 
 __global__ void __launch_bounds__(kScanThreads)
-exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_state* state)
+exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_state* state, uint32_t base)
 {
     __shared__ uint32_t s_warp_total[kScanWarps];
     __shared__ uint32_t s_tile;
@@ -129,7 +129,7 @@ exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_st
         if (lane == 0) s_tile_prefix = exclusive;
     }
     __syncthreads();
-    const uint32_t prefix = s_tile_prefix + warp_prefix;
+    const uint32_t prefix = s_tile_prefix + warp_prefix + base;
 
 #pragma unroll
     for (int v = 0; v < kScanVecs; v++)
@@ -193,6 +193,13 @@ extern "C" size_t vrenb200_scan_scratch_bytes(uint32_t n)
 extern "C" int vrenb200_exclusive_scan_u32(vrenb200_stream_t stream, const uint32_t* in, uint32_t* out, uint32_t n,
                                            void* scratch, size_t scratch_bytes)
 {
+    return vrenb200_exclusive_scan_u32_base(stream, in, out, n, 0u, scratch, scratch_bytes);
+}
+
+// out[i] = base + sum_{k<i} in[k]: the local step of the sharded scan (base = total of the lower ranks)
+extern "C" int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const uint32_t* in, uint32_t* out, uint32_t n,
+                                                uint32_t base, void* scratch, size_t scratch_bytes)
+{
     if (in == nullptr || out == nullptr) return VRENB200_EINVAL_ARG;
     if (n == 0) return VRENB200_EINVAL_LENGTH;
     const size_t need = vrenb200_scan_scratch_bytes(n);
@@ -201,7 +208,7 @@ extern "C" int vrenb200_exclusive_scan_u32(vrenb200_stream_t stream, const uint3
     cudaStream_t s = as_stream(stream);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, need, s)));
     const uint32_t tiles = (uint32_t) (((size_t) n + kScanTile - 1) / kScanTile);
-    exclusive_scan_u32_kernel<<<tiles, kScanThreads, 0, s>>>(in, out, n, static_cast<scan_state*>(scratch));
+    exclusive_scan_u32_kernel<<<tiles, kScanThreads, 0, s>>>(in, out, n, static_cast<scan_state*>(scratch), base);
     return check_launch();
 }
 

@@ -1,0 +1,145 @@
+"""Multi-GPU (one process per GPU, torch.distributed) versions of the primitives that shard — SURVEY 8e.
+
+The reference is single-device; this is new work specified by the north-star:
+  * sharded_sort_pairs  : every rank holds n_r pairs.  Local top-digit histogram -> all_gather -> contiguous digit
+                          ranges per rank (balanced by count) -> stable local partition by the top digit (one
+                          onesweep pass) -> all-to-all-v of keys and values over NVLink (NCCL) -> local 4-pass
+                          onesweep of the received pairs.  Concatenating the ranks' outputs in rank order gives the
+                          stable sort of the concatenated input.
+  * sharded_exclusive_scan : local reduce -> all_gather of the partial sums -> local scan with base.
+  * views are independent: batched clustered shading needs no exchange (one view per rank, see bench.py).
+
+The collective plumbing is backend-agnostic (NCCL on GPUs, gloo in the CPU tests); the local compute steps come from
+a `LocalOps` object.  The product `CudaOps` calls the C ABI; tests may inject a numpy stand-in to exercise the
+exchange logic on CPU.  There is no CPU fallback in this module: without CUDA, `CudaOps()` raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+class CudaOps:
+    """local steps on the current CUDA device through libvrenb200.so"""
+
+    def __init__(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vren_b200.dist.CudaOps needs a CUDA device (no CPU fallback)")
+        from . import lib as vlib
+
+        self.vlib = vlib
+        self.lib = vlib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def digit_histograms(self, keys: torch.Tensor) -> torch.Tensor:
+        hist = torch.empty(4, 256, dtype=torch.int32, device=keys.device)
+        self.vlib.check(self.lib.vrenb200_radix_digit_histograms(self._stream(), keys.data_ptr(), keys.numel(), hist.data_ptr()),
+                        "radix_digit_histograms")
+        return hist
+
+    def partition_by_top_digit(self, keys: torch.Tensor, vals: torch.Tensor):
+        """stable partition by bits 24..31 (one onesweep pass); returns new tensors"""
+        n = keys.numel()
+        ok, ov = torch.empty_like(keys), torch.empty_like(vals)
+        sb = self.lib.vrenb200_radix_sort_range_scratch_bytes(n)
+        scratch = torch.empty(max(sb, 256), dtype=torch.uint8, device=keys.device)
+        self.vlib.check(self.lib.vrenb200_radix_sort_pairs_range(self._stream(), keys.data_ptr(), vals.data_ptr(), ok.data_ptr(), ov.data_ptr(),
+                                                                 n, 3, 1, scratch.data_ptr(), sb, None), "radix_sort_pairs_range")
+        return ok, ov
+
+    def sort_pairs(self, keys: torch.Tensor, vals: torch.Tensor):
+        self.vlib.radix_sort_pairs(keys, vals)
+        return keys, vals
+
+    def reduce_add(self, x: torch.Tensor) -> int:
+        n = x.numel()
+        out = self.vlib.reduce(x, n, "u32", "add", mode="final")
+        P = self.lib.vrenb200_round_to_next_power_of_2(n)
+        return int(out[P - 1].item()) & 0xFFFFFFFF
+
+    def exclusive_scan(self, x: torch.Tensor, base: int) -> torch.Tensor:
+        n = x.numel()
+        sb = self.lib.vrenb200_scan_scratch_bytes(n)
+        scratch = torch.empty(max(sb, 256), dtype=torch.uint8, device=x.device)
+        self.vlib.check(self.lib.vrenb200_exclusive_scan_u32_base(self._stream(), x.data_ptr(), x.data_ptr(), n, base & 0xFFFFFFFF,
+                                                                  scratch.data_ptr(), sb), "exclusive_scan_u32_base")
+        return x
+
+
+@dataclass
+class SortPlan:
+    """what every rank derives from the gathered top-digit histograms (identical on all ranks)"""
+    digit_lo: list            # rank r owns top digits [digit_lo[r], digit_lo[r+1])
+    send_counts: list         # pairs this rank sends to each destination
+    recv_counts: list         # pairs this rank receives from each source
+
+
+def plan_digit_ranges(total_hist: torch.Tensor, world: int) -> list:
+    """split the 256 top digits into `world` contiguous ranges with (nearly) equal pair counts.
+    total_hist: int64[256] on CPU.  Returns world+1 boundaries, boundaries[0] = 0, boundaries[world] = 256."""
+    cum = torch.cumsum(total_hist, 0)
+    total = int(cum[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = (total * r + world - 1) // world
+        # first digit whose inclusive cumulative count reaches the target, rounded to the nearer boundary
+        d = int(torch.searchsorted(cum, torch.tensor(target, dtype=cum.dtype)).item())
+        d = min(max(d, bounds[-1]), 255)
+        before = int(cum[d - 1]) if d > 0 else 0
+        after = int(cum[d])
+        cut = d if (target - before) <= (after - target) else d + 1
+        bounds.append(min(max(cut, bounds[-1]), 256))
+    bounds.append(256)
+    return bounds
+
+
+def make_sort_plan(local_top_hist: torch.Tensor, group=None) -> SortPlan:
+    """local_top_hist: int64[256] on the rank's device (top-digit counts of the local keys)"""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    gathered = [torch.empty_like(local_top_hist) for _ in range(world)]
+    dist.all_gather(gathered, local_top_hist, group=group)
+    hists = torch.stack(gathered).cpu()                      # [world, 256]
+    bounds = plan_digit_ranges(hists.sum(0), world)
+    per_dest = torch.stack([hists[:, bounds[r]:bounds[r + 1]].sum(1) for r in range(world)], dim=1)   # [src, dst]
+    return SortPlan(bounds, [int(v) for v in per_dest[rank]], [int(v) for v in per_dest[:, rank]])
+
+
+def sharded_sort_pairs(keys: torch.Tensor, vals: torch.Tensor, ops=None, group=None):
+    """globally stable sort by key of the pairs held by all ranks.  keys/vals: int32 storage of uint32 values.
+    Returns (keys_out, vals_out, plan): rank r holds the pairs whose top digit falls in its range, sorted."""
+    ops = ops or CudaOps()
+    hist = ops.digit_histograms(keys)
+    plan = make_sort_plan(hist[3].to(torch.int64), group)
+    pk, pv = ops.partition_by_top_digit(keys, vals)
+    n_recv = sum(plan.recv_counts)
+    rk = torch.empty(n_recv, dtype=keys.dtype, device=keys.device)
+    rv = torch.empty(n_recv, dtype=vals.dtype, device=vals.device)
+    dist.all_to_all_single(rk, pk, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts, group=group)
+    dist.all_to_all_single(rv, pv, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts, group=group)
+    ops.sort_pairs(rk, rv)
+    return rk, rv, plan
+
+
+def sharded_exclusive_scan(x: torch.Tensor, ops=None, group=None) -> torch.Tensor:
+    """in-place exclusive add-scan (mod 2^32) of the concatenation of every rank's `x` (rank order)"""
+    ops = ops or CudaOps()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    total = torch.tensor([ops.reduce_add(x)], dtype=torch.int64, device=x.device)
+    gathered = [torch.empty_like(total) for _ in range(world)]
+    dist.all_gather(gathered, total, group=group)
+    base = sum(int(t.item()) for t in gathered[:rank]) & 0xFFFFFFFF
+    return ops.exclusive_scan(x, base)
+
+
+def sharded_reduce_add(x: torch.Tensor, ops=None, group=None) -> int:
+    ops = ops or CudaOps()
+    total = torch.tensor([ops.reduce_add(x)], dtype=torch.int64, device=x.device)
+    dist.all_reduce(total, group=group)
+    return int(total.item()) & 0xFFFFFFFF
