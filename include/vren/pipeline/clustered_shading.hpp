@@ -118,7 +118,7 @@ namespace vren
                             vren::vk_utils::buffer const& view_space_point_light_position_buffer, uint32_t* status_out = nullptr)
             {
                 const uint32_t max_keys = (uint32_t) (assigned_light_counts_buffer.m_size / 4);
-                const size_t bytes = vrenb200_assign_lights_scratch_bytes(max_keys);
+                const size_t bytes = vrenb200_assign_lights_scratch_bytes(max_keys, (uint32_t) (assigned_light_indices_buffer.m_size / 4));
                 void* scratch = m_scratch.reserve(bytes);
                 const vrenb200_camera cam = camera.abi();
                 check_status(vrenb200_assign_lights((vrenb200_stream_t) command_buffer, screen.x, screen.y, &cam, cluster_key_buffer.ptr<uint32_t>(),

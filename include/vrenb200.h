@@ -187,7 +187,7 @@ int vrenb200_find_unique_clusters(vrenb200_stream_t stream,
                                   uint32_t* cluster_ref,
                                   void* scratch, size_t scratch_bytes);
 
-size_t vrenb200_assign_lights_scratch_bytes(uint32_t max_keys);
+size_t vrenb200_assign_lights_scratch_bytes(uint32_t max_keys, uint32_t max_assigned);
 /* counts/offsets: uint[max_keys]; indices: uint[max_assigned] (assign_lights.comp:121-241,
  * clustered_shading.cpp:473-690). status_out (device uint[4], may be NULL):
  * {total_assigned, overflow_flag, node_visits, leaf_tests} */

@@ -69,6 +69,8 @@ struct light_leaf_source
     const float4* view_pos;
     const float4* lights;    // point_light {vec3 color; float intensity}
     uint32_t light_count;
+    float4* leaf_spheres;    // out (may be null): {view_pos.xyz, (max.x - min.x) / 2} per leaf, the operands of the
+                             // leaf test of assign_lights.comp:97-102,209-214 in 16 B instead of 56 B
 };
 
 template <bool FROM_LIGHTS>
@@ -93,6 +95,8 @@ build_bvh_kernel(vrenb200_bvh_node* nodes, uint32_t padded_leaf_count, light_lea
                 const float r = src.lights[l].w;
                 c.lo = make_float4(__fsub_rn(p.x, r), __fsub_rn(p.y, r), __fsub_rn(p.z, r), __uint_as_float(kLeaf));
                 c.hi = make_float4(__fadd_rn(p.x, r), __fadd_rn(p.y, r), __fadd_rn(p.z, r), __uint_as_float(0u));
+                if (src.leaf_spheres)
+                    src.leaf_spheres[i] = make_float4(p.x, p.y, p.z, __fdiv_rn(__fsub_rn(c.hi.x, c.lo.x), 2.0f));
             }
             else
             {
@@ -159,10 +163,10 @@ int launch_build(cudaStream_t s, vrenb200_bvh_node* nodes, uint32_t padded, cons
 
 // used by light_bvh.cu
 int build_light_bvh_fused(cudaStream_t s, vrenb200_bvh_node* nodes, uint32_t padded, const void* sorted_pairs,
-                          const float* view_pos, const float* lights, uint32_t light_count)
+                          const float* view_pos, const float* lights, uint32_t light_count, void* leaf_spheres)
 {
     light_leaf_source src{static_cast<const uint2*>(sorted_pairs), reinterpret_cast<const float4*>(view_pos),
-                          reinterpret_cast<const float4*>(lights), light_count};
+                          reinterpret_cast<const float4*>(lights), light_count, static_cast<float4*>(leaf_spheres)};
     return launch_build(s, nodes, padded, &src);
 }
 

@@ -11,10 +11,12 @@
 // Tile bases come from a decoupled look-back over tiles in tile-major order, which makes the list order
 // deterministic (the canonical order of the oracle).  One launch, 4 B/px read (+8 B/px normals) + 4 B/px written.
 //
-// a8: one warp per unique cluster walks the 32-ary light BVH with a per-level overlap bitmask (lane t tests child
-// t, lowest set bit first), leaf level = sphere vs box.  Count pass -> exclusive scan -> write pass, as the
-// reference, but with persistent warps and the single-pass scan; light order inside a list follows
-// assign_lights.comp:229-232 (descending lane inside a leaf group).
+// a8, reference: count traversal -> copy -> blelloch_scan(2^17) -> write traversal (the BVH is walked twice).
+// a8, here: ONE traversal per cluster.  A warp takes a cluster from a ticket, walks the 32-ary light BVH with a
+// per-level overlap bitmask (lane t tests child t, lowest set bit first; leaf level = sphere vs box on a compact
+// 16-byte leaf sphere), remembers the (leaf group, hit mask) pairs and writes the list - in the order of
+// assign_lights.comp:229-232, descending lane inside a leaf group - into a bump-allocated arena; the single-pass
+// scan of the counts gives the reference's offsets, and a copy kernel moves every list to its final place.
 //
 // fp32 contract: every op is an explicitly rounded _rn intrinsic in GLSL source order; tan/pow/log are evaluated
 // on the host once per camera (tables below) with the formulas stated in oracle/oracle_clustered.cpp.
@@ -173,7 +175,9 @@ __device__ __forceinline__ uint32_t discretize_normal(float nx, float ny, float 
     return (face_idx * 9u + dx * 3u + dy) & 0x3Fu;
 }
 
-__global__ void __launch_bounds__(1024)
+constexpr int kKeyThreads = 256;   // one CTA per 32x32 tile, 4 pixels (rows warp, warp+8, +16, +24) per thread
+
+__global__ void __launch_bounds__(kKeyThreads)
 find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const __grid_constant__ CUtensorMap normal_map,
                             const float* __restrict__ depth, const uint2* __restrict__ normals,
                             const float* __restrict__ thresholds, cluster_key_params prm,
@@ -183,75 +187,84 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
     __shared__ alignas(128) uint2 s_normal[32 * 32];
     __shared__ uint32_t s_bitmap[2048];
     __shared__ uint32_t s_prefix[2048];
-    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_warp[kKeyThreads / 32];
     __shared__ alignas(8) uint64_t s_bar;
-    __shared__ uint32_t s_tile, s_base;
+    __shared__ uint32_t s_base;
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0)
+    // tile id = block index: CTAs are dispatched in index order, so a tile only waits on tiles that already started
+    const uint32_t tile = blockIdx.x;
+    const uint32_t ti = tile % prm.tiles_x, tj = tile / prm.tiles_x;   // canonical tile-major order
+    const bool interior = (ti << 5) + 32 <= prm.width && (tj << 5) + 32 <= prm.height;
+    const bool tma = prm.use_tma && interior;
+    if (tid == 0 && tma)
     {
-        s_tile = atomicAdd(&state->ticket, 1u);
         mbar_init(&s_bar, 1);
         mbar_fence_init();
+        mbar_arrive_expect_tx(&s_bar, 32 * 32 * 4 + (prm.has_normals ? 32 * 32 * 8 : 0));
+        tma_load_2d(s_depth, &depth_map, (int) (ti << 5), (int) (tj << 5), &s_bar);
+        if (prm.has_normals) tma_load_2d(s_normal, &normal_map, (int) (ti << 5), (int) (tj << 5), &s_bar);
     }
-    s_bitmap[tid] = 0;
-    s_bitmap[tid + 1024] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s_bitmap[tid + i * kKeyThreads] = 0;
     __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t ti = tile % prm.tiles_x, tj = tile / prm.tiles_x;   // canonical tile-major order
-    const uint32_t x = (ti << 5) + lane, y = (tj << 5) + warp;         // local invocation (lane, warp)
-    const bool interior = (ti << 5) + 32 <= prm.width && (tj << 5) + 32 <= prm.height;
+    if (tma) mbar_wait(&s_bar, 0);
 
-    float d;
-    uint2 nraw = make_uint2(0u, 0u);
-    if (prm.use_tma && interior)
+    uint32_t sub[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
     {
-        if (tid == 0)
+        const uint32_t row = warp + 8 * r;
+        const uint32_t x = (ti << 5) + lane, y = (tj << 5) + row;      // local invocation (lane, row)
+        float d;
+        uint2 nraw = make_uint2(0u, 0u);
+        if (tma)
         {
-            mbar_arrive_expect_tx(&s_bar, 32 * 32 * 4 + (prm.has_normals ? 32 * 32 * 8 : 0));
-            tma_load_2d(s_depth, &depth_map, (int) (ti << 5), (int) (tj << 5), &s_bar);
-            if (prm.has_normals) tma_load_2d(s_normal, &normal_map, (int) (ti << 5), (int) (tj << 5), &s_bar);
+            d = s_depth[row * 32 + lane];
+            if (prm.has_normals) nraw = s_normal[row * 32 + lane];
         }
-        mbar_wait(&s_bar, 0);
-        d = s_depth[tid];
-        if (prm.has_normals) nraw = s_normal[tid];
+        else
+        {
+            // partial tiles wrap like the reference's REPEAT sampler (gbuffer.cpp:28-34)
+            const uint32_t sx = x % prm.width, sy = y % prm.height;
+            d = depth[(size_t) sy * prm.width + sx];
+            if (prm.has_normals) nraw = normals[(size_t) sy * prm.width + sx];
+        }
+        // view-space depth and slice (find_unique_clusters.comp:48-65)
+        const float w = __fadd_rn(__fmul_rn(d, prm.iB), __fmul_rn(1.0f, prm.nAB));
+        const float z = __fdiv_rn(1.0f, w);
+        uint32_t k = 0;
+        if (z > 0.0f)
+        {
+            const float zc = fminf(z, 3.4028234e38f);
+            int g = (int) (__log2f(zc * prm.inv_near) * prm.inv_log2a);
+            g = max(0, min(g, (int) prm.table_len - 1));
+            while (g > 0 && zc < __ldg(&thresholds[g])) g--;
+            while (g + 1 < (int) prm.table_len && zc >= __ldg(&thresholds[g + 1])) g++;
+            k = (uint32_t) g;
+        }
+        uint32_t nb = 0xFFFFFFFFu;
+        if (prm.has_normals)
+        {
+            const __half2 h01 = *reinterpret_cast<const __half2*>(&nraw.x);
+            const __half2 h23 = *reinterpret_cast<const __half2*>(&nraw.y);
+            nb = discretize_normal(__low2float(h01), __high2float(h01), __low2float(h23));
+        }
+        sub[r] = ((nb & 0x3Fu) << 10) | (k & 0x3FFu);   // key bits 16..31
+        atomicOr(&s_bitmap[sub[r] >> 5], 1u << (sub[r] & 31));
     }
-    else
-    {
-        // partial tiles wrap like the reference's REPEAT sampler (gbuffer.cpp:28-34)
-        const uint32_t sx = x % prm.width, sy = y % prm.height;
-        d = depth[(size_t) sy * prm.width + sx];
-        if (prm.has_normals) nraw = normals[(size_t) sy * prm.width + sx];
-    }
-
-    // view-space depth and slice (find_unique_clusters.comp:48-65)
-    const float w = __fadd_rn(__fmul_rn(d, prm.iB), __fmul_rn(1.0f, prm.nAB));
-    const float z = __fdiv_rn(1.0f, w);
-    uint32_t k = 0;
-    if (z > 0.0f)
-    {
-        const float zc = fminf(z, 3.4028234e38f);
-        int g = (int) (__log2f(zc * prm.inv_near) * prm.inv_log2a);
-        g = max(0, min(g, (int) prm.table_len - 1));
-        while (g > 0 && zc < thresholds[g]) g--;
-        while (g + 1 < (int) prm.table_len && zc >= thresholds[g + 1]) g++;
-        k = (uint32_t) g;
-    }
-    uint32_t nb = 0xFFFFFFFFu;
-    if (prm.has_normals)
-    {
-        const __half2 h01 = *reinterpret_cast<const __half2*>(&nraw.x);
-        const __half2 h23 = *reinterpret_cast<const __half2*>(&nraw.y);
-        nb = discretize_normal(__low2float(h01), __high2float(h01), __low2float(h23));
-    }
-    const uint32_t sub = ((nb & 0x3Fu) << 10) | (k & 0x3FFu);   // key bits 16..31
-    atomicOr(&s_bitmap[sub >> 5], 1u << (sub & 31));
     __syncthreads();
 
-    // popcount prefix over the 2048 bitmap words: thread t owns words 2t, 2t+1
-    const uint32_t w0 = s_bitmap[2 * tid], w1 = s_bitmap[2 * tid + 1];
-    const uint32_t c0 = __popc(w0), c01 = c0 + __popc(w1);
-    uint32_t inc = c01;
+    // popcount prefix over the 2048 bitmap words: thread t owns words 8t .. 8t+7
+    uint32_t words[8], local[8], mine = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        words[i] = s_bitmap[8 * tid + i];
+        local[i] = mine;
+        mine += __popc(words[i]);
+    }
+    uint32_t inc = mine;
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1)
     {
@@ -260,22 +273,17 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
     }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    if (warp == 0)
-    {
-        uint32_t v = s_warp[lane];
+    uint32_t warp_prefix = 0, unique = 0;
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1)
-        {
-            const uint32_t t = __shfl_up_sync(kFullMask, v, s);
-            if (lane >= (unsigned) s) v += t;
-        }
-        s_warp[lane] = v; // inclusive over warps
+    for (int w = 0; w < kKeyThreads / 32; w++)
+    {
+        const uint32_t t = s_warp[w];
+        if (w < (int) warp) warp_prefix += t;
+        unique += t;
     }
-    __syncthreads();
-    const uint32_t excl = inc - c01 + (warp > 0 ? s_warp[warp - 1] : 0u);
-    s_prefix[2 * tid] = excl;
-    s_prefix[2 * tid + 1] = excl + c0;
-    const uint32_t unique = s_warp[31];
+    const uint32_t excl = warp_prefix + inc - mine;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s_prefix[8 * tid + i] = excl + local[i];
 
     // decoupled look-back across tiles (tile-major order)
     if (warp == 0)
@@ -320,28 +328,29 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
     const uint32_t base = s_base;
 
     // per-pixel cluster reference (imageStore, find_unique_clusters.comp:113-120); out-of-image pixels are dropped
-    const uint32_t word = s_bitmap[sub >> 5];
-    const uint32_t r = base + s_prefix[sub >> 5] + __popc(word & ((1u << (sub & 31)) - 1u));
-    if (x < prm.width && y < prm.height) cluster_ref[(size_t) y * prm.width + x] = r;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        const uint32_t x = (ti << 5) + lane, y = (tj << 5) + warp + 8 * r;
+        const uint32_t word = s_bitmap[sub[r] >> 5];
+        const uint32_t ref = base + s_prefix[sub[r] >> 5] + __popc(word & ((1u << (sub[r] & 31)) - 1u));
+        if (x < prm.width && y < prm.height) cluster_ref[(size_t) y * prm.width + x] = ref;
+    }
 
     // unique keys, ascending inside the tile
     const uint32_t tile_bits = (ti & 0xFFu) | ((tj & 0xFFu) << 8);
     uint32_t out = base + excl;
-    uint32_t bits = w0;
-    while (bits)
+#pragma unroll
+    for (int i = 0; i < 8; i++)
     {
-        const uint32_t b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        if (out < prm.max_keys) keys_out[out] = tile_bits | (((2 * tid) * 32 + b) << 16);
-        out++;
-    }
-    bits = w1;
-    while (bits)
-    {
-        const uint32_t b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        if (out < prm.max_keys) keys_out[out] = tile_bits | (((2 * tid + 1) * 32 + b) << 16);
-        out++;
+        uint32_t bits = words[i];
+        while (bits)
+        {
+            const uint32_t b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (out < prm.max_keys) keys_out[out] = tile_bits | (((8 * tid + i) * 32 + b) << 16);
+            out++;
+        }
     }
 }
 
@@ -389,19 +398,136 @@ __device__ __forceinline__ void cluster_aabb(uint32_t key, const assign_params& 
 
 constexpr int kAssignThreads = 256;
 constexpr int kAssignWarps = kAssignThreads / 32;
+constexpr int kHitCap = 96;    // leaf groups with hits remembered per cluster before falling back to a second walk
 
-template <bool WRITE>
+struct assign_state
+{
+    uint32_t ticket;        // next cluster to process (dynamic: balances the very uneven per-cluster work)
+    uint32_t arena_top;     // bump allocator over the arena of provisional light lists
+    uint32_t _pad[62];
+};
+
+// One walk of the light BVH for one cluster (assign_lights.comp:121-241).  Warp-uniform control flow.
+//   write == false: counts hits, remembers (leaf group, hit mask) in `hits` (up to kHitCap entries)
+//   write == true : writes the light indices at out_base in traversal order, descending lane inside a group
+struct walk_result { uint32_t total, groups; };
+
+__device__ __forceinline__ walk_result walk_cluster(const float3x& cmin, const float3x& cmax, const float4* __restrict__ bvh,
+                                                    const float4* __restrict__ spheres, const uint2* __restrict__ sorted_pairs,
+                                                    const assign_params& prm, const uint32_t* level_base, uint32_t* ov, uint2* hits,
+                                                    bool write, uint32_t out_base, uint32_t* indices,
+                                                    uint32_t& stat_nodes, uint32_t& stat_leaves)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned ge = lanemask_ge();
+    uint32_t running = 0, groups = 0;
+    uint32_t level = 0, idx = 0; // idx = index of the current 32-group inside its level
+    bool enter = true;
+    while (true)
+    {
+        if (enter)
+        {
+            uint32_t lb = level_base[0];
+#pragma unroll
+            for (int l = 1; l < kMaxBvhLevels; l++)
+                if ((int) level == l) lb = level_base[l];
+            const uint32_t addr = lb + idx * 32 + lane;
+            if (level + 1 < prm.levels)
+            {
+                // test_aabb_aabb(cluster_min, cluster_max, node.min, node.max), assign_lights.comp:84-94
+                const float4 lo = bvh[2 * (size_t) addr], hi = bvh[2 * (size_t) addr + 1];
+                const bool valid = __float_as_uint(lo.w) != kInvalid;
+                const bool overlap = valid && cmax.v[0] >= lo.x && cmin.v[0] <= hi.x && cmax.v[1] >= lo.y &&
+                                     cmin.v[1] <= hi.y && cmax.v[2] >= lo.z && cmin.v[2] <= hi.z;
+                const unsigned mask = __ballot_sync(kFullMask, overlap);
+                stat_nodes += 32;
+                if (mask == 0) enter = false; // POP
+                else
+                {
+                    if (lane == 0) ov[level] = mask;
+                    __syncwarp();
+                    idx = idx * 32 + (__ffs(mask) - 1);
+                    level++;
+                }
+            }
+            else
+            {
+                // leaf group: sphere (light) vs cluster box, assign_lights.comp:97-102,209-214.  The sphere
+                // {view_pos.xyz, (max.x - min.x)/2} was precomputed per leaf by the light-BVH build (same fp32 ops).
+                bool hit = false;
+                if (addr < prm.light_count)
+                {
+                    const float4 o = spheres[addr];
+                    const float oc[3] = {o.x, o.y, o.z};
+                    float q[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                    {
+                        const float m = cmax.v[k] < oc[k] ? cmax.v[k] : oc[k];     // min(o, cmax)
+                        const float t = cmin.v[k] < m ? m : cmin.v[k];             // max(cmin, .)
+                        q[k] = __fsub_rn(t, oc[k]);
+                    }
+                    const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q[0], q[0]), __fmul_rn(q[1], q[1])), __fmul_rn(q[2], q[2])));
+                    hit = dist < o.w;
+                }
+                const unsigned mask = __ballot_sync(kFullMask, hit);
+                stat_leaves += 32;
+                if (mask != 0)
+                {
+                    if (write)
+                    {
+                        if (hit)
+                        {
+                            const uint32_t slot = out_base + running + (__popc(mask & ge) - 1);   // descending lane order
+                            if (slot < prm.max_assigned) indices[slot] = sorted_pairs[addr].y;
+                        }
+                    }
+                    else
+                    {
+                        if (groups < (uint32_t) kHitCap && lane == 0) hits[groups] = make_uint2(addr, mask);
+                        groups++;
+                    }
+                    running += __popc(mask);
+                }
+                enter = false; // POP
+            }
+        }
+        else
+        {
+            // POP then ADVANCE (assign_lights.comp:137-166): clear the lowest set bit of the parent level
+            if (level == 0) break;
+            level--;
+            idx >>= 5;
+            uint32_t m = ov[level];
+            m &= m - 1;
+            if (m != 0)
+            {
+                __syncwarp();
+                if (lane == 0) ov[level] = m;
+                __syncwarp();
+                idx = idx * 32 + (__ffs(m) - 1);
+                level++;
+                enter = true;
+            }
+        }
+    }
+    return walk_result{running, groups};
+}
+
+// Phase 1 — ONE traversal per cluster: count the hits, remember (leaf group, hit mask), bump-allocate the list in the
+// arena and write the light indices there in their final within-list order.
 __global__ void __launch_bounds__(kAssignThreads)
-assign_lights_kernel(const uint32_t* __restrict__ cluster_keys, const uint32_t* __restrict__ dispatch_params,
-                     const float4* __restrict__ bvh, const uint2* __restrict__ sorted_pairs,
-                     const float4* __restrict__ view_pos, const float* __restrict__ near_table, assign_params prm,
-                     uint32_t* counts, const uint32_t* __restrict__ offsets, uint32_t* indices, uint32_t* status_out)
+assign_lights_walk_kernel(const uint32_t* __restrict__ cluster_keys, const uint32_t* __restrict__ dispatch_params,
+                          const float4* __restrict__ bvh, const uint2* __restrict__ sorted_pairs, const float4* __restrict__ spheres,
+                          const float* __restrict__ near_table, assign_params prm, assign_state* state,
+                          uint32_t* counts, uint32_t* alloc, uint32_t* arena, uint32_t* status_out)
 {
     __shared__ uint32_t s_overlaps[kAssignWarps][kMaxBvhLevels];
+    __shared__ uint2 s_hits[kAssignWarps][kHitCap];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t count = min(dispatch_params[0], prm.max_keys);
-    const uint32_t total_warps = gridDim.x * kAssignWarps;
     uint32_t* ov = s_overlaps[warp];
+    uint2* hits = s_hits[warp];
     const unsigned ge = lanemask_ge();
 
     // level_base[l] = address of the first node of traversal level l (0 = children of the root)
@@ -416,111 +542,102 @@ assign_lights_kernel(const uint32_t* __restrict__ cluster_keys, const uint32_t* 
             level_base[l] = prm.bvh_root - acc;
         }
     }
-    uint32_t stat_nodes = 0, stat_leaves = 0, stat_total = 0;
+    uint32_t stat_nodes = 0, stat_leaves = 0;
 
-    for (uint32_t c = blockIdx.x * kAssignWarps + warp; c < count; c += total_warps)
+    while (true)
     {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(&state->ticket, 1u);
+        c = __shfl_sync(kFullMask, c, 0);
+        if (c >= count) break;
+
         float3x cmin, cmax;
         cluster_aabb(cluster_keys[c], prm, near_table, cmin, cmax);
-        const uint32_t out_base = WRITE ? offsets[c] : 0u;
-        uint32_t running = 0;
-
-        uint32_t level = 0, idx = 0; // idx = index of the current 32-group inside its level
-        bool enter = true;
-        while (true)
+        const walk_result r = walk_cluster(cmin, cmax, bvh, spheres, sorted_pairs, prm, level_base, ov, hits, false, 0u, nullptr,
+                                           stat_nodes, stat_leaves);
+        uint32_t at = 0;
+        if (lane == 0)
         {
-            if (enter)
-            {
-                uint32_t lb = level_base[0];
-#pragma unroll
-                for (int l = 1; l < kMaxBvhLevels; l++)
-                    if ((int) level == l) lb = level_base[l];
-                const uint32_t addr = lb + idx * 32 + lane;
-                const float4 lo = bvh[2 * (size_t) addr], hi = bvh[2 * (size_t) addr + 1];
-                if (level + 1 < prm.levels)
-                {
-                    // test_aabb_aabb(cluster_min, cluster_max, node.min, node.max), assign_lights.comp:84-94
-                    const bool valid = __float_as_uint(lo.w) != kInvalid;
-                    const bool overlap = valid && cmax.v[0] >= lo.x && cmin.v[0] <= hi.x && cmax.v[1] >= lo.y &&
-                                         cmin.v[1] <= hi.y && cmax.v[2] >= lo.z && cmin.v[2] <= hi.z;
-                    const unsigned mask = __ballot_sync(kFullMask, overlap);
-                    stat_nodes += 32;
-                    if (mask == 0) enter = false; // POP
-                    else
-                    {
-                        if (lane == 0) ov[level] = mask;
-                        __syncwarp();
-                        idx = idx * 32 + (__ffs(mask) - 1);
-                        level++;
-                    }
-                }
-                else
-                {
-                    // leaf group: sphere (light) vs cluster box, assign_lights.comp:97-102,209-214
-                    bool hit = false;
-                    uint32_t light = 0;
-                    if (addr < prm.light_count)
-                    {
-                        light = sorted_pairs[addr].y;
-                        const float4 o = view_pos[light];
-                        const float r = __fdiv_rn(__fsub_rn(hi.x, lo.x), 2.0f);
-                        const float oc[3] = {o.x, o.y, o.z};
-                        float q[3];
-#pragma unroll
-                        for (int k = 0; k < 3; k++)
-                        {
-                            const float m = cmax.v[k] < oc[k] ? cmax.v[k] : oc[k];     // min(o, cmax)
-                            const float t = cmin.v[k] < m ? m : cmin.v[k];             // max(cmin, .)
-                            q[k] = __fsub_rn(t, oc[k]);
-                        }
-                        const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q[0], q[0]), __fmul_rn(q[1], q[1])), __fmul_rn(q[2], q[2])));
-                        hit = dist < r;
-                    }
-                    const unsigned mask = __ballot_sync(kFullMask, hit);
-                    stat_leaves += 32;
-                    if (WRITE && hit)
-                    {
-                        const uint32_t slot = out_base + running + (__popc(mask & ge) - 1);   // descending lane order
-                        if (slot < prm.max_assigned) indices[slot] = light;
-                    }
-                    running += __popc(mask);
-                    enter = false; // POP
-                }
-            }
-            else
-            {
-                // POP then ADVANCE (assign_lights.comp:137-166): clear the lowest set bit of the parent level
-                if (level == 0) break;
-                level--;
-                idx >>= 5;
-                uint32_t m = ov[level];
-                m &= m - 1;
-                if (m != 0)
-                {
-                    __syncwarp();
-                    if (lane == 0) ov[level] = m;
-                    __syncwarp();
-                    idx = idx * 32 + (__ffs(m) - 1);
-                    level++;
-                    enter = true;
-                }
-            }
+            at = r.total ? atomicAdd(&state->arena_top, r.total) : 0u;
+            counts[c] = r.total;
+            alloc[c] = at;
         }
-        if (!WRITE && lane == 0) counts[c] = running;
-        stat_total += running;
+        at = __shfl_sync(kFullMask, at, 0);
+        if (r.total == 0 || (uint64_t) at + r.total > prm.max_assigned) continue;   // arena full: phase 3 re-walks everything
+        if (r.groups <= (uint32_t) kHitCap)
+        {
+            uint32_t running = 0;
+            for (uint32_t g = 0; g < r.groups; g++)
+            {
+                const uint2 h = hits[g];
+                if (h.y & (1u << lane)) arena[at + running + (__popc(h.y & ge) - 1)] = sorted_pairs[h.x + lane].y;
+                running += __popc(h.y);
+            }
+            __syncwarp();
+        }
+        else
+        {
+            assign_params local = prm;
+            local.max_assigned = 0xFFFFFFFFu; // bounds were checked against the arena above
+            uint32_t dummy_n = 0, dummy_l = 0;
+            walk_cluster(cmin, cmax, bvh, spheres, sorted_pairs, local, level_base, ov, hits, true, at, arena, dummy_n, dummy_l);
+        }
     }
-    if (!WRITE && status_out != nullptr && lane == 0)
+    if (status_out != nullptr && lane == 0)
     {
-        if (stat_total) atomicAdd(&status_out[0], stat_total);
         if (stat_nodes) atomicAdd(&status_out[2], stat_nodes);
         if (stat_leaves) atomicAdd(&status_out[3], stat_leaves);
     }
 }
 
-// overflow flag of the assigned-light list: total > max_assigned (reference overruns silently, config.hpp:24)
-__global__ void assign_overflow_kernel(uint32_t* status_out, uint32_t max_assigned)
+// Phase 3 — lists move from the arena to offsets[c] (exclusive scan of the counts in cluster-list order, phase 2).
+// If the arena overflowed (more hits than max_assigned) every cluster is walked again and written in place, clamped.
+__global__ void __launch_bounds__(kAssignThreads)
+assign_lights_place_kernel(const uint32_t* __restrict__ cluster_keys, const uint32_t* __restrict__ dispatch_params,
+                           const float4* __restrict__ bvh, const uint2* __restrict__ sorted_pairs, const float4* __restrict__ spheres,
+                           const float* __restrict__ near_table, assign_params prm, const assign_state* state,
+                           const uint32_t* __restrict__ counts, const uint32_t* __restrict__ alloc, const uint32_t* __restrict__ arena,
+                           const uint32_t* __restrict__ offsets, uint32_t* indices, uint32_t* status_out)
 {
-    if (status_out[0] > max_assigned) status_out[1] = 1;
+    __shared__ uint32_t s_overlaps[kAssignWarps][kMaxBvhLevels];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t count = min(dispatch_params[0], prm.max_keys);
+    const uint32_t total = state->arena_top;
+    const bool overflow = total > prm.max_assigned;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && status_out != nullptr)
+    {
+        status_out[0] = total;                 // reference overruns VREN_MAX_ASSIGNED_LIGHT_COUNT silently (config.hpp:24)
+        status_out[1] = overflow ? 1u : 0u;
+    }
+    const uint32_t total_warps = gridDim.x * kAssignWarps;
+    if (!overflow)
+    {
+        for (uint32_t c = blockIdx.x * kAssignWarps + warp; c < count; c += total_warps)
+        {
+            const uint32_t n = counts[c], src = alloc[c], dst = offsets[c];
+            for (uint32_t i = lane; i < n; i += 32) indices[dst + i] = arena[src + i];
+        }
+        return;
+    }
+    uint32_t level_base[kMaxBvhLevels];
+    {
+        uint32_t acc = 0, p = 1;
+#pragma unroll
+        for (int l = 0; l < kMaxBvhLevels; l++)
+        {
+            p *= 32;
+            acc += p;
+            level_base[l] = prm.bvh_root - acc;
+        }
+    }
+    for (uint32_t c = blockIdx.x * kAssignWarps + warp; c < count; c += total_warps)
+    {
+        float3x cmin, cmax;
+        cluster_aabb(cluster_keys[c], prm, near_table, cmin, cmax);
+        uint32_t dummy_n = 0, dummy_l = 0;
+        walk_cluster(cmin, cmax, bvh, spheres, sorted_pairs, prm, level_base, s_overlaps[warp], nullptr, true, offsets[c], indices,
+                     dummy_n, dummy_l);
+    }
 }
 
 // ---- tensor maps ----------------------------------------------------------------------------------------------------
@@ -605,14 +722,18 @@ extern "C" int vrenb200_find_unique_clusters(vrenb200_stream_t stream,
     std::memset(&nmap, 0, sizeof(nmap));
     prm.use_tma = make_tile_map(&dmap, depth, width, height, 4) &&
                   (!prm.has_normals || make_tile_map(&nmap, normals_rgba16f, width, height, 8));
-    find_unique_clusters_kernel<<<tiles_x * tiles_y, 1024, 0, s>>>(dmap, nmap, depth, static_cast<const uint2*>(normals_rgba16f),
+    find_unique_clusters_kernel<<<tiles_x * tiles_y, kKeyThreads, 0, s>>>(dmap, nmap, depth, static_cast<const uint2*>(normals_rgba16f),
                                                                  thresholds, prm, state, keys_out, dispatch_params, cluster_ref);
     return check_launch();
 }
 
-extern "C" size_t vrenb200_assign_lights_scratch_bytes(uint32_t max_keys)
+namespace vrenb200 { size_t light_leaf_sphere_offset(uint32_t light_count); }
+
+extern "C" size_t vrenb200_assign_lights_scratch_bytes(uint32_t max_keys, uint32_t max_assigned)
 {
-    return 1024 * sizeof(float) + vrenb200_scan_scratch_bytes(max_keys) + 256;
+    // near_k table | state | alloc[max_keys] | scan scratch | arena[max_assigned]
+    return 1024 * sizeof(float) + 256 + align_up((size_t) max_keys * 4, 256) + vrenb200_scan_scratch_bytes(max_keys) +
+           align_up((size_t) max_assigned * 4, 256);
 }
 
 extern "C" int vrenb200_assign_lights(vrenb200_stream_t stream,
@@ -632,7 +753,7 @@ extern "C" int vrenb200_assign_lights(vrenb200_stream_t stream,
     if (status_out) VRENB200_TRY(check_cuda(cudaMemsetAsync(status_out, 0, 16, s)));
     if (light_count == 0) return VRENB200_OK;
     if (!bvh_buffer || !light_index_buffer || !view_pos) return VRENB200_EINVAL_ARG;
-    if (scratch == nullptr || scratch_bytes < vrenb200_assign_lights_scratch_bytes(max_keys)) return VRENB200_ESCRATCH;
+    if (scratch == nullptr || scratch_bytes < vrenb200_assign_lights_scratch_bytes(max_keys, max_assigned)) return VRENB200_ESCRATCH;
     if (reinterpret_cast<uintptr_t>(scratch) & 255) return VRENB200_EALIGN;
     const uint32_t levels = vrenb200_calc_bvh_level_count(light_count);
     if (levels > (uint32_t) kMaxBvhLevels) return VRENB200_ELIMIT;
@@ -650,27 +771,28 @@ extern "C" int vrenb200_assign_lights(vrenb200_stream_t stream,
     // near_k = near * pow(a, k), k < 1024 (clustered_shading.glsl:97) evaluated on the host with powf
     float near_host[1024];
     for (int k = 0; k < 1024; k++) near_host[k] = camera->near_plane * powf(prm.a, (float) k);
-    float* near_table = static_cast<float*>(scratch);
-    void* scan_scratch = static_cast<char*>(scratch) + 1024 * sizeof(float);
+    char* sp = static_cast<char*>(scratch);
+    float* near_table = reinterpret_cast<float*>(sp);
+    assign_state* state = reinterpret_cast<assign_state*>(sp + 1024 * sizeof(float));
+    uint32_t* alloc = reinterpret_cast<uint32_t*>(sp + 1024 * sizeof(float) + 256);
+    void* scan_scratch = sp + 1024 * sizeof(float) + 256 + align_up((size_t) max_keys * 4, 256);
     const size_t scan_bytes = vrenb200_scan_scratch_bytes(max_keys);
+    uint32_t* arena = reinterpret_cast<uint32_t*>(static_cast<char*>(scan_scratch) + scan_bytes);
     VRENB200_TRY(check_cuda(cudaMemcpyAsync(near_table, near_host, sizeof(near_host), cudaMemcpyHostToDevice, s)));
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(state, 0, sizeof(assign_state), s)));
 
     const float4* bvh = static_cast<const float4*>(bvh_buffer);
     const uint2* pairs = static_cast<const uint2*>(light_index_buffer);
-    const float4* vp = reinterpret_cast<const float4*>(view_pos);
+    // compact leaf spheres written by vrenb200_construct_point_light_bvh behind the bucket-sort counters
+    const float4* spheres = reinterpret_cast<const float4*>(static_cast<const char*>(light_index_buffer) + light_leaf_sphere_offset(light_count));
+    (void) view_pos; // its xyz live in the leaf spheres; kept in the signature like the reference (assign_lights.comp:72-75)
     const int grid = kNumSMs * 8;
-    assign_lights_kernel<false><<<grid, kAssignThreads, 0, s>>>(cluster_keys, dispatch_params, bvh, pairs, vp, near_table, prm,
-                                                               counts_out, nullptr, nullptr, status_out);
+    assign_lights_walk_kernel<<<grid, kAssignThreads, 0, s>>>(cluster_keys, dispatch_params, bvh, pairs, spheres, near_table, prm, state,
+                                                            counts_out, alloc, arena, status_out);
     VRENB200_TRY(check_launch());
     // copy counts -> offsets + blelloch_scan over all max_keys slots (clustered_shading.cpp:586-619), one pass here
     VRENB200_TRY(vrenb200_exclusive_scan_u32(stream, counts_out, offsets_out, max_keys, scan_scratch, scan_bytes));
-    assign_lights_kernel<true><<<grid, kAssignThreads, 0, s>>>(cluster_keys, dispatch_params, bvh, pairs, vp, near_table, prm,
-                                                              counts_out, offsets_out, indices_out, status_out);
-    VRENB200_TRY(check_launch());
-    if (status_out)
-    {
-        assign_overflow_kernel<<<1, 1, 0, s>>>(status_out, max_assigned);
-        VRENB200_TRY(check_launch());
-    }
-    return VRENB200_OK;
+    assign_lights_place_kernel<<<grid, kAssignThreads, 0, s>>>(cluster_keys, dispatch_params, bvh, pairs, spheres, near_table, prm, state,
+                                                             counts_out, alloc, arena, offsets_out, indices_out, status_out);
+    return check_launch();
 }

@@ -16,7 +16,8 @@
 namespace vrenb200 {
 
 int build_light_bvh_fused(cudaStream_t s, vrenb200_bvh_node* nodes, uint32_t padded, const void* sorted_pairs,
-                          const float* view_pos, const float* lights, uint32_t light_count);
+                          const float* view_pos, const float* lights, uint32_t light_count, void* leaf_spheres);
+size_t light_leaf_sphere_offset(uint32_t light_count);
 
 namespace {
 
@@ -133,11 +134,17 @@ extern "C" size_t vrenb200_light_bvh_buffer_bytes(uint32_t light_count)
     return std::max<size_t>(ref, vrenb200_light_bvh_scratch_bytes(light_count));
 }
 
+// the index buffer = bucket-sort output {sorted pairs | 65536 END offsets} followed by one compact leaf sphere per light
+size_t vrenb200::light_leaf_sphere_offset(uint32_t light_count)
+{
+    return align_up(vrenb200_bucket_sort_output_bytes(light_count), 256);
+}
+
 extern "C" size_t vrenb200_light_index_buffer_bytes(uint32_t light_count)
 {
     // clustered_shading.cpp:54-58 is smaller than what bucket_sort itself asserts (bucket_sort.cpp:84): take the max
     return std::max<size_t>(std::max<size_t>((size_t) light_count * 8, ((size_t) light_count + 2) * 16),
-                            vrenb200_bucket_sort_output_bytes(light_count));
+                            light_leaf_sphere_offset(light_count) + (size_t) light_count * 16);
 }
 
 extern "C" int vrenb200_construct_point_light_bvh(vrenb200_stream_t stream,
@@ -178,5 +185,6 @@ extern "C" int vrenb200_construct_point_light_bvh(vrenb200_stream_t stream,
     VRENB200_TRY(check_launch());
     VRENB200_TRY(vrenb200_bucket_sort(stream, pairs, light_count, index_buffer, sort_scratch, sort_scratch_bytes));
     const uint32_t padded = vrenb200_calc_bvh_padded_leaf_count(light_count);
-    return build_light_bvh_fused(s, static_cast<vrenb200_bvh_node*>(bvh_buffer), padded, index_buffer, view_pos, lights, light_count);
+    return build_light_bvh_fused(s, static_cast<vrenb200_bvh_node*>(bvh_buffer), padded, index_buffer, view_pos, lights, light_count,
+                                 static_cast<char*>(index_buffer) + light_leaf_sphere_offset(light_count));
 }

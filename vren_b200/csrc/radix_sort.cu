@@ -529,14 +529,14 @@ int launch_onesweep(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const u
 
 #define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B> }
 const sort_variant g_variants[] = {
-    VARIANT(512, 16, MATCH_BALLOT, 2),   // 0: default
+    VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),   // 0: default (best of the sweeps in profiles/)
+    VARIANT(256, 24, MATCH_BALLOT, 3),       // ticket instead of block index
     VARIANT(512, 16, TILE_BY_BLOCKIDX, 2),
-    VARIANT(384, 16, TILE_BY_BLOCKIDX, 2),
-    VARIANT(256, 16, TILE_BY_BLOCKIDX, 3),
-    VARIANT(256, 16, TILE_BY_BLOCKIDX, 4),
     VARIANT(384, 20, TILE_BY_BLOCKIDX, 2),
-    VARIANT(512, 20, TILE_BY_BLOCKIDX, 1),
-    VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),
+    VARIANT(256, 16, TILE_BY_BLOCKIDX, 4),
+    VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),
+    VARIANT(256, 20, TILE_BY_BLOCKIDX, 3),
+    VARIANT(256, 24, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 3),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile

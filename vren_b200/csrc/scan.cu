@@ -3,8 +3,8 @@
 //
 // operator(): exclusive add-scan of uint32 (mod 2^32).  The reference runs reduce (up-sweep) + one strided
 // dispatch per level above 2^10 + a workgroup pass (~22 dispatches and ~3 round trips over the data at 2^28).
-// Here: ONE single-pass chained scan with decoupled look-back: each CTA scans a 4096-element tile held in
-// registers (128-bit loads, warp-shuffle scans), publishes {aggregate | inclusive prefix} in a 64-bit
+// Here: ONE single-pass chained scan with decoupled look-back: each CTA scans an 8192-element tile held in
+// registers (8 x 128-bit loads per thread, warp-shuffle scans), publishes {aggregate | inclusive prefix} in a 64-bit
 // status word, and a warp-wide look-back window resolves its exclusive prefix.  8 B/elt of HBM traffic.
 //
 // downsweep(): kept for API parity (radix_sort.cpp:281-289 calls it directly): takes an up-sweep TREE and
@@ -17,16 +17,17 @@ namespace {
 
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kScanVecs = 4;                                        // uint4 per thread
-constexpr uint32_t kScanTile = kScanThreads * kScanVecs * 4;        // 4096 elements
-constexpr uint32_t kWarpChunk = 32 * kScanVecs * 4;                 // 512 contiguous elements per warp
+constexpr int kScanVecs = 8;                                        // uint4 per thread
+constexpr uint32_t kScanTile = kScanThreads * kScanVecs * 4;        // 8192 elements
+constexpr uint32_t kWarpChunk = 32 * kScanVecs * 4;                 // 1024 contiguous elements per warp
 
 constexpr uint64_t kFlagAggregate = 1ull << 32;
 constexpr uint64_t kFlagInclusive = 2ull << 32;
 
 struct scan_state
 {
-    uint32_t ticket;      // dynamic tile id: guarantees a tile only waits on tiles that already started
+    uint32_t ticket;      // unused: tile id = block index (CTAs are dispatched in index order, so a tile only waits on
+                          // tiles that already started; saves an L2 atomic round trip before the first load)
     uint32_t _pad[63];
     uint64_t status[1];   // [tiles]
 };
@@ -35,12 +36,10 @@ __global__ void __launch_bounds__(kScanThreads)
 exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_state* state, uint32_t base)
 {
     __shared__ uint32_t s_warp_total[kScanWarps];
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_tile_prefix;
+    __shared__ uint32_t s_lb_sum[kScanWarps];
+    __shared__ uint32_t s_lb_found[kScanWarps];
 
-    if (threadIdx.x == 0) s_tile = atomicAdd(&state->ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = blockIdx.x;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t warp_base = (uint64_t) tile * kScanTile + warp * kWarpChunk;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
@@ -94,42 +93,50 @@ exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_st
         tile_total += t;
     }
 
-    // decoupled look-back, one warp, 32 predecessors per probe
-    if (warp == 0)
+    // decoupled look-back with a CTA-wide window: 256 predecessors per probe (thread i looks at tile-1-i), because
+    // with ~1000 tiles in flight a 32-wide window needs dozens of dependent L2 round trips per tile
+    uint64_t* status = state->status;
+    if (threadIdx.x == 0)
+        st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | tile_total);
+    uint32_t exclusive = 0;
+    if (tile > 0)
     {
-        uint64_t* status = state->status;
-        if (lane == 0)
-            st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | tile_total);
-        uint32_t exclusive = 0;
-        if (tile > 0)
+        int64_t window = (int64_t) tile - 1;
+        while (true)
         {
-            int64_t base = (int64_t) tile - 1;
-            while (true)
+            const int64_t t = window - threadIdx.x;
+            uint64_t s = kFlagInclusive; // virtual tile before tile 0: inclusive prefix 0
+            if (t >= 0)
             {
-                const int64_t t = base - lane;
-                uint64_t s = kFlagInclusive; // virtual tile before tile 0: inclusive prefix 0
-                if (t >= 0)
-                {
-                    do { s = ld_relaxed_u64(&status[t]); } while ((s >> 32) == 0);
-                }
-                const unsigned incl = __ballot_sync(kFullMask, (s >> 32) == 2);
-                uint32_t val = (uint32_t) s;
-                if (incl != 0)
-                {
-                    const unsigned first = __ffs(incl) - 1;
-                    if (lane > first) val = 0;
-                }
-                val = __reduce_add_sync(kFullMask, val);
-                exclusive += val;
-                if (incl != 0) break;
-                base -= 32;
+                do { s = ld_relaxed_u64(&status[t]); } while ((s >> 32) == 0);
             }
-            if (lane == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (exclusive + tile_total));
+            const unsigned incl = __ballot_sync(kFullMask, (s >> 32) == 2);
+            uint32_t val = (uint32_t) s;
+            if (incl != 0 && lane > (unsigned) (__ffs(incl) - 1)) val = 0;
+            val = __reduce_add_sync(kFullMask, val);
+            if (lane == 0)
+            {
+                s_lb_sum[warp] = val;
+                s_lb_found[warp] = incl != 0;
+            }
+            __syncthreads();
+            bool found = false;
+#pragma unroll
+            for (int w = 0; w < kScanWarps; w++)
+            {
+                if (!found)
+                {
+                    exclusive += s_lb_sum[w];
+                    found = s_lb_found[w] != 0;
+                }
+            }
+            __syncthreads();
+            if (found) break;
+            window -= kScanThreads;
         }
-        if (lane == 0) s_tile_prefix = exclusive;
+        if (threadIdx.x == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (exclusive + tile_total));
     }
-    __syncthreads();
-    const uint32_t prefix = s_tile_prefix + warp_prefix + base;
+    const uint32_t prefix = exclusive + warp_prefix + base;
 
 #pragma unroll
     for (int v = 0; v < kScanVecs; v++)

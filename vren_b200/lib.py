@@ -118,7 +118,7 @@ _LATE_SIGS = [
     ("vrenb200_find_unique_clusters_scratch_bytes", _sz, (_u32, _u32)),
     ("vrenb200_find_unique_clusters", _i32,
      (_vp, _vp, _vp, _u32, _u32, C.POINTER(Camera), _vp, _u32, _vp, _vp, _vp, _sz)),
-    ("vrenb200_assign_lights_scratch_bytes", _sz, (_u32,)),
+    ("vrenb200_assign_lights_scratch_bytes", _sz, (_u32, _u32)),
     ("vrenb200_assign_lights", _i32,
      (_vp, _u32, _u32, C.POINTER(Camera), _vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _sz)),
 ]
@@ -281,7 +281,7 @@ def assign_lights(width: int, height: int, camera: Camera, keys, disp, bvh, ligh
     offsets = torch.zeros(max_keys, dtype=torch.int32, device=dev)
     indices = torch.zeros(max_assigned, dtype=torch.int32, device=dev)
     status = torch.zeros(4, dtype=torch.int32, device=dev)
-    sb = lib.vrenb200_assign_lights_scratch_bytes(max_keys)
+    sb = lib.vrenb200_assign_lights_scratch_bytes(max_keys, max_assigned)
     scratch = _scratch(sb)
     root = lib.vrenb200_calc_bvh_root_index(light_count)
     check(lib.vrenb200_assign_lights(_stream(), width, height, C.byref(camera), _ptr(keys), _ptr(disp), max_keys, _ptr(bvh), root,

@@ -29,7 +29,7 @@ class ClusterAndShade:
         self.offsets = torch.empty(max_unique_cluster_keys, dtype=torch.int32, device=dev)
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
         self.scratch_keys = u8(self.lib.vrenb200_find_unique_clusters_scratch_bytes(max_width, max_height))
-        self.scratch_assign = u8(self.lib.vrenb200_assign_lights_scratch_bytes(max_unique_cluster_keys))
+        self.scratch_assign = u8(self.lib.vrenb200_assign_lights_scratch_bytes(max_unique_cluster_keys, max_assigned_lights))
 
     def __call__(self, width, height, camera: vlib.Camera, view16, depth, normals, positions, lights, light_count, stream=None):
         """enqueues steps 1-3 on the current stream; every argument is a device tensor or a scalar"""
