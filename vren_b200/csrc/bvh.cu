@@ -69,9 +69,20 @@ struct light_leaf_source
     const float4* view_pos;
     const float4* lights;    // point_light {vec3 color; float intensity}
     uint32_t light_count;
-    float4* leaf_spheres;    // out (may be null): {view_pos.xyz, (max.x - min.x) / 2} per leaf, the operands of the
-                             // leaf test of assign_lights.comp:97-102,209-214 in 16 B instead of 56 B
+    float4* leaf_spheres;    // out (may be null): {view_pos.xyz, T} per leaf with T = sq_threshold((max.x - min.x) / 2): the
+                             // operands of the leaf test of assign_lights.comp:97-102,209-214 in 16 B instead of 56 B
 };
+
+// smallest float s >= 0 with sqrt_rn(s) >= r.  sqrt_rn is monotone, so for every s >= 0:
+//   sqrt_rn(s) < r  <=>  s < sq_threshold(r)      (r <= 0 or NaN: never true -> 0)
+__device__ __forceinline__ float sq_threshold(float r)
+{
+    if (!(r > 0.0f)) return 0.0f;
+    uint32_t t = __float_as_uint(__fmul_rn(r, r));          // non-negative floats order like their bit patterns
+    while (t > 0 && __fsqrt_rn(__uint_as_float(t)) >= r) t--;
+    while (t < 0x7F800000u && __fsqrt_rn(__uint_as_float(t)) < r) t++;
+    return __uint_as_float(t);
+}
 
 template <bool FROM_LIGHTS>
 __global__ void __launch_bounds__(256)
@@ -96,7 +107,7 @@ build_bvh_kernel(vrenb200_bvh_node* nodes, uint32_t padded_leaf_count, light_lea
                 c.lo = make_float4(__fsub_rn(p.x, r), __fsub_rn(p.y, r), __fsub_rn(p.z, r), __uint_as_float(kLeaf));
                 c.hi = make_float4(__fadd_rn(p.x, r), __fadd_rn(p.y, r), __fadd_rn(p.z, r), __uint_as_float(0u));
                 if (src.leaf_spheres)
-                    src.leaf_spheres[i] = make_float4(p.x, p.y, p.z, __fdiv_rn(__fsub_rn(c.hi.x, c.lo.x), 2.0f));
+                    src.leaf_spheres[i] = make_float4(p.x, p.y, p.z, sq_threshold(__fdiv_rn(__fsub_rn(c.hi.x, c.lo.x), 2.0f)));
             }
             else
             {

@@ -188,8 +188,8 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
     __shared__ uint32_t s_bitmap[2048];
     __shared__ uint32_t s_prefix[2048];
     __shared__ uint32_t s_warp[kKeyThreads / 32];
+    __shared__ uint32_t s_found[kKeyThreads / 32];
     __shared__ alignas(8) uint64_t s_bar;
-    __shared__ uint32_t s_base;
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // tile id = block index: CTAs are dispatched in index order, so a tile only waits on tiles that already started
@@ -285,47 +285,60 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
 #pragma unroll
     for (int i = 0; i < 8; i++) s_prefix[8 * tid + i] = excl + local[i];
 
-    // decoupled look-back across tiles (tile-major order)
-    if (warp == 0)
+    // decoupled look-back across tiles (tile-major order) with a CTA-wide window: thread i probes tile-1-i, so the
+    // ~1000 tiles in flight resolve in a handful of L2 round trips instead of dozens
+    uint64_t* status = state->status;
+    if (tid == 0) st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | unique);
+    uint32_t base = 0;
+    if (tile > 0)
     {
-        uint64_t* status = state->status;
-        if (lane == 0) st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | unique);
-        uint32_t exclusive = 0;
-        if (tile > 0)
+        int64_t window = (int64_t) tile - 1;
+        while (true)
         {
-            int64_t base = (int64_t) tile - 1;
-            while (true)
+            const int64_t t = window - tid;
+            uint64_t sv = kFlagInclusive;
+            if (t >= 0)
             {
-                const int64_t t = base - lane;
-                uint64_t s = kFlagInclusive;
-                if (t >= 0)
+                do { sv = ld_relaxed_u64(&status[t]); } while ((sv >> 32) == 0);
+            }
+            const unsigned incl = __ballot_sync(kFullMask, (sv >> 32) == 2);
+            uint32_t val = (uint32_t) sv;
+            if (incl != 0 && lane > (unsigned) (__ffs(incl) - 1)) val = 0;
+            val = __reduce_add_sync(kFullMask, val);
+            __syncthreads();                       // s_warp / s_found are free again
+            if (lane == 0)
+            {
+                s_warp[warp] = val;
+                s_found[warp] = incl != 0;
+            }
+            __syncthreads();
+            bool found = false;
+#pragma unroll
+            for (int w = 0; w < kKeyThreads / 32; w++)
+            {
+                if (!found)
                 {
-                    do { s = ld_relaxed_u64(&status[t]); } while ((s >> 32) == 0);
+                    base += s_warp[w];
+                    found = s_found[w] != 0;
                 }
-                const unsigned incl = __ballot_sync(kFullMask, (s >> 32) == 2);
-                uint32_t val = (uint32_t) s;
-                if (incl != 0 && lane > (unsigned) (__ffs(incl) - 1)) val = 0;
-                exclusive += __reduce_add_sync(kFullMask, val);
-                if (incl != 0) break;
-                base -= 32;
             }
-            if (lane == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (exclusive + unique));
+            if (found) break;
+            window -= kKeyThreads;
         }
-        if (lane == 0)
+        if (tid == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (base + unique));
+    }
+    if (tid == 0)
+    {
+        if (base + unique > prm.max_keys) atomicOr(&dispatch_params[3], 1u);   // overflow, detected not silent
+        if (tile == prm.tiles_x * prm.tiles_y - 1)
         {
-            s_base = exclusive;
-            if (exclusive + unique > prm.max_keys) atomicOr(&dispatch_params[3], 1u);   // overflow, detected not silent
-            if (tile == prm.tiles_x * prm.tiles_y - 1)
-            {
-                // indirect-dispatch block of the reference: {count, 1, 1, _} (clustered_shading.cpp:386-394)
-                dispatch_params[0] = min(exclusive + unique, prm.max_keys);
-                dispatch_params[1] = 1;
-                dispatch_params[2] = 1;
-            }
+            // indirect-dispatch block of the reference: {count, 1, 1, _} (clustered_shading.cpp:386-394)
+            dispatch_params[0] = min(base + unique, prm.max_keys);
+            dispatch_params[1] = 1;
+            dispatch_params[2] = 1;
         }
     }
-    __syncthreads();
-    const uint32_t base = s_base;
+    __syncthreads();   // s_prefix complete
 
     // per-pixel cluster reference (imageStore, find_unique_clusters.comp:113-120); out-of-image pixels are dropped
 #pragma unroll
@@ -407,142 +420,121 @@ struct assign_state
     uint32_t _pad[62];
 };
 
-// One walk of the light BVH for one cluster (assign_lights.comp:121-241).  Warp-uniform control flow.
-//   write == false: counts hits, remembers (leaf group, hit mask) in `hits` (up to kHitCap entries)
-//   write == true : writes the light indices at out_base in traversal order, descending lane inside a group
-struct walk_result { uint32_t total, groups; };
-
-__device__ __forceinline__ walk_result walk_cluster(const float3x& cmin, const float3x& cmax, const float4* __restrict__ bvh,
-                                                    const float4* __restrict__ spheres, const uint2* __restrict__ sorted_pairs,
-                                                    const assign_params& prm, const uint32_t* level_base, uint32_t* ov, uint2* hits,
-                                                    bool write, uint32_t out_base, uint32_t* indices,
-                                                    uint32_t& stat_nodes, uint32_t& stat_leaves)
+// One walk of the light BVH for one cluster (assign_lights.comp:121-241), warp-uniform control flow.
+// The reference's state machine (ENTER / ADVANCE / POP over per-level overlap bitmasks) is a depth-first walk that
+// visits the set bits of every level lowest first; with the level count known at launch it unrolls into LEVELS nested
+// loops whose masks live in registers.
+//   WRITE == false: counts hits, remembers (leaf group, hit mask) in `hits` (up to kHitCap entries)
+//   WRITE == true : writes the light indices at out_base in traversal order, descending lane inside a group
+struct walk_ctx
 {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned ge = lanemask_ge();
-    uint32_t running = 0, groups = 0;
-    uint32_t level = 0, idx = 0; // idx = index of the current 32-group inside its level
-    bool enter = true;
-    while (true)
+    float cmin[3], cmax[3];
+    const float4* __restrict__ bvh;
+    const float4* __restrict__ spheres;
+    const uint2* __restrict__ sorted_pairs;
+    uint32_t level_base[kMaxBvhLevels];
+    uint32_t light_count, max_assigned;
+    uint2* hits;
+    uint32_t* out;
+    uint32_t out_base;
+    uint32_t running, groups;
+    uint32_t stat_nodes, stat_leaves;
+};
+
+template <int LEVEL, int LEVELS, bool WRITE>
+struct walker
+{
+    static __device__ __forceinline__ void visit(walk_ctx& c, uint32_t idx)
     {
-        if (enter)
+        const unsigned lane = threadIdx.x & 31;
+        const uint32_t addr = c.level_base[LEVEL] + idx * 32 + lane;
+        if constexpr (LEVEL + 1 < LEVELS)
         {
-            uint32_t lb = level_base[0];
-#pragma unroll
-            for (int l = 1; l < kMaxBvhLevels; l++)
-                if ((int) level == l) lb = level_base[l];
-            const uint32_t addr = lb + idx * 32 + lane;
-            if (level + 1 < prm.levels)
+            // test_aabb_aabb(cluster_min, cluster_max, node.min, node.max), assign_lights.comp:84-94
+            const float4 lo = c.bvh[2 * (size_t) addr], hi = c.bvh[2 * (size_t) addr + 1];
+            const bool overlap = __float_as_uint(lo.w) != kInvalid && c.cmax[0] >= lo.x && c.cmin[0] <= hi.x && c.cmax[1] >= lo.y &&
+                                 c.cmin[1] <= hi.y && c.cmax[2] >= lo.z && c.cmin[2] <= hi.z;
+            unsigned mask = __ballot_sync(kFullMask, overlap);
+            c.stat_nodes += 32;
+            while (mask != 0)
             {
-                // test_aabb_aabb(cluster_min, cluster_max, node.min, node.max), assign_lights.comp:84-94
-                const float4 lo = bvh[2 * (size_t) addr], hi = bvh[2 * (size_t) addr + 1];
-                const bool valid = __float_as_uint(lo.w) != kInvalid;
-                const bool overlap = valid && cmax.v[0] >= lo.x && cmin.v[0] <= hi.x && cmax.v[1] >= lo.y &&
-                                     cmin.v[1] <= hi.y && cmax.v[2] >= lo.z && cmin.v[2] <= hi.z;
-                const unsigned mask = __ballot_sync(kFullMask, overlap);
-                stat_nodes += 32;
-                if (mask == 0) enter = false; // POP
-                else
-                {
-                    if (lane == 0) ov[level] = mask;
-                    __syncwarp();
-                    idx = idx * 32 + (__ffs(mask) - 1);
-                    level++;
-                }
-            }
-            else
-            {
-                // leaf group: sphere (light) vs cluster box, assign_lights.comp:97-102,209-214.  The sphere
-                // {view_pos.xyz, (max.x - min.x)/2} was precomputed per leaf by the light-BVH build (same fp32 ops).
-                bool hit = false;
-                if (addr < prm.light_count)
-                {
-                    const float4 o = spheres[addr];
-                    const float oc[3] = {o.x, o.y, o.z};
-                    float q[3];
-#pragma unroll
-                    for (int k = 0; k < 3; k++)
-                    {
-                        const float m = cmax.v[k] < oc[k] ? cmax.v[k] : oc[k];     // min(o, cmax)
-                        const float t = cmin.v[k] < m ? m : cmin.v[k];             // max(cmin, .)
-                        q[k] = __fsub_rn(t, oc[k]);
-                    }
-                    const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q[0], q[0]), __fmul_rn(q[1], q[1])), __fmul_rn(q[2], q[2])));
-                    hit = dist < o.w;
-                }
-                const unsigned mask = __ballot_sync(kFullMask, hit);
-                stat_leaves += 32;
-                if (mask != 0)
-                {
-                    if (write)
-                    {
-                        if (hit)
-                        {
-                            const uint32_t slot = out_base + running + (__popc(mask & ge) - 1);   // descending lane order
-                            if (slot < prm.max_assigned) indices[slot] = sorted_pairs[addr].y;
-                        }
-                    }
-                    else
-                    {
-                        if (groups < (uint32_t) kHitCap && lane == 0) hits[groups] = make_uint2(addr, mask);
-                        groups++;
-                    }
-                    running += __popc(mask);
-                }
-                enter = false; // POP
+                const uint32_t child = __ffs(mask) - 1;
+                mask &= mask - 1;
+                walker<LEVEL + 1, LEVELS, WRITE>::visit(c, idx * 32 + child);
             }
         }
         else
         {
-            // POP then ADVANCE (assign_lights.comp:137-166): clear the lowest set bit of the parent level
-            if (level == 0) break;
-            level--;
-            idx >>= 5;
-            uint32_t m = ov[level];
-            m &= m - 1;
-            if (m != 0)
+            // leaf group: sphere (light) vs cluster box, assign_lights.comp:97-102,209-214.  The leaf record
+            // {view_pos.xyz, T} comes from the light-BVH build; T is the smallest float s with sqrt(s) >= radius, so
+            // "length(p - o) < radius" == "dot(p - o, p - o) < T" bit for bit, without the square root.
+            bool hit = false;
+            if (addr < c.light_count)
             {
-                __syncwarp();
-                if (lane == 0) ov[level] = m;
-                __syncwarp();
-                idx = idx * 32 + (__ffs(m) - 1);
-                level++;
-                enter = true;
+                const float4 o = c.spheres[addr];
+                // min/max pick identical values as the GLSL ternaries (only the sign of a zero may differ, squared away)
+                const float q0 = __fsub_rn(fmaxf(c.cmin[0], fminf(o.x, c.cmax[0])), o.x);
+                const float q1 = __fsub_rn(fmaxf(c.cmin[1], fminf(o.y, c.cmax[1])), o.y);
+                const float q2 = __fsub_rn(fmaxf(c.cmin[2], fminf(o.z, c.cmax[2])), o.z);
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), __fmul_rn(q2, q2));
+                hit = d2 < o.w;
+            }
+            const unsigned mask = __ballot_sync(kFullMask, hit);
+            c.stat_leaves += 32;
+            if (mask != 0)
+            {
+                if (WRITE)
+                {
+                    if (hit)
+                    {
+                        const uint32_t slot = c.out_base + c.running + (__popc(mask & lanemask_ge()) - 1);   // descending lane order
+                        if (slot < c.max_assigned) c.out[slot] = c.sorted_pairs[addr].y;
+                    }
+                }
+                else
+                {
+                    if (c.groups < (uint32_t) kHitCap && lane == 0) c.hits[c.groups] = make_uint2(addr, mask);
+                    c.groups++;
+                }
+                c.running += __popc(mask);
             }
         }
     }
-    return walk_result{running, groups};
+};
+
+__device__ __forceinline__ void init_walk_ctx(walk_ctx& c, const assign_params& prm, const float4* bvh, const float4* spheres,
+                                              const uint2* sorted_pairs)
+{
+    c.bvh = bvh; c.spheres = spheres; c.sorted_pairs = sorted_pairs;
+    c.light_count = prm.light_count; c.max_assigned = prm.max_assigned;
+    // level_base[l] = address of the first node of traversal level l (0 = children of the root), assign_lights.comp:108-119
+    uint32_t acc = 0, p = 1;
+#pragma unroll
+    for (int l = 0; l < kMaxBvhLevels; l++)
+    {
+        p *= 32;
+        acc += p;
+        c.level_base[l] = prm.bvh_root - acc;
+    }
+    c.stat_nodes = c.stat_leaves = 0;
 }
 
 // Phase 1 — ONE traversal per cluster: count the hits, remember (leaf group, hit mask), bump-allocate the list in the
 // arena and write the light indices there in their final within-list order.
+template <int LEVELS>
 __global__ void __launch_bounds__(kAssignThreads)
 assign_lights_walk_kernel(const uint32_t* __restrict__ cluster_keys, const uint32_t* __restrict__ dispatch_params,
                           const float4* __restrict__ bvh, const uint2* __restrict__ sorted_pairs, const float4* __restrict__ spheres,
                           const float* __restrict__ near_table, assign_params prm, assign_state* state,
                           uint32_t* counts, uint32_t* alloc, uint32_t* arena, uint32_t* status_out)
 {
-    __shared__ uint32_t s_overlaps[kAssignWarps][kMaxBvhLevels];
     __shared__ uint2 s_hits[kAssignWarps][kHitCap];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t count = min(dispatch_params[0], prm.max_keys);
-    uint32_t* ov = s_overlaps[warp];
-    uint2* hits = s_hits[warp];
     const unsigned ge = lanemask_ge();
-
-    // level_base[l] = address of the first node of traversal level l (0 = children of the root)
-    uint32_t level_base[kMaxBvhLevels];
-    {
-        uint32_t acc = 0, p = 1;
-#pragma unroll
-        for (int l = 0; l < kMaxBvhLevels; l++)
-        {
-            p *= 32;
-            acc += p;
-            level_base[l] = prm.bvh_root - acc;
-        }
-    }
-    uint32_t stat_nodes = 0, stat_leaves = 0;
+    walk_ctx ctx;
+    init_walk_ctx(ctx, prm, bvh, spheres, sorted_pairs);
+    ctx.hits = s_hits[warp];
 
     while (true)
     {
@@ -553,23 +545,27 @@ assign_lights_walk_kernel(const uint32_t* __restrict__ cluster_keys, const uint3
 
         float3x cmin, cmax;
         cluster_aabb(cluster_keys[c], prm, near_table, cmin, cmax);
-        const walk_result r = walk_cluster(cmin, cmax, bvh, spheres, sorted_pairs, prm, level_base, ov, hits, false, 0u, nullptr,
-                                           stat_nodes, stat_leaves);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ctx.cmin[k] = cmin.v[k]; ctx.cmax[k] = cmax.v[k]; }
+        ctx.running = ctx.groups = 0;
+        walker<0, LEVELS, false>::visit(ctx, 0);
+        const uint32_t total = ctx.running, groups = ctx.groups;
         uint32_t at = 0;
         if (lane == 0)
         {
-            at = r.total ? atomicAdd(&state->arena_top, r.total) : 0u;
-            counts[c] = r.total;
+            at = total ? atomicAdd(&state->arena_top, total) : 0u;
+            counts[c] = total;
             alloc[c] = at;
         }
         at = __shfl_sync(kFullMask, at, 0);
-        if (r.total == 0 || (uint64_t) at + r.total > prm.max_assigned) continue;   // arena full: phase 3 re-walks everything
-        if (r.groups <= (uint32_t) kHitCap)
+        if (total == 0 || (uint64_t) at + total > prm.max_assigned) continue;   // arena full: phase 3 re-walks everything
+        if (groups <= (uint32_t) kHitCap)
         {
+            __syncwarp();
             uint32_t running = 0;
-            for (uint32_t g = 0; g < r.groups; g++)
+            for (uint32_t g = 0; g < groups; g++)
             {
-                const uint2 h = hits[g];
+                const uint2 h = ctx.hits[g];
                 if (h.y & (1u << lane)) arena[at + running + (__popc(h.y & ge) - 1)] = sorted_pairs[h.x + lane].y;
                 running += __popc(h.y);
             }
@@ -577,21 +573,22 @@ assign_lights_walk_kernel(const uint32_t* __restrict__ cluster_keys, const uint3
         }
         else
         {
-            assign_params local = prm;
-            local.max_assigned = 0xFFFFFFFFu; // bounds were checked against the arena above
-            uint32_t dummy_n = 0, dummy_l = 0;
-            walk_cluster(cmin, cmax, bvh, spheres, sorted_pairs, local, level_base, ov, hits, true, at, arena, dummy_n, dummy_l);
+            ctx.out = arena; ctx.out_base = at; ctx.max_assigned = 0xFFFFFFFFu; // bounds were checked against the arena above
+            ctx.running = ctx.groups = 0;
+            walker<0, LEVELS, true>::visit(ctx, 0);
+            ctx.max_assigned = prm.max_assigned;
         }
     }
     if (status_out != nullptr && lane == 0)
     {
-        if (stat_nodes) atomicAdd(&status_out[2], stat_nodes);
-        if (stat_leaves) atomicAdd(&status_out[3], stat_leaves);
+        if (ctx.stat_nodes) atomicAdd(&status_out[2], ctx.stat_nodes);
+        if (ctx.stat_leaves) atomicAdd(&status_out[3], ctx.stat_leaves);
     }
 }
 
 // Phase 3 — lists move from the arena to offsets[c] (exclusive scan of the counts in cluster-list order, phase 2).
 // If the arena overflowed (more hits than max_assigned) every cluster is walked again and written in place, clamped.
+template <int LEVELS>
 __global__ void __launch_bounds__(kAssignThreads)
 assign_lights_place_kernel(const uint32_t* __restrict__ cluster_keys, const uint32_t* __restrict__ dispatch_params,
                            const float4* __restrict__ bvh, const uint2* __restrict__ sorted_pairs, const float4* __restrict__ spheres,
@@ -599,7 +596,6 @@ assign_lights_place_kernel(const uint32_t* __restrict__ cluster_keys, const uint
                            const uint32_t* __restrict__ counts, const uint32_t* __restrict__ alloc, const uint32_t* __restrict__ arena,
                            const uint32_t* __restrict__ offsets, uint32_t* indices, uint32_t* status_out)
 {
-    __shared__ uint32_t s_overlaps[kAssignWarps][kMaxBvhLevels];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t count = min(dispatch_params[0], prm.max_keys);
     const uint32_t total = state->arena_top;
@@ -619,25 +615,37 @@ assign_lights_place_kernel(const uint32_t* __restrict__ cluster_keys, const uint
         }
         return;
     }
-    uint32_t level_base[kMaxBvhLevels];
-    {
-        uint32_t acc = 0, p = 1;
-#pragma unroll
-        for (int l = 0; l < kMaxBvhLevels; l++)
-        {
-            p *= 32;
-            acc += p;
-            level_base[l] = prm.bvh_root - acc;
-        }
-    }
+    walk_ctx ctx;
+    init_walk_ctx(ctx, prm, bvh, spheres, sorted_pairs);
+    ctx.hits = nullptr;
+    ctx.out = indices;
     for (uint32_t c = blockIdx.x * kAssignWarps + warp; c < count; c += total_warps)
     {
         float3x cmin, cmax;
         cluster_aabb(cluster_keys[c], prm, near_table, cmin, cmax);
-        uint32_t dummy_n = 0, dummy_l = 0;
-        walk_cluster(cmin, cmax, bvh, spheres, sorted_pairs, prm, level_base, s_overlaps[warp], nullptr, true, offsets[c], indices,
-                     dummy_n, dummy_l);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ctx.cmin[k] = cmin.v[k]; ctx.cmax[k] = cmax.v[k]; }
+        ctx.running = ctx.groups = 0;
+        ctx.out_base = offsets[c];
+        walker<0, LEVELS, true>::visit(ctx, 0);
     }
+}
+
+template <int LEVELS>
+int launch_assign(cudaStream_t s, const uint32_t* cluster_keys, const uint32_t* dispatch_params, const float4* bvh, const uint2* pairs,
+                  const float4* spheres, const float* near_table, const assign_params& prm, assign_state* state, uint32_t* counts,
+                  uint32_t* alloc, uint32_t* arena, uint32_t* offsets, uint32_t* indices, uint32_t* status_out,
+                  vrenb200_stream_t stream, void* scan_scratch, size_t scan_bytes)
+{
+    const int grid = kNumSMs * 8;
+    assign_lights_walk_kernel<LEVELS><<<grid, kAssignThreads, 0, s>>>(cluster_keys, dispatch_params, bvh, pairs, spheres, near_table, prm,
+                                                                     state, counts, alloc, arena, status_out);
+    VRENB200_TRY(check_launch());
+    // copy counts -> offsets + blelloch_scan over all max_keys slots (clustered_shading.cpp:586-619), one pass here
+    VRENB200_TRY(vrenb200_exclusive_scan_u32(stream, counts, offsets, prm.max_keys, scan_scratch, scan_bytes));
+    assign_lights_place_kernel<LEVELS><<<grid, kAssignThreads, 0, s>>>(cluster_keys, dispatch_params, bvh, pairs, spheres, near_table, prm,
+                                                                      state, counts, alloc, arena, offsets, indices, status_out);
+    return check_launch();
 }
 
 // ---- tensor maps ----------------------------------------------------------------------------------------------------
@@ -786,13 +794,13 @@ extern "C" int vrenb200_assign_lights(vrenb200_stream_t stream,
     // compact leaf spheres written by vrenb200_construct_point_light_bvh behind the bucket-sort counters
     const float4* spheres = reinterpret_cast<const float4*>(static_cast<const char*>(light_index_buffer) + light_leaf_sphere_offset(light_count));
     (void) view_pos; // its xyz live in the leaf spheres; kept in the signature like the reference (assign_lights.comp:72-75)
-    const int grid = kNumSMs * 8;
-    assign_lights_walk_kernel<<<grid, kAssignThreads, 0, s>>>(cluster_keys, dispatch_params, bvh, pairs, spheres, near_table, prm, state,
-                                                            counts_out, alloc, arena, status_out);
-    VRENB200_TRY(check_launch());
-    // copy counts -> offsets + blelloch_scan over all max_keys slots (clustered_shading.cpp:586-619), one pass here
-    VRENB200_TRY(vrenb200_exclusive_scan_u32(stream, counts_out, offsets_out, max_keys, scan_scratch, scan_bytes));
-    assign_lights_place_kernel<<<grid, kAssignThreads, 0, s>>>(cluster_keys, dispatch_params, bvh, pairs, spheres, near_table, prm, state,
-                                                             counts_out, alloc, arena, offsets_out, indices_out, status_out);
-    return check_launch();
+#define VRENB200_ASSIGN(L) case L: return launch_assign<L>(s, cluster_keys, dispatch_params, bvh, pairs, spheres, near_table, prm, state, \
+                                                       counts_out, alloc, arena, offsets_out, indices_out, status_out, stream,      \
+                                                       scan_scratch, scan_bytes)
+    switch (levels)
+    {
+        VRENB200_ASSIGN(1); VRENB200_ASSIGN(2); VRENB200_ASSIGN(3); VRENB200_ASSIGN(4); VRENB200_ASSIGN(5); VRENB200_ASSIGN(6);
+    default: return VRENB200_ELIMIT;
+    }
+#undef VRENB200_ASSIGN
 }

@@ -235,13 +235,14 @@ struct onesweep_smem
     alignas(128) uint32_t kv[KV_WORDS];
     uint32_t warp_hist[WARPS][kRadix];
     uint32_t digit_base[kRadix];
+    uint32_t tile_hist[kRadix];       // EARLY_HIST: digit counts of the tile, known before the ranking
     uint32_t scan_warp[kRadix / 32];
     alignas(8) uint64_t bar_keys;
     alignas(8) uint64_t bar_vals;
     uint32_t tile;
 };
 
-enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2 }; // option bits of the MATCH template argument
+enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4 }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -312,6 +313,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     // warp-private digit counters
 #pragma unroll
     for (int i = lane; i < kRadix; i += 32) sm.warp_hist[warp][i] = 0;
+    if ((MATCH & EARLY_HIST) && tid < kRadix) sm.tile_hist[tid] = 0;
     __syncthreads();
 
     const uint32_t tile = sm.tile;
@@ -352,6 +354,28 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) key[j] = sm.kv[(warp_off + j * 32) * KSTRIDE];
 
+    // EARLY_HIST: count the tile's digits with shared atomics right away, publish the aggregate and put the first
+    // look-back loads in flight BEFORE the (long) ranking phase: successors never find an empty word, and this
+    // tile's own look-back latency hides behind its ranking
+    constexpr int LBK = 4;
+    uint32_t* lb = lookback + ((size_t) pass * num_tiles + tile) * kRadix;
+    uint32_t early_cnt = 0, lb_pre[LBK];
+    if (MATCH & EARLY_HIST)
+    {
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) atomicAdd(&sm.tile_hist[(key[j] >> shift) & 0xFFu], 1u);
+        __syncthreads();
+        if (tid < kRadix)
+        {
+            early_cnt = sm.tile_hist[tid];
+            const uint32_t real = early_cnt - ((tid == kRadix - 1) ? (uint32_t) TILE - valid : 0u);
+            st_relaxed_u32(&lb[tid], (tile == 0 ? kLbFlagInclusive : kLbFlagAggregate) | real);
+#pragma unroll
+            for (int k = 0; k < LBK; k++)
+                lb_pre[k] = ((int64_t) tile - 1 - k >= 0) ? ld_relaxed_u32(lb - (k + 1) * kRadix + tid) : kLbFlagInclusive;
+        }
+    }
+
     // stable in-warp ranking: ballot match + warp-private running digit counters.  Every lane of a match group
     // reads the counter, then every lane writes back the same new value (no leader election, no divergence).
     uint32_t rank[ITEMS];
@@ -372,13 +396,17 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 
     // per digit: tile count, publish aggregate, tile-local exclusive offsets
     uint32_t cnt = 0, inc = 0, real_cnt = 0;
-    uint32_t* lb = lookback + ((size_t) pass * num_tiles + tile) * kRadix;
     if (tid < kRadix)
     {
+        if (MATCH & EARLY_HIST)
+            cnt = early_cnt;
+        else
+        {
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) cnt += sm.warp_hist[w][tid];
+            for (int w = 0; w < WARPS; w++) cnt += sm.warp_hist[w][tid];
+        }
         real_cnt = cnt - ((tid == kRadix - 1) ? (uint32_t) TILE - valid : 0u);
-        st_relaxed_u32(&lb[tid], (tile == 0 ? kLbFlagInclusive : kLbFlagAggregate) | real_cnt);
+        if (!(MATCH & EARLY_HIST)) st_relaxed_u32(&lb[tid], (tile == 0 ? kLbFlagInclusive : kLbFlagAggregate) | real_cnt);
         inc = cnt;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1)
@@ -436,13 +464,34 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
         uint32_t exclusive = 0;
         if (tile > 0)
         {
+            // K predecessors are fetched per round trip (independent loads), then consumed in order: with hundreds of
+            // tiles in flight a one-at-a-time walk spends most of the tile's life in dependent L2 round trips
+            constexpr int K = 4;
             const uint32_t* p = lb - kRadix + tid;
-            for (int64_t t = (int64_t) tile - 1; t >= 0; t--, p -= kRadix)
+            int64_t t = (int64_t) tile - 1;
+            bool done = false;
+            while (!done)
             {
-                uint32_t s;
-                do { s = ld_relaxed_u32(p); } while ((s >> 30) == 0);
-                exclusive += s & kLbValueMask;
-                if ((s >> 30) == 2) break;
+                uint32_t s[K];
+                static_assert(K == LBK, "prefetch depth");
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                {
+                    if ((MATCH & EARLY_HIST) && t == (int64_t) tile - 1)
+                        s[k] = lb_pre[k];   // fetched before the ranking; anything still empty is re-polled below
+                    else
+                        s[k] = (t - k >= 0) ? ld_relaxed_u32(p - k * kRadix) : kLbFlagInclusive;
+                }
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                {
+                    if (done) break;
+                    while ((s[k] >> 30) == 0) s[k] = ld_relaxed_u32(p - k * kRadix);
+                    exclusive += s[k] & kLbValueMask;
+                    done = (s[k] >> 30) == 2;
+                }
+                t -= K;
+                p -= K * kRadix;
             }
             st_relaxed_u32(&lb[tid], kLbFlagInclusive | (exclusive + real_cnt));
         }
@@ -530,12 +579,12 @@ int launch_onesweep(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const u
 #define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B> }
 const sort_variant g_variants[] = {
     VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),   // 0: default (best of the sweeps in profiles/)
-    VARIANT(256, 24, MATCH_BALLOT, 3),       // ticket instead of block index
-    VARIANT(512, 16, TILE_BY_BLOCKIDX, 2),
-    VARIANT(384, 20, TILE_BY_BLOCKIDX, 2),
-    VARIANT(256, 16, TILE_BY_BLOCKIDX, 4),
+    VARIANT(256, 24, TILE_BY_BLOCKIDX | EARLY_HIST, 3),
     VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),
-    VARIANT(256, 20, TILE_BY_BLOCKIDX, 3),
+    VARIANT(256, 32, TILE_BY_BLOCKIDX | EARLY_HIST, 2),
+    VARIANT(512, 16, TILE_BY_BLOCKIDX | EARLY_HIST, 2),
+    VARIANT(384, 20, TILE_BY_BLOCKIDX | EARLY_HIST, 2),
+    VARIANT(256, 24, MATCH_BALLOT, 3),       // ticket instead of block index
     VARIANT(256, 24, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 3),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
