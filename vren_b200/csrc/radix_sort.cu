@@ -97,13 +97,17 @@ radix_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, sort_contr
         atomicAdd(&s_hist[3][k >> 24], 1u);
     };
     uint32_t i = blockIdx.x * kHistThreads + threadIdx.x;
-    // two independent 128-bit loads in flight per thread per iteration
-    for (; i + stride < n4; i += 2 * stride)
+    // four independent 128-bit loads in flight per thread per iteration (the kernel is latency-bound otherwise)
+    for (; (uint64_t) i + 3ull * stride < n4; i += 4 * stride)
     {
         const uint4 a = ldg_stream_u4(keys4 + i);
         const uint4 b = ldg_stream_u4(keys4 + i + stride);
+        const uint4 c = ldg_stream_u4(keys4 + i + 2 * stride);
+        const uint4 d = ldg_stream_u4(keys4 + i + 3 * stride);
         count(a.x); count(a.y); count(a.z); count(a.w);
         count(b.x); count(b.y); count(b.z); count(b.w);
+        count(c.x); count(c.y); count(c.z); count(c.w);
+        count(d.x); count(d.y); count(d.z); count(d.w);
     }
     for (; i < n4; i += stride)
     {
@@ -253,20 +257,24 @@ __device__ __forceinline__ unsigned match_digit(uint32_t d)
     unsigned mask = kFullMask;
     if ((MATCH & MATCH_BALLOT_C) == 0)
     {
+        // peers = AND of the ballots of my set bits, minus OR of the ballots of my clear bits: two independent
+        // accumulators, each updated by ONE predicated LOP3 per bit (vote + 2 instructions per bit)
+        unsigned ones = kFullMask, zeros = 0u;
 #pragma unroll
         for (int b = 0; b < kRadixBits; b++)
         {
             asm("{\n"
                 ".reg .pred p;\n"
                 ".reg .b32 t, bal;\n"
-                "and.b32 t, %1, %2;\n"
+                "and.b32 t, %2, %3;\n"
                 "setp.ne.u32 p, t, 0;\n"
                 "vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
                 "@p and.b32 %0, %0, bal;\n"
-                "@!p lop3.b32 %0, %0, bal, 0, 0x30;\n"   // mask & ~bal
+                "@!p or.b32 %1, %1, bal;\n"
                 "}\n"
-                : "+r"(mask) : "r"(d), "r"(1u << b));
+                : "+r"(ones), "+r"(zeros) : "r"(d), "r"(1u << b));
         }
+        mask = ones & ~zeros;
     }
     else
     {
@@ -280,6 +288,8 @@ __device__ __forceinline__ unsigned match_digit(uint32_t d)
     }
     return mask;
 }
+
+__device__ __forceinline__ uint32_t digit_of(uint32_t key, uint32_t prmt_sel) { return __byte_perm(key, 0u, prmt_sel); }
 
 template <int THREADS, int ITEMS, int LAYOUT, int MATCH, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
@@ -299,7 +309,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     smem_t& sm = *reinterpret_cast<smem_t*>(smem_raw);
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int shift = pass * kRadixBits;
+    const uint32_t prmt_sel = 0x4440u | (uint32_t) pass;   // byte `pass` of the key -> one PRMT per digit extraction
 
     if (tid == 0)
     {
@@ -363,7 +373,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     if (MATCH & EARLY_HIST)
     {
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) atomicAdd(&sm.tile_hist[(key[j] >> shift) & 0xFFu], 1u);
+        for (int j = 0; j < ITEMS; j++) atomicAdd(&sm.tile_hist[digit_of(key[j], prmt_sel)], 1u);
         __syncthreads();
         if (tid < kRadix)
         {
@@ -384,7 +394,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 #pragma unroll
     for (int j = 0; j < ITEMS; j++)
     {
-        const uint32_t d = (key[j] >> shift) & 0xFFu;
+        const uint32_t d = digit_of(key[j], prmt_sel);
         const unsigned mask = match_digit<MATCH>(d);
         const uint32_t prior = my_hist[d];
         rank[j] = prior + __popc(mask & lt);
@@ -438,7 +448,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 
     // in-tile destination of every item; fetch the staged values with the same striping
 #pragma unroll
-    for (int j = 0; j < ITEMS; j++) rank[j] += my_hist[(key[j] >> shift) & 0xFFu];
+    for (int j = 0; j < ITEMS; j++) rank[j] += my_hist[digit_of(key[j], prmt_sel)];
     uint32_t val[HAS_VALUES ? ITEMS : 1];
     if (HAS_VALUES)
     {
@@ -509,7 +519,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
             if (HAS_VALUES)
             {
                 const uint2 e = reinterpret_cast<const uint2*>(sm.kv)[p];
-                const uint32_t g = sm.digit_base[(e.x >> shift) & 0xFFu] + p;
+                const uint32_t g = sm.digit_base[digit_of(e.x, prmt_sel)] + p;
                 if (LAYOUT == LAYOUT_AOS)
                     reinterpret_cast<uint2*>(keys_out)[g] = e;
                 else
@@ -521,7 +531,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
             else
             {
                 const uint32_t k = sm.kv[p];
-                keys_out[sm.digit_base[(k >> shift) & 0xFFu] + p] = k;
+                keys_out[sm.digit_base[digit_of(k, prmt_sel)] + p] = k;
             }
         }
     }
@@ -530,7 +540,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
         for (uint32_t p = tid; p < valid; p += THREADS)
         {
             const uint32_t k = sm.kv[p * (HAS_VALUES ? 2 : 1)];
-            const uint32_t g = sm.digit_base[(k >> shift) & 0xFFu] + p;
+            const uint32_t g = sm.digit_base[digit_of(k, prmt_sel)] + p;
             if (LAYOUT == LAYOUT_AOS)
                 reinterpret_cast<uint2*>(keys_out)[g] = make_uint2(k, sm.kv[p * 2 + 1]);
             else
@@ -578,14 +588,14 @@ int launch_onesweep(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const u
 
 #define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B> }
 const sort_variant g_variants[] = {
-    VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),   // 0: default (best of the sweeps in profiles/)
-    VARIANT(256, 24, TILE_BY_BLOCKIDX | EARLY_HIST, 3),
-    VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),
+    VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),   // 0: default (best of the sweeps in profiles/)
+    VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),
+    VARIANT(256, 28, TILE_BY_BLOCKIDX, 2),
+    VARIANT(288, 28, TILE_BY_BLOCKIDX, 2),
+    VARIANT(320, 24, TILE_BY_BLOCKIDX, 2),
     VARIANT(256, 32, TILE_BY_BLOCKIDX | EARLY_HIST, 2),
-    VARIANT(512, 16, TILE_BY_BLOCKIDX | EARLY_HIST, 2),
-    VARIANT(384, 20, TILE_BY_BLOCKIDX | EARLY_HIST, 2),
-    VARIANT(256, 24, MATCH_BALLOT, 3),       // ticket instead of block index
-    VARIANT(256, 24, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 3),
+    VARIANT(256, 32, MATCH_BALLOT, 2),       // ticket instead of block index
+    VARIANT(256, 32, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 2),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
@@ -635,7 +645,7 @@ int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, 
     const size_t clear = sizeof(sort_control) + (size_t) kPasses * tiles * kRadix * sizeof(uint32_t);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(ctl_mem, 0, clear, s)));
     if (prof) cudaEventRecord(prof->ev[0], s);
-    radix_histogram_kernel<<<kNumSMs * 2, kHistThreads, 0, s>>>(keys, n, ctl);
+    radix_histogram_kernel<<<kNumSMs * 4, kHistThreads, 0, s>>>(keys, n, ctl);
     VRENB200_TRY(check_launch());
     if (prof) cudaEventRecord(prof->ev[1], s);
     radix_scan_histograms_kernel<<<kPasses, kRadix, 0, s>>>(ctl);
@@ -745,7 +755,7 @@ extern "C" int vrenb200_radix_digit_histograms(vrenb200_stream_t stream, const u
     if (n == 0) return VRENB200_OK;
     // the kernel addresses its output through sort_control::hist
     sort_control* fake = reinterpret_cast<sort_control*>(reinterpret_cast<char*>(hist_out) - offsetof(sort_control, hist));
-    radix_histogram_kernel<<<kNumSMs * 2, kHistThreads, 0, s>>>(keys, n, fake);
+    radix_histogram_kernel<<<kNumSMs * 4, kHistThreads, 0, s>>>(keys, n, fake);
     return check_launch();
 }
 
