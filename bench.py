@@ -260,10 +260,18 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     dops = None
+    exchange = None
     if world > 1:
         from vren_b200 import dist as vdist
 
         dops = vdist.CudaOps()
+        exchange = None
+        if not args.nccl_exchange:
+            try:
+                exchange = vdist.P2PExchange(int(n * 1.25) + 4096, dev)    # receive buffers in symmetric (peer-mapped) memory
+            except Exception as e:      # no P2P / symmetric memory: NCCL all-to-all-v path
+                if rank == 0:
+                    print(f"bench: symmetric memory unavailable ({e}); using the NCCL exchange", file=sys.stderr)
     last = {}
 
     def one_step(profile):
@@ -277,7 +285,10 @@ def run_ours(args):
             vlib.check(lib.vrenb200_radix_sort_pairs_profiled(stream, keys.data_ptr(), vals.data_ptr(), n, scratch.data_ptr(),
                                                               sbytes, prof if profile else None), "radix_sort_pairs")
         else:
-            last["k"], last["v"], last["plan"] = vdist.sharded_sort_pairs(keys, vals, ops=dops)
+            if exchange is not None:
+                last["k"], last["v"], last["plan"] = vdist.sharded_sort_pairs_p2p(keys, vals, exchange, ops=dops)
+            else:
+                last["k"], last["v"], last["plan"] = vdist.sharded_sort_pairs(keys, vals, ops=dops)
         e1.record()
         return e0, e1
 
@@ -377,7 +388,9 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (2 GiB restored between steps)",
                        "variant": lib.vrenb200_radix_sort_variant_name(args.variant or 0).decode(),
                        "parallelism": "1 GPU" if world == 1 else
-                       f"one global sort of {world}x2^{args.log2n} pairs: top-digit split + NCCL all-to-all-v + local onesweep"},
+                       f"one global sort of {world}x2^{args.log2n} pairs: top-digit split + " +
+                       ("partition kernel storing into peer receive buffers over NVLink" if (world > 1 and exchange is not None)
+                        else "NCCL all-to-all-v") + " + local onesweep"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "onesweep_pass_kernel", "peak_source": peak_src,
                          "kernel_ms": pass_avg_ms, "histogram_ms": sum(hist_ms) / len(hist_ms),
@@ -385,7 +398,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                     "ms_per_step": float(te.item())},
-            "gpu_launches": (6 if world == 1 else 1 + 1 + 2 + 6) * args.steps,
+            "gpu_launches": (6 if world == 1 else (2 + 6 if exchange is not None else 1 + 1 + 2 + 6)) * args.steps,
             "secondary": secondary,
             "clocks": clocks.summary(),
         }
@@ -405,6 +418,7 @@ def main():
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use the NCCL all-to-all-v exchange instead of the fused P2P one")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -124,3 +124,25 @@ def test_plan_digit_ranges_properties():
     h[200] = 12345
     b = vdist.plan_digit_ranges(h, 8)
     assert sum(int(h[b[r]:b[r + 1]].sum()) for r in range(8)) == 12345
+
+
+def test_plan_p2p_offsets_tile_the_receive_buffers():
+    """the fused exchange writes every (src, digit) run at plan_p2p_offsets: runs must tile each receive buffer exactly,
+    ordered by (digit, source rank) so that the final local stable sort yields the global stable order"""
+    rng = np.random.Generator(np.random.PCG64(7))
+    for world in (2, 4, 8):
+        hists = torch.from_numpy(rng.integers(0, 50, size=(world, 256)).astype(np.int64))
+        bounds = vdist.plan_digit_ranges(hists.sum(0), world)
+        cover = [dict() for _ in range(world)]
+        for src in range(world):
+            dest_rank, dest_off, recv_counts = vdist.plan_p2p_offsets(hists, bounds, src)
+            for d in range(256):
+                r = int(dest_rank[d])
+                assert bounds[r] <= d < bounds[r + 1]
+                cover[r][(d, src)] = (int(dest_off[d]), int(hists[src, d]))
+        for r in range(world):
+            pos = 0
+            for (d, src), (off, cnt) in sorted(cover[r].items()):
+                assert off == pos, (world, r, d, src)
+                pos += cnt
+            assert pos == recv_counts[r] == int(hists[:, bounds[r]:bounds[r + 1]].sum())

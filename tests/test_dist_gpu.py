@@ -25,7 +25,7 @@ def _shard(rank, n, skew):
     return keys.astype(np.uint32), (np.arange(n, dtype=np.uint64) + rank * (1 << 26)).astype(np.uint32)
 
 
-def _worker(rank, world, port, sizes, skew, out_dir):
+def _worker(rank, world, port, sizes, skew, out_dir, p2p=False):
     import torch
     import torch.distributed as dist
 
@@ -39,7 +39,13 @@ def _worker(rank, world, port, sizes, skew, out_dir):
         keys, vals = _shard(rank, sizes[rank], skew)
         tk = torch.from_numpy(keys.view(np.int32).copy()).cuda()
         tv = torch.from_numpy(vals.view(np.int32).copy()).cuda()
-        rk, rv, plan = vdist.sharded_sort_pairs(tk, tv)
+        if p2p:
+            ex = vdist.P2PExchange(int(sum(sizes) * 1.5) + 4096, torch.device("cuda", rank))
+            for _ in range(2):      # twice: the receive buffers are reused
+                rk, rv, plan = vdist.sharded_sort_pairs_p2p(tk, tv, ex)
+            rk, rv = rk.clone(), rv.clone()
+        else:
+            rk, rv, plan = vdist.sharded_sort_pairs(tk, tv)
         np.save(os.path.join(out_dir, f"k{rank}.npy"), rk.cpu().numpy().view(np.uint32))
         np.save(os.path.join(out_dir, f"v{rank}.npy"), rv.cpu().numpy().view(np.uint32))
         x = torch.from_numpy((keys % 1000).astype(np.uint32).view(np.int32).copy()).cuda()
@@ -49,15 +55,16 @@ def _worker(rank, world, port, sizes, skew, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("sizes,skew", [((1 << 20, 1 << 20), False), ((300001, 77), False), ((1 << 18, 1 << 19), True)])
-def test_sharded_sort_and_scan_nccl(vren, tmp_path, sizes, skew):
+def test_sharded_sort_and_scan_nccl(vren, tmp_path, sizes, skew, p2p):
     import torch
     import torch.multiprocessing as mp
 
     world = 2
     if torch.cuda.device_count() < world:
         pytest.skip("needs 2 GPUs")
-    mp.spawn(_worker, args=(world, _free_port(), sizes, skew, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), sizes, skew, str(tmp_path), p2p), nprocs=world, join=True)
     shards = [_shard(r, sizes[r], skew) for r in range(world)]
     all_k = np.concatenate([s[0] for s in shards])
     all_v = np.concatenate([s[1] for s in shards])

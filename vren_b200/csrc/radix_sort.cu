@@ -229,7 +229,7 @@ radix_scan_histograms_kernel(sort_control* ctl)
 // ---- 3. the fused onesweep pass ------------------------------------------------------------------------------
 enum { LAYOUT_KEYS = 0, LAYOUT_SOA = 1, LAYOUT_AOS = 2 };
 
-template <int THREADS, int ITEMS, int LAYOUT>
+template <int THREADS, int ITEMS, int LAYOUT, bool P2P = false>
 struct onesweep_smem
 {
     static constexpr int WARPS = THREADS / 32;
@@ -240,13 +240,15 @@ struct onesweep_smem
     uint32_t warp_hist[WARPS][kRadix];
     uint32_t digit_base[kRadix];
     uint32_t tile_hist[kRadix];       // EARLY_HIST: digit counts of the tile, known before the ranking
+    // P2P_DEST: per-digit destination base pointers (keys, values), possibly in a peer GPU's memory
+    alignas(8) unsigned long long dst_ptr[P2P ? 2 : 1][P2P ? kRadix : 1];
     uint32_t scan_warp[kRadix / 32];
     alignas(8) uint64_t bar_keys;
     alignas(8) uint64_t bar_vals;
     uint32_t tile;
 };
 
-enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4 }; // option bits of the MATCH template argument
+enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8 }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -297,7 +299,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                      uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t num_tiles)
 {
-    using smem_t = onesweep_smem<THREADS, ITEMS, LAYOUT>;
+    using smem_t = onesweep_smem<THREADS, ITEMS, LAYOUT, (MATCH & P2P_DEST) != 0>;
     constexpr int WARPS = smem_t::WARPS;
     constexpr int TILE = smem_t::TILE;
     constexpr bool HAS_VALUES = LAYOUT != LAYOUT_KEYS;
@@ -505,7 +507,17 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
             }
             st_relaxed_u32(&lb[tid], kLbFlagInclusive | (exclusive + real_cnt));
         }
-        sm.digit_base[tid] = ctl->hist[pass][tid] + exclusive - tile_off;
+        if (MATCH & P2P_DEST)
+        {
+            // exchange mode: keys_out is a device table [2][256] of per-digit destination pointers (keys, values);
+            // a digit's run starts at its pointer, this tile's slice of it at the look-back prefix
+            const unsigned long long* table = reinterpret_cast<const unsigned long long*>(keys_out);
+            sm.dst_ptr[0][tid] = table[tid];
+            sm.dst_ptr[(MATCH & P2P_DEST) ? 1 : 0][tid] = table[kRadix + tid];
+            sm.digit_base[tid] = exclusive - tile_off;
+        }
+        else
+            sm.digit_base[tid] = ctl->hist[pass][tid] + exclusive - tile_off;
     }
     __syncthreads();
 
@@ -522,6 +534,12 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
                 const uint32_t g = sm.digit_base[digit_of(e.x, prmt_sel)] + p;
                 if (LAYOUT == LAYOUT_AOS)
                     reinterpret_cast<uint2*>(keys_out)[g] = e;
+                else if (MATCH & P2P_DEST)
+                {
+                    const uint32_t d = digit_of(e.x, prmt_sel);
+                    reinterpret_cast<uint32_t*>(sm.dst_ptr[0][d])[g] = e.x;          // st.global, peer or local
+                    reinterpret_cast<uint32_t*>(sm.dst_ptr[(MATCH & P2P_DEST) ? 1 : 0][d])[g] = e.y;
+                }
                 else
                 {
                     keys_out[g] = e.x;
@@ -543,12 +561,265 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
             const uint32_t g = sm.digit_base[digit_of(k, prmt_sel)] + p;
             if (LAYOUT == LAYOUT_AOS)
                 reinterpret_cast<uint2*>(keys_out)[g] = make_uint2(k, sm.kv[p * 2 + 1]);
+            else if (MATCH & P2P_DEST)
+            {
+                const uint32_t d = digit_of(k, prmt_sel);
+                reinterpret_cast<uint32_t*>(sm.dst_ptr[0][d])[g] = k;
+                reinterpret_cast<uint32_t*>(sm.dst_ptr[(MATCH & P2P_DEST) ? 1 : 0][d])[g] = sm.kv[p * 2 + 1];
+            }
             else
             {
                 keys_out[g] = k;
                 if (HAS_VALUES) vals_out[g] = sm.kv[p * 2 + 1];
             }
         }
+    }
+}
+
+// ---- 3b. persistent onesweep pass: CTAs loop over tiles, the next tile's keys are prefetched ---------------------
+// Same algorithm as onesweep_pass_kernel (LAYOUT_KEYS / LAYOUT_SOA only), restructured so that no tile waits for its
+// input: a CTA takes the ticket of its NEXT tile and starts the TMA bulk copy of that tile's keys into a second
+// shared buffer while the current tile is being scanned, regrouped and written out; values are fetched at the start
+// of a tile and land during its ranking.  Tickets keep the look-back deadlock-free whatever the residency: a tile is
+// only ever waited on after a running CTA has taken it.
+template <int THREADS, int ITEMS, int LAYOUT>
+struct persistent_smem
+{
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * ITEMS;
+    static constexpr int KV_WORDS = LAYOUT == LAYOUT_KEYS ? TILE : 2 * TILE;
+    alignas(128) uint32_t kv[KV_WORDS];   // values staging (SOA: second half), then interleaved regroup area
+    alignas(128) uint32_t pre[TILE];      // keys of the current tile (prefetched during the previous one)
+    uint32_t warp_hist[WARPS][kRadix];
+    uint32_t digit_base[kRadix];
+    uint32_t scan_warp[kRadix / 32];
+    alignas(8) uint64_t bar_keys;
+    alignas(8) uint64_t bar_vals;
+    uint32_t tile_next;
+};
+
+template <int THREADS, int ITEMS, int LAYOUT, int MATCH, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+onesweep_persistent_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
+                           const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
+                           uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t num_tiles)
+{
+    using smem_t = persistent_smem<THREADS, ITEMS, LAYOUT>;
+    constexpr int WARPS = smem_t::WARPS;
+    constexpr int TILE = smem_t::TILE;
+    constexpr bool HAS_VALUES = LAYOUT == LAYOUT_SOA;
+    static_assert(LAYOUT != LAYOUT_AOS, "persistent kernel: keys or keys+values arrays");
+    static_assert(THREADS >= kRadix, "one thread per digit needed");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    smem_t& sm = *reinterpret_cast<smem_t*>(smem_raw);
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t prmt_sel = 0x4440u | (uint32_t) pass;
+    const unsigned lt = lanemask_lt();
+    uint32_t* my_hist = sm.warp_hist[warp];
+    const uint32_t warp_off = warp * (ITEMS * 32) + lane;
+    const uint32_t last_full_tiles = n / TILE;   // tiles [0, last_full_tiles) are full
+
+    if (tid == 0)
+    {
+        mbar_init(&sm.bar_keys, 1);
+        mbar_init(&sm.bar_vals, 1);
+        mbar_fence_init();
+        const uint32_t t0 = atomicAdd(&ctl->tickets[pass], 1u);
+        sm.tile_next = t0;
+        if (t0 < last_full_tiles)
+        {
+            mbar_arrive_expect_tx(&sm.bar_keys, TILE * 4);
+            bulk_copy_g2s(sm.pre, keys_in + (uint64_t) t0 * TILE, TILE * 4, &sm.bar_keys);
+        }
+    }
+    __syncthreads();
+    uint32_t kphase = 0, vphase = 0;
+
+    while (true)
+    {
+        const uint32_t tile = sm.tile_next;
+        if (tile >= num_tiles) break;
+        const uint64_t tile_base = (uint64_t) tile * TILE;
+        const uint32_t valid = (n - tile_base) < (uint64_t) TILE ? (uint32_t) (n - tile_base) : (uint32_t) TILE;
+        const bool full = valid == (uint32_t) TILE;
+
+        if (HAS_VALUES && full && tid == 0)
+        {
+            mbar_arrive_expect_tx(&sm.bar_vals, TILE * 4);
+            bulk_copy_g2s(sm.kv + TILE, vals_in + tile_base, TILE * 4, &sm.bar_vals);
+        }
+#pragma unroll
+        for (int i = lane; i < kRadix; i += 32) my_hist[i] = 0;
+        if (full)
+        {
+            mbar_wait(&sm.bar_keys, kphase);
+            kphase ^= 1;
+        }
+        else
+        {
+            for (uint32_t i = tid; i < (uint32_t) TILE; i += THREADS)
+            {
+                const bool in = i < valid;
+                sm.pre[i] = in ? keys_in[tile_base + i] : 0xFFFFFFFFu;
+                if (HAS_VALUES) sm.kv[TILE + i] = in ? vals_in[tile_base + i] : 0u;
+            }
+            __syncthreads();
+        }
+        __syncwarp();
+
+        uint32_t key[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) key[j] = sm.pre[warp_off + j * 32];
+
+        uint32_t rank[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++)
+        {
+            const uint32_t d = digit_of(key[j], prmt_sel);
+            const unsigned mask = match_digit<MATCH>(d);
+            const uint32_t prior = my_hist[d];
+            rank[j] = prior + __popc(mask & lt);
+            __syncwarp();
+            my_hist[d] = prior + __popc(mask);
+            __syncwarp();
+        }
+        __syncthreads();   // S1: every warp has its keys in registers -> `pre` can take the next tile
+
+        if (tid == 0)
+        {
+            const uint32_t tn = atomicAdd(&ctl->tickets[pass], 1u);
+            sm.tile_next = tn;
+            if (tn < last_full_tiles)
+            {
+                mbar_arrive_expect_tx(&sm.bar_keys, TILE * 4);
+                bulk_copy_g2s(sm.pre, keys_in + (uint64_t) tn * TILE, TILE * 4, &sm.bar_keys);
+            }
+        }
+
+        uint32_t cnt = 0, inc = 0, real_cnt = 0;
+        uint32_t* lb = lookback + ((size_t) pass * num_tiles + tile) * kRadix;
+        if (tid < kRadix)
+        {
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) cnt += sm.warp_hist[w][tid];
+            real_cnt = cnt - ((tid == kRadix - 1) ? (uint32_t) TILE - valid : 0u);
+            st_relaxed_u32(&lb[tid], (tile == 0 ? kLbFlagInclusive : kLbFlagAggregate) | real_cnt);
+            inc = cnt;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(kFullMask, inc, s);
+                if (lane >= (unsigned) s) inc += t;
+            }
+            if (lane == 31) sm.scan_warp[warp] = inc;
+        }
+        __syncthreads();   // S2
+        uint32_t tile_off = 0;
+        if (tid < kRadix)
+        {
+            uint32_t wp = 0;
+#pragma unroll
+            for (int w = 0; w < kRadix / 32; w++)
+                if (w < (int) warp) wp += sm.scan_warp[w];
+            tile_off = wp + inc - cnt;
+            uint32_t run = tile_off;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++)
+            {
+                const uint32_t c = sm.warp_hist[w][tid];
+                sm.warp_hist[w][tid] = run;
+                run += c;
+            }
+        }
+        __syncthreads();   // S3
+
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) rank[j] += my_hist[digit_of(key[j], prmt_sel)];
+        uint32_t val[HAS_VALUES ? ITEMS : 1];
+        if (HAS_VALUES)
+        {
+            if (full)
+            {
+                mbar_wait(&sm.bar_vals, vphase);
+                vphase ^= 1;
+            }
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) val[j] = sm.kv[TILE + warp_off + j * 32];
+        }
+        __syncthreads();   // S4: staged values consumed, kv becomes the regroup area
+
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++)
+        {
+            if (HAS_VALUES)
+                reinterpret_cast<uint2*>(sm.kv)[rank[j]] = make_uint2(key[j], val[j]);
+            else
+                sm.kv[rank[j]] = key[j];
+        }
+
+        if (tid < kRadix)
+        {
+            uint32_t exclusive = 0;
+            if (tile > 0)
+            {
+                constexpr int K = 4;
+                const uint32_t* p = lb - kRadix + tid;
+                int64_t t = (int64_t) tile - 1;
+                bool done = false;
+                while (!done)
+                {
+                    uint32_t s[K];
+#pragma unroll
+                    for (int k = 0; k < K; k++) s[k] = (t - k >= 0) ? ld_relaxed_u32(p - k * kRadix) : kLbFlagInclusive;
+#pragma unroll
+                    for (int k = 0; k < K; k++)
+                    {
+                        if (done) break;
+                        while ((s[k] >> 30) == 0) s[k] = ld_relaxed_u32(p - k * kRadix);
+                        exclusive += s[k] & kLbValueMask;
+                        done = (s[k] >> 30) == 2;
+                    }
+                    t -= K;
+                    p -= K * kRadix;
+                }
+                st_relaxed_u32(&lb[tid], kLbFlagInclusive | (exclusive + real_cnt));
+            }
+            sm.digit_base[tid] = ctl->hist[pass][tid] + exclusive - tile_off;
+        }
+        __syncthreads();   // S5
+
+        if (full)
+        {
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++)
+            {
+                const uint32_t p = j * THREADS + tid;
+                if (HAS_VALUES)
+                {
+                    const uint2 e = reinterpret_cast<const uint2*>(sm.kv)[p];
+                    const uint32_t g = sm.digit_base[digit_of(e.x, prmt_sel)] + p;
+                    keys_out[g] = e.x;
+                    vals_out[g] = e.y;
+                }
+                else
+                {
+                    const uint32_t k = sm.kv[p];
+                    keys_out[sm.digit_base[digit_of(k, prmt_sel)] + p] = k;
+                }
+            }
+        }
+        else
+        {
+            for (uint32_t p = tid; p < valid; p += THREADS)
+            {
+                const uint32_t k = sm.kv[p * (HAS_VALUES ? 2 : 1)];
+                const uint32_t g = sm.digit_base[digit_of(k, prmt_sel)] + p;
+                keys_out[g] = k;
+                if (HAS_VALUES) vals_out[g] = sm.kv[p * 2 + 1];
+            }
+        }
+        __syncthreads();   // S6: kv and warp_hist are free again, tile_next is visible
     }
 }
 
@@ -568,7 +839,7 @@ int launch_one(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const uint32
                uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t tiles)
 {
     auto kern = onesweep_pass_kernel<THREADS, ITEMS, LAYOUT, MATCH, MIN_BLOCKS>;
-    constexpr size_t smem = sizeof(onesweep_smem<THREADS, ITEMS, LAYOUT>);
+    constexpr size_t smem = sizeof(onesweep_smem<THREADS, ITEMS, LAYOUT, (MATCH & P2P_DEST) != 0>);
     VRENB200_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)));
     kern<<<tiles, THREADS, smem, s>>>(kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
     return check_launch();
@@ -586,14 +857,39 @@ int launch_onesweep(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const u
     }
 }
 
+template <int THREADS, int ITEMS, int MATCH, int MIN_BLOCKS>
+int launch_persistent(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout,
+                      uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t tiles, int layout)
+{
+    if (layout == LAYOUT_AOS)   // interleaved pairs (bucket sort) keep the one-tile-per-CTA kernel
+        return launch_one<THREADS, ITEMS, LAYOUT_AOS, MATCH | TILE_BY_BLOCKIDX, MIN_BLOCKS>(s, kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t) kNumSMs * MIN_BLOCKS);
+    if (layout == LAYOUT_SOA)
+    {
+        auto kern = onesweep_persistent_kernel<THREADS, ITEMS, LAYOUT_SOA, MATCH, MIN_BLOCKS>;
+        constexpr size_t smem = sizeof(persistent_smem<THREADS, ITEMS, LAYOUT_SOA>);
+        VRENB200_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)));
+        kern<<<grid, THREADS, smem, s>>>(kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    }
+    else
+    {
+        auto kern = onesweep_persistent_kernel<THREADS, ITEMS, LAYOUT_KEYS, MATCH, MIN_BLOCKS>;
+        constexpr size_t smem = sizeof(persistent_smem<THREADS, ITEMS, LAYOUT_KEYS>);
+        VRENB200_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)));
+        kern<<<grid, THREADS, smem, s>>>(kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    }
+    return check_launch();
+}
+
 #define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B> }
+#define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
 const sort_variant g_variants[] = {
     VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),   // 0: default (best of the sweeps in profiles/)
+    PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent CTAs + key prefetch
+    PVARIANT(256, 24, MATCH_BALLOT, 2),
+    PVARIANT(512, 16, MATCH_BALLOT, 1),
     VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),
     VARIANT(256, 28, TILE_BY_BLOCKIDX, 2),
-    VARIANT(288, 28, TILE_BY_BLOCKIDX, 2),
-    VARIANT(320, 24, TILE_BY_BLOCKIDX, 2),
-    VARIANT(256, 32, TILE_BY_BLOCKIDX | EARLY_HIST, 2),
     VARIANT(256, 32, MATCH_BALLOT, 2),       // ticket instead of block index
     VARIANT(256, 32, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 2),
 };
@@ -760,6 +1056,62 @@ extern "C" int vrenb200_radix_digit_histograms(vrenb200_stream_t stream, const u
 }
 
 extern "C" size_t vrenb200_radix_sort_range_scratch_bytes(uint32_t n) { return control_bytes(n); }
+
+// 256-bin histogram of the most significant byte only (one shared atomic per key instead of four)
+__global__ void __launch_bounds__(kHistThreads)
+radix_top_digit_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* hist_out)
+{
+    __shared__ uint32_t s_hist[kRadix];
+    if (threadIdx.x < kRadix) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n4 = n / 4;
+    const uint4* keys4 = reinterpret_cast<const uint4*>(keys);
+    for (uint32_t i = blockIdx.x * kHistThreads + threadIdx.x; i < n4; i += gridDim.x * kHistThreads)
+    {
+        const uint4 a = ldg_stream_u4(keys4 + i);
+        atomicAdd(&s_hist[a.x >> 24], 1u); atomicAdd(&s_hist[a.y >> 24], 1u);
+        atomicAdd(&s_hist[a.z >> 24], 1u); atomicAdd(&s_hist[a.w >> 24], 1u);
+    }
+    if (blockIdx.x == 0)
+        for (uint32_t t = n4 * 4 + threadIdx.x; t < n; t += kHistThreads) atomicAdd(&s_hist[keys[t] >> 24], 1u);
+    __syncthreads();
+    if (threadIdx.x < kRadix && s_hist[threadIdx.x] != 0) atomicAdd(&hist_out[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+extern "C" int vrenb200_radix_top_digit_histogram(vrenb200_stream_t stream, const uint32_t* keys, uint32_t n, uint32_t* hist_out)
+{
+    if (hist_out == nullptr || (n > 0 && keys == nullptr)) return VRENB200_EINVAL_ARG;
+    if (reinterpret_cast<uintptr_t>(keys) & 15) return VRENB200_EALIGN;
+    cudaStream_t s = as_stream(stream);
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(hist_out, 0, sizeof(uint32_t) * kRadix, s)));
+    if (n == 0) return VRENB200_OK;
+    radix_top_digit_histogram_kernel<<<kNumSMs * 4, kHistThreads, 0, s>>>(keys, n, hist_out);
+    return check_launch();
+}
+
+// Fused partition + exchange of the multi-GPU sort: one onesweep pass on the most significant byte whose write-out
+// stores every pair straight into its destination rank's receive buffer (plain st.global on peer-mapped pointers over
+// NVLink, or local memory for the rank's own range).  dest_table: device uint64[2][256], for every top digit the
+// address where THIS rank's run of that digit starts (keys, then values).  No histogram kernel is needed: the run
+// offsets come from the all-gathered histograms (vren_b200/dist.py).
+extern "C" int vrenb200_radix_partition_scatter(vrenb200_stream_t stream, const uint32_t* keys, const uint32_t* values, uint32_t n,
+                                                const uint64_t* dest_table, void* scratch, size_t scratch_bytes)
+{
+    if (n == 0) return VRENB200_OK;
+    if (keys == nullptr || values == nullptr || dest_table == nullptr) return VRENB200_EINVAL_ARG;
+    if (n >= (1u << 30)) return VRENB200_ELIMIT;
+    if (scratch == nullptr || scratch_bytes < control_bytes(n)) return VRENB200_ESCRATCH;
+    if ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(values) | reinterpret_cast<uintptr_t>(scratch)) & 15) return VRENB200_EALIGN;
+    cudaStream_t s = as_stream(stream);
+    constexpr int T = 256, I = 32;
+    const uint32_t tiles = (uint32_t) (((size_t) n + T * I - 1) / (T * I));
+    sort_control* ctl = static_cast<sort_control*>(scratch);
+    uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
+    const size_t clear = sizeof(sort_control) + (size_t) kPasses * tiles * kRadix * sizeof(uint32_t);
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, clear, s)));
+    return launch_one<T, I, LAYOUT_SOA, TILE_BY_BLOCKIDX | P2P_DEST, 2>(
+        s, keys, reinterpret_cast<uint32_t*>(const_cast<uint64_t*>(dest_table)), values, nullptr, n, kPasses - 1, ctl, lookback, tiles);
+}
 
 // stable sort by the digits [first_pass, first_pass + num_passes) only (8 bits each, pass 0 = least significant).
 // Ping-pongs between (keys, values) and (alt_keys, alt_values); *result_in_alt = num_passes & 1. values may be NULL.

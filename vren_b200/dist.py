@@ -52,6 +52,20 @@ class CudaOps:
                                                                  n, 3, 1, scratch.data_ptr(), sb, None), "radix_sort_pairs_range")
         return ok, ov
 
+    def top_digit_histogram(self, keys: torch.Tensor) -> torch.Tensor:
+        hist = torch.empty(256, dtype=torch.int32, device=keys.device)
+        self.vlib.check(self.lib.vrenb200_radix_top_digit_histogram(self._stream(), keys.data_ptr(), keys.numel(), hist.data_ptr()),
+                        "radix_top_digit_histogram")
+        return hist
+
+    def partition_scatter(self, keys: torch.Tensor, vals: torch.Tensor, dest_table: torch.Tensor):
+        """fused partition + exchange: pairs are stored straight at dest_table[0/1][top digit] (peer-mapped or local)"""
+        n = keys.numel()
+        sb = self.lib.vrenb200_radix_sort_range_scratch_bytes(n)
+        scratch = torch.empty(max(sb, 256), dtype=torch.uint8, device=keys.device)
+        self.vlib.check(self.lib.vrenb200_radix_partition_scatter(self._stream(), keys.data_ptr(), vals.data_ptr(), n, dest_table.data_ptr(),
+                                                                  scratch.data_ptr(), sb), "radix_partition_scatter")
+
     def sort_pairs(self, keys: torch.Tensor, vals: torch.Tensor):
         self.vlib.radix_sort_pairs(keys, vals)
         return keys, vals
@@ -123,6 +137,74 @@ def sharded_sort_pairs(keys: torch.Tensor, vals: torch.Tensor, ops=None, group=N
     dist.all_to_all_single(rk, pk, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts, group=group)
     dist.all_to_all_single(rv, pv, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts, group=group)
     ops.sort_pairs(rk, rv)
+    return rk, rv, plan
+
+
+def plan_p2p_offsets(hists: torch.Tensor, bounds: list, rank: int):
+    """receive-buffer layout of the fused exchange: rank r's buffer holds, for every top digit d of its range in ascending
+    order, the runs of source ranks 0..G-1 back to back.  hists: int64 [G, 256] (CPU).  Returns (dest_rank[256],
+    dest_offset[256] = element offset of THIS rank's run of digit d inside the destination's buffer, recv_count per rank)."""
+    world = hists.shape[0]
+    total = hists.sum(0)
+    dest_rank = torch.zeros(256, dtype=torch.int64)
+    dest_off = torch.zeros(256, dtype=torch.int64)
+    recv_counts = []
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        acc = 0
+        for d in range(lo, hi):
+            dest_rank[d] = r
+            dest_off[d] = acc + int(hists[:rank, d].sum())
+            acc += int(total[d])
+        recv_counts.append(acc)
+    return dest_rank, dest_off, recv_counts
+
+
+class P2PExchange:
+    """symmetric-memory receive buffers (keys, values) of one process group, created once and reused"""
+
+    def __init__(self, capacity: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.capacity = capacity
+        self.keys = symm.empty(capacity, dtype=torch.int32, device=device)
+        self.vals = symm.empty(capacity, dtype=torch.int32, device=device)
+        self.hk = symm.rendezvous(self.keys, self.group)
+        self.hv = symm.rendezvous(self.vals, self.group)
+        self.key_ptrs = [int(p) for p in self.hk.buffer_ptrs]
+        self.val_ptrs = [int(p) for p in self.hv.buffer_ptrs]
+
+    def barrier(self):
+        self.hk.barrier()
+
+
+def sharded_sort_pairs_p2p(keys: torch.Tensor, vals: torch.Tensor, exchange: P2PExchange, ops=None, group=None):
+    """same contract as sharded_sort_pairs, but the all-to-all is fused into the partition kernel: every rank's
+    onesweep pass on the top digit stores its pairs directly into the destination ranks' receive buffers through
+    NVLink peer pointers (no NCCL on the data path, no send-side staging copy)."""
+    ops = ops or CudaOps()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    hist = ops.top_digit_histogram(keys).to(torch.int64)
+    gathered = [torch.empty_like(hist) for _ in range(world)]
+    dist.all_gather(gathered, hist, group=group)
+    hists = torch.stack(gathered).cpu()
+    bounds = plan_digit_ranges(hists.sum(0), world)
+    dest_rank, dest_off, recv_counts = plan_p2p_offsets(hists, bounds, rank)
+    if max(recv_counts) > exchange.capacity:
+        raise RuntimeError(f"P2P receive buffer too small: need {max(recv_counts)} pairs, capacity {exchange.capacity}")
+    kp = torch.tensor(exchange.key_ptrs, dtype=torch.int64)[dest_rank] + 4 * dest_off
+    vp = torch.tensor(exchange.val_ptrs, dtype=torch.int64)[dest_rank] + 4 * dest_off
+    table = torch.stack([kp, vp]).contiguous().to(keys.device)
+    exchange.barrier()                       # every rank is done with the previous contents of the receive buffers
+    ops.partition_scatter(keys, vals, table)
+    exchange.barrier()                       # all remote stores into my buffers have completed
+    n_recv = recv_counts[rank]
+    rk, rv = exchange.keys[:n_recv], exchange.vals[:n_recv]
+    ops.sort_pairs(rk, rv)
+    per_dest = torch.stack([hists[:, bounds[r]:bounds[r + 1]].sum(1) for r in range(world)], dim=1)
+    plan = SortPlan(bounds, [int(v) for v in per_dest[rank]], [int(v) for v in per_dest[:, rank]])
     return rk, rv, plan
 
 

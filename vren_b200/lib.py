@@ -98,6 +98,8 @@ def load() -> C.CDLL:
 
 _vp, _u32, _sz, _i32 = C.c_void_p, C.c_uint32, C.c_size_t, C.c_int
 _LATE_SIGS = [
+    ("vrenb200_radix_top_digit_histogram", _i32, (_vp, _vp, _u32, _vp)),
+    ("vrenb200_radix_partition_scatter", _i32, (_vp, _vp, _vp, _u32, _vp, _vp, _sz)),
     ("vrenb200_exclusive_scan_u32_base", _i32, (_vp, _vp, _vp, _u32, _u32, _vp, _sz)),
     ("vrenb200_radix_digit_histograms", _i32, (_vp, _vp, _u32, _vp)),
     ("vrenb200_radix_sort_range_scratch_bytes", _sz, (_u32,)),
