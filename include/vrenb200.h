@@ -118,9 +118,10 @@ int vrenb200_radix_sort_pairs_range(vrenb200_stream_t stream, uint32_t* keys, ui
 
 /* histogram of the most significant byte only: hist_out device uint32[256] */
 int vrenb200_radix_top_digit_histogram(vrenb200_stream_t stream, const uint32_t* keys, uint32_t n, uint32_t* hist_out);
-/* fused partition + exchange: one onesweep pass on the most significant byte that stores every pair directly at
- * dest_table[0][digit] (keys) / dest_table[1][digit] (values) + its stable rank inside this rank's run of the digit.
- * dest_table: device uint64[2][256] of (possibly peer-mapped) addresses. scratch: vrenb200_radix_sort_range_scratch_bytes(n) */
+/* fused partition + exchange of the multi-GPU sort: one onesweep pass that partitions the pairs by DESTINATION RANK
+ * (rank_of[most significant byte]) and stores them, in input order, at kptr[rank] / vptr[rank] — plain stores on
+ * (possibly peer-mapped) addresses.  dest_table: device struct { uint64 kptr[32]; uint64 vptr[32]; uint8 rank_of[256]; }.
+ * scratch: vrenb200_radix_sort_range_scratch_bytes(n) */
 int vrenb200_radix_partition_scatter(vrenb200_stream_t stream, const uint32_t* keys, const uint32_t* values, uint32_t n,
                                      const uint64_t* dest_table, void* scratch, size_t scratch_bytes);
 

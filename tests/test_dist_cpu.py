@@ -127,22 +127,22 @@ def test_plan_digit_ranges_properties():
 
 
 def test_plan_p2p_offsets_tile_the_receive_buffers():
-    """the fused exchange writes every (src, digit) run at plan_p2p_offsets: runs must tile each receive buffer exactly,
-    ordered by (digit, source rank) so that the final local stable sort yields the global stable order"""
+    """the fused exchange writes every source's block at plan_p2p_offsets: blocks must tile each receive buffer exactly, in
+    source-rank order, so that the final local stable sort yields the global stable order"""
     rng = np.random.Generator(np.random.PCG64(7))
-    for world in (2, 4, 8):
+    for world in (1, 2, 4, 8):
         hists = torch.from_numpy(rng.integers(0, 50, size=(world, 256)).astype(np.int64))
         bounds = vdist.plan_digit_ranges(hists.sum(0), world)
-        cover = [dict() for _ in range(world)]
-        for src in range(world):
-            dest_rank, dest_off, recv_counts = vdist.plan_p2p_offsets(hists, bounds, src)
-            for d in range(256):
-                r = int(dest_rank[d])
-                assert bounds[r] <= d < bounds[r + 1]
-                cover[r][(d, src)] = (int(dest_off[d]), int(hists[src, d]))
-        for r in range(world):
+        plans = [vdist.plan_p2p_offsets(hists, bounds, src) for src in range(world)]
+        rank_of = plans[0][0]
+        for d in range(256):
+            r = int(rank_of[d])
+            assert bounds[r] <= d < bounds[r + 1]
+        for dst in range(world):
             pos = 0
-            for (d, src), (off, cnt) in sorted(cover[r].items()):
-                assert off == pos, (world, r, d, src)
-                pos += cnt
-            assert pos == recv_counts[r] == int(hists[:, bounds[r]:bounds[r + 1]].sum())
+            for src in range(world):
+                _, my_offset, recv_counts, per_dest = plans[src]
+                assert int(my_offset[dst]) == pos
+                pos += int(hists[src, bounds[dst]:bounds[dst + 1]].sum())
+                assert int(per_dest[src, dst]) == int(hists[src, bounds[dst]:bounds[dst + 1]].sum())
+            assert pos == plans[0][2][dst]

@@ -34,6 +34,15 @@ constexpr uint32_t kLbFlagInclusive = 2u << 30;
 constexpr uint32_t kLbValueMask = (1u << 30) - 1;
 
 constexpr uint32_t kBucketKeys = 1u << 16; // bucket_sort.hpp:15-16
+constexpr int kMaxRanks = 32;              // fused exchange: destinations per call
+
+// device table of the fused partition + exchange (vrenb200_radix_partition_scatter)
+struct p2p_table
+{
+    unsigned long long kptr[kMaxRanks];   // where THIS rank's block starts in every destination's key buffer
+    unsigned long long vptr[kMaxRanks];   // ... value buffer
+    uint8_t rank_of[kRadix];              // destination rank of a key, indexed by its most significant byte
+};
 
 // ---- control block carved from scratch ----------------------------------------------------------------------
 struct sort_control
@@ -241,7 +250,8 @@ struct onesweep_smem
     uint32_t digit_base[kRadix];
     uint32_t tile_hist[kRadix];       // EARLY_HIST: digit counts of the tile, known before the ranking
     // P2P_DEST: per-digit destination base pointers (keys, values), possibly in a peer GPU's memory
-    alignas(8) unsigned long long dst_ptr[P2P ? 2 : 1][P2P ? kRadix : 1];
+    alignas(8) unsigned long long dst_ptr[P2P ? 2 : 1][P2P ? kMaxRanks : 1];
+    uint8_t rank_of[P2P ? kRadix : 4];    // P2P_DEST: destination rank of every most-significant byte
     uint32_t scan_warp[kRadix / 32];
     alignas(8) uint64_t bar_keys;
     alignas(8) uint64_t bar_vals;
@@ -312,6 +322,17 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t prmt_sel = 0x4440u | (uint32_t) pass;   // byte `pass` of the key -> one PRMT per digit extraction
+    // P2P_DEST: the "digit" is the destination rank of the key (looked up by its most significant byte), so a tile
+    // produces one long run per destination instead of 256 short ones: long contiguous stores over NVLink
+    auto digit_of = [&](uint32_t k, uint32_t sel) -> uint32_t {
+        if (MATCH & P2P_DEST) return sm.rank_of[k >> 24];
+        return __byte_perm(k, 0u, sel);
+    };
+    if (MATCH & P2P_DEST)
+    {
+        const p2p_table* table = reinterpret_cast<const p2p_table*>(keys_out);
+        if (tid < kRadix) sm.rank_of[tid] = table->rank_of[tid];
+    }
 
     if (tid == 0)
     {
@@ -511,9 +532,12 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
         {
             // exchange mode: keys_out is a device table [2][256] of per-digit destination pointers (keys, values);
             // a digit's run starts at its pointer, this tile's slice of it at the look-back prefix
-            const unsigned long long* table = reinterpret_cast<const unsigned long long*>(keys_out);
-            sm.dst_ptr[0][tid] = table[tid];
-            sm.dst_ptr[(MATCH & P2P_DEST) ? 1 : 0][tid] = table[kRadix + tid];
+            const p2p_table* table = reinterpret_cast<const p2p_table*>(keys_out);
+            if (tid < kMaxRanks)
+            {
+                sm.dst_ptr[0][(MATCH & P2P_DEST) ? tid : 0] = table->kptr[tid];
+                sm.dst_ptr[(MATCH & P2P_DEST) ? 1 : 0][(MATCH & P2P_DEST) ? tid : 0] = table->vptr[tid];
+            }
             sm.digit_base[tid] = exclusive - tile_off;
         }
         else
@@ -625,7 +649,9 @@ onesweep_persistent_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __res
         mbar_init(&sm.bar_keys, 1);
         mbar_init(&sm.bar_vals, 1);
         mbar_fence_init();
-        const uint32_t t0 = atomicAdd(&ctl->tickets[pass], 1u);
+        // static striding (TILE_BY_BLOCKIDX: needs every CTA of the grid co-resident, guaranteed by the launcher) keeps
+        // consecutive tiles in lock-step; tickets are safe under any residency but start a tile one tile-time late
+        const uint32_t t0 = (MATCH & TILE_BY_BLOCKIDX) ? blockIdx.x : atomicAdd(&ctl->tickets[pass], 1u);
         sm.tile_next = t0;
         if (t0 < last_full_tiles)
         {
@@ -688,7 +714,7 @@ onesweep_persistent_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __res
 
         if (tid == 0)
         {
-            const uint32_t tn = atomicAdd(&ctl->tickets[pass], 1u);
+            const uint32_t tn = (MATCH & TILE_BY_BLOCKIDX) ? tile + gridDim.x : atomicAdd(&ctl->tickets[pass], 1u);
             sm.tile_next = tn;
             if (tn < last_full_tiles)
             {
@@ -863,12 +889,22 @@ int launch_persistent(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const
 {
     if (layout == LAYOUT_AOS)   // interleaved pairs (bucket sort) keep the one-tile-per-CTA kernel
         return launch_one<THREADS, ITEMS, LAYOUT_AOS, MATCH | TILE_BY_BLOCKIDX, MIN_BLOCKS>(s, kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
-    const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t) kNumSMs * MIN_BLOCKS);
+    uint32_t grid = std::min<uint32_t>(tiles, (uint32_t) kNumSMs * MIN_BLOCKS);
     if (layout == LAYOUT_SOA)
     {
         auto kern = onesweep_persistent_kernel<THREADS, ITEMS, LAYOUT_SOA, MATCH, MIN_BLOCKS>;
         constexpr size_t smem = sizeof(persistent_smem<THREADS, ITEMS, LAYOUT_SOA>);
         VRENB200_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)));
+        if (MATCH & TILE_BY_BLOCKIDX)
+        {
+            // static striding spins on tiles of other resident CTAs: never launch more CTAs than fit at once
+            int per_sm = 0, sms = 0, devid = 0;
+            VRENB200_TRY(check_cuda(cudaGetDevice(&devid)));
+            VRENB200_TRY(check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid)));
+            VRENB200_TRY(check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem)));
+            if (per_sm < 1) return VRENB200_ELIMIT;
+            grid = std::min<uint32_t>(tiles, (uint32_t) (per_sm * sms));
+        }
         kern<<<grid, THREADS, smem, s>>>(kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
     }
     else
@@ -885,9 +921,9 @@ int launch_persistent(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const
 #define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
 const sort_variant g_variants[] = {
     VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),   // 0: default (best of the sweeps in profiles/)
-    PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent CTAs + key prefetch
-    PVARIANT(256, 24, MATCH_BALLOT, 2),
-    PVARIANT(512, 16, MATCH_BALLOT, 1),
+    PVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // persistent CTAs + key prefetch, static tile striding
+    PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent, tickets
+    PVARIANT(256, 24, TILE_BY_BLOCKIDX, 2),
     VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),
     VARIANT(256, 28, TILE_BY_BLOCKIDX, 2),
     VARIANT(256, 32, MATCH_BALLOT, 2),       // ticket instead of block index
@@ -1091,9 +1127,10 @@ extern "C" int vrenb200_radix_top_digit_histogram(vrenb200_stream_t stream, cons
 
 // Fused partition + exchange of the multi-GPU sort: one onesweep pass on the most significant byte whose write-out
 // stores every pair straight into its destination rank's receive buffer (plain st.global on peer-mapped pointers over
-// NVLink, or local memory for the rank's own range).  dest_table: device uint64[2][256], for every top digit the
-// address where THIS rank's run of that digit starts (keys, then values).  No histogram kernel is needed: the run
-// offsets come from the all-gathered histograms (vren_b200/dist.py).
+// NVLink, or local memory for the rank's own range).  The pass partitions by DESTINATION RANK (a lookup on the most
+// significant byte), so every tile emits one long contiguous run per destination.  dest_table: device struct
+// { uint64 kptr[32]; uint64 vptr[32]; uint8 rank_of[256]; } — where THIS rank's block starts in every destination's
+// key / value buffer.  No histogram kernel is needed: the offsets come from the all-gathered histograms (dist.py).
 extern "C" int vrenb200_radix_partition_scatter(vrenb200_stream_t stream, const uint32_t* keys, const uint32_t* values, uint32_t n,
                                                 const uint64_t* dest_table, void* scratch, size_t scratch_bytes)
 {

@@ -120,7 +120,7 @@ def make_sort_plan(local_top_hist: torch.Tensor, group=None) -> SortPlan:
     dist.all_gather(gathered, local_top_hist, group=group)
     hists = torch.stack(gathered).cpu()                      # [world, 256]
     bounds = plan_digit_ranges(hists.sum(0), world)
-    per_dest = torch.stack([hists[:, bounds[r]:bounds[r + 1]].sum(1) for r in range(world)], dim=1)   # [src, dst]
+    per_dest = plan_p2p_offsets(hists, bounds, rank)[3]                                               # [src, dst]
     return SortPlan(bounds, [int(v) for v in per_dest[rank]], [int(v) for v in per_dest[:, rank]])
 
 
@@ -128,8 +128,8 @@ def sharded_sort_pairs(keys: torch.Tensor, vals: torch.Tensor, ops=None, group=N
     """globally stable sort by key of the pairs held by all ranks.  keys/vals: int32 storage of uint32 values.
     Returns (keys_out, vals_out, plan): rank r holds the pairs whose top digit falls in its range, sorted."""
     ops = ops or CudaOps()
-    hist = ops.digit_histograms(keys)
-    plan = make_sort_plan(hist[3].to(torch.int64), group)
+    hist = ops.top_digit_histogram(keys) if hasattr(ops, "top_digit_histogram") else ops.digit_histograms(keys)[3]
+    plan = make_sort_plan(hist.to(torch.int64), group)
     pk, pv = ops.partition_by_top_digit(keys, vals)
     n_recv = sum(plan.recv_counts)
     rk = torch.empty(n_recv, dtype=keys.dtype, device=keys.device)
@@ -141,23 +141,17 @@ def sharded_sort_pairs(keys: torch.Tensor, vals: torch.Tensor, ops=None, group=N
 
 
 def plan_p2p_offsets(hists: torch.Tensor, bounds: list, rank: int):
-    """receive-buffer layout of the fused exchange: rank r's buffer holds, for every top digit d of its range in ascending
-    order, the runs of source ranks 0..G-1 back to back.  hists: int64 [G, 256] (CPU).  Returns (dest_rank[256],
-    dest_offset[256] = element offset of THIS rank's run of digit d inside the destination's buffer, recv_count per rank)."""
+    """receive-buffer layout of the fused exchange: rank r's buffer holds one block per source rank, in source-rank order,
+    each block = that source's pairs whose top digit falls in r's range, in the source's original order.
+    hists: int64 [G, 256] (CPU).  Returns (rank_of[256] uint8, my_offset[G] = element offset of THIS rank's block inside
+    every destination's buffer, recv_counts[G])."""
     world = hists.shape[0]
-    total = hists.sum(0)
-    dest_rank = torch.zeros(256, dtype=torch.int64)
-    dest_off = torch.zeros(256, dtype=torch.int64)
-    recv_counts = []
-    for r in range(world):
-        lo, hi = bounds[r], bounds[r + 1]
-        acc = 0
-        for d in range(lo, hi):
-            dest_rank[d] = r
-            dest_off[d] = acc + int(hists[:rank, d].sum())
-            acc += int(total[d])
-        recv_counts.append(acc)
-    return dest_rank, dest_off, recv_counts
+    b = torch.tensor(bounds, dtype=torch.int64)
+    rank_of = (torch.bucketize(torch.arange(256), b[1:-1], right=True)).to(torch.uint8) if world > 1 else torch.zeros(256, dtype=torch.uint8)
+    csum = torch.cat([torch.zeros(world, 1, dtype=torch.int64), torch.cumsum(hists, 1)], dim=1)        # [G, 257]
+    per_dest = csum[:, b[1:]] - csum[:, b[:-1]]                                                        # [src, dst]
+    my_offset = per_dest[:rank].sum(0)
+    return rank_of, my_offset, [int(v) for v in per_dest.sum(0)], per_dest
 
 
 class P2PExchange:
@@ -191,19 +185,23 @@ def sharded_sort_pairs_p2p(keys: torch.Tensor, vals: torch.Tensor, exchange: P2P
     dist.all_gather(gathered, hist, group=group)
     hists = torch.stack(gathered).cpu()
     bounds = plan_digit_ranges(hists.sum(0), world)
-    dest_rank, dest_off, recv_counts = plan_p2p_offsets(hists, bounds, rank)
+    rank_of, my_offset, recv_counts, per_dest = plan_p2p_offsets(hists, bounds, rank)
     if max(recv_counts) > exchange.capacity:
         raise RuntimeError(f"P2P receive buffer too small: need {max(recv_counts)} pairs, capacity {exchange.capacity}")
-    kp = torch.tensor(exchange.key_ptrs, dtype=torch.int64)[dest_rank] + 4 * dest_off
-    vp = torch.tensor(exchange.val_ptrs, dtype=torch.int64)[dest_rank] + 4 * dest_off
-    table = torch.stack([kp, vp]).contiguous().to(keys.device)
+    if world > 32:
+        raise RuntimeError("fused exchange supports up to 32 ranks")
+    # device table {u64 kptr[32]; u64 vptr[32]; u8 rank_of[256]} (vrenb200_radix_partition_scatter)
+    kp = torch.zeros(32, dtype=torch.int64)
+    vp = torch.zeros(32, dtype=torch.int64)
+    kp[:world] = torch.tensor(exchange.key_ptrs, dtype=torch.int64) + 4 * my_offset
+    vp[:world] = torch.tensor(exchange.val_ptrs, dtype=torch.int64) + 4 * my_offset
+    table = torch.cat([kp.view(torch.uint8), vp.view(torch.uint8), rank_of]).to(keys.device, non_blocking=True)
     exchange.barrier()                       # every rank is done with the previous contents of the receive buffers
     ops.partition_scatter(keys, vals, table)
     exchange.barrier()                       # all remote stores into my buffers have completed
     n_recv = recv_counts[rank]
     rk, rv = exchange.keys[:n_recv], exchange.vals[:n_recv]
     ops.sort_pairs(rk, rv)
-    per_dest = torch.stack([hists[:, bounds[r]:bounds[r + 1]].sum(1) for r in range(world)], dim=1)
     plan = SortPlan(bounds, [int(v) for v in per_dest[rank]], [int(v) for v in per_dest[:, rank]])
     return rk, rv, plan
 
