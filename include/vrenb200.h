@@ -209,6 +209,25 @@ int vrenb200_assign_lights(vrenb200_stream_t stream,
                            uint32_t* counts_out, uint32_t* offsets_out, uint32_t* status_out,
                            void* scratch, size_t scratch_bytes);
 
+/* ---- n1: consumer side of the light lists (shade.comp:101-105, vren_demo show_clusters.comp:97-118) -------- */
+/* out_count_hash: uvec2[W*H] = {assigned_light_counts[cluster_reference(x,y)], XOR of that cluster's light indices} */
+size_t vrenb200_light_list_hash_scratch_bytes(uint32_t max_keys);
+int vrenb200_light_list_hash(vrenb200_stream_t stream, uint32_t width, uint32_t height, const uint32_t* cluster_ref,
+                             const uint32_t* dispatch_params, uint32_t max_keys, const uint32_t* counts,
+                             const uint32_t* offsets, const uint32_t* indices, uint32_t max_assigned,
+                             uint32_t* out_count_hash, void* scratch, size_t scratch_bytes);
+
+/* ---- n2: depth-buffer pyramid (pipeline/depth_buffer_pyramid.{hpp,cpp}, depth_buffer_{copy,reduce}.comp) ----- */
+/* level_count = floor(log2(max(W,H))) + 1 (depth_buffer_pyramid.cpp:18); level l is max(W>>l,1) x max(H>>l,1) */
+uint32_t vrenb200_depth_pyramid_level_count(uint32_t width, uint32_t height);
+uint32_t vrenb200_depth_pyramid_level_width(uint32_t width, uint32_t level);
+uint32_t vrenb200_depth_pyramid_level_height(uint32_t height, uint32_t level);
+/* the mip chain is one flat float buffer, levels back to back: element offset of a level, total size in bytes */
+size_t vrenb200_depth_pyramid_level_offset(uint32_t width, uint32_t height, uint32_t level);
+size_t vrenb200_depth_pyramid_bytes(uint32_t width, uint32_t height);
+/* depth_buffer_reductor::copy_and_reduce (depth_buffer_pyramid.cpp:177-305): level 0 = copy, level l+1 = 2x2 max */
+int vrenb200_depth_pyramid_build(vrenb200_stream_t stream, const float* depth, uint32_t width, uint32_t height, float* pyramid);
+
 #ifdef __cplusplus
 }
 #endif

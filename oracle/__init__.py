@@ -85,6 +85,8 @@ class Camera(C.Structure):
 
 
 _LATE: list = [
+    ("oracle_light_list_hash", None, (C.c_uint32, C.c_uint32, u32p, u32p, u32p, u32p, u32p)),
+    ("oracle_depth_pyramid", C.c_uint32, (f32p, C.c_uint32, C.c_uint32, f32p)),
     ("oracle_construct_point_light_bvh", None, (f32p, f32p, C.c_uint32, f32p, f32p, voidp, u32p)),
     ("oracle_find_unique_clusters", C.c_uint32, (f32p, voidp, C.c_uint32, C.c_uint32, C.POINTER(Camera), u32p, u32p)),
     ("oracle_assign_lights", C.c_uint64,
@@ -234,3 +236,28 @@ def build_bvh(nodes: np.ndarray, padded: int) -> np.ndarray:
     nodes = np.ascontiguousarray(nodes).copy()
     load().oracle_build_bvh(nodes.ctypes.data, padded)
     return nodes
+
+
+def depth_pyramid(depth: np.ndarray):
+    """-> (flat pyramid float32, level_count)"""
+    lib = load()
+    H, W = depth.shape
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    total, l = 0, 0
+    while True:
+        w, h = max(W >> l, 1), max(H >> l, 1)
+        total += w * h
+        l += 1
+        if w == 1 and h == 1:
+            break
+    out = np.zeros(total, np.float32)
+    levels = lib.oracle_depth_pyramid(depth.reshape(-1), W, H, out)
+    return out, int(levels)
+
+
+def light_list_hash(cluster_ref: np.ndarray, counts: np.ndarray, offsets: np.ndarray, indices: np.ndarray) -> np.ndarray:
+    H, W = cluster_ref.shape
+    out = np.zeros(H * W * 2, np.uint32)
+    load().oracle_light_list_hash(W, H, np.ascontiguousarray(cluster_ref, dtype=np.uint32).reshape(-1), np.ascontiguousarray(counts, dtype=np.uint32),
+                                  np.ascontiguousarray(offsets, dtype=np.uint32), np.ascontiguousarray(indices, dtype=np.uint32), out)
+    return out.reshape(H, W, 2)

@@ -382,4 +382,56 @@ uint64_t oracle_assign_lights(uint32_t W, uint32_t H, const camera_t* cam, const
     return total;
 }
 
+// ---- n2: depth-buffer pyramid -------------------------------------------------------------------------------------------
+// depth_buffer_copy.comp:8-18 (level 0 = copy) + depth_buffer_reduce.comp:10-35 per level (depth_buffer_pyramid.cpp:177-305).
+// pyramid: levels back to back, level l = max(W>>l,1) x max(H>>l,1), level_count = floor(log2(max(W,H))) + 1 (:18).
+uint32_t oracle_depth_pyramid(const float* depth, uint32_t W, uint32_t H, float* pyramid)
+{
+    uint32_t levels = 1;
+    for (uint32_t m = W > H ? W : H; m >>= 1;) levels++;
+    std::memcpy(pyramid, depth, (size_t) W * H * sizeof(float));
+    const float* from = pyramid;
+    uint32_t fw = W, fh = H;
+    float* to = pyramid + (size_t) W * H;
+    for (uint32_t l = 1; l < levels; l++)
+    {
+        const uint32_t tw = (W >> l) ? (W >> l) : 1u, th = (H >> l) ? (H >> l) : 1u;
+        for (uint32_t y = 0; y < th; y++)
+            for (uint32_t x = 0; x < tw; x++)
+            {
+                float max_depth = 0.0f;
+                for (uint32_t dx = 0; dx < 2; dx++)
+                    for (uint32_t dy = 0; dy < 2; dy++)
+                    {
+                        const uint32_t sx = 2 * x + dx, sy = 2 * y + dy;
+                        if (sx < fw && sy < fh)
+                        {
+                            const float d = from[(size_t) sy * fw + sx];
+                            max_depth = max_depth < d ? d : max_depth;   // GLSL max(max_depth, depth)
+                        }
+                    }
+                to[(size_t) y * tw + x] = max_depth;
+            }
+        from = to;
+        to += (size_t) tw * th;
+        fw = tw; fh = th;
+    }
+    return levels;
+}
+
+// ---- n1: per-pixel walk of the light lists ------------------------------------------------------------------------------
+// shade.comp:101-105 access pattern with the integer payload of show_clusters.comp:97-118 (count, XOR of the indices)
+void oracle_light_list_hash(uint32_t W, uint32_t H, const uint32_t* cluster_ref, const uint32_t* counts, const uint32_t* offsets,
+                            const uint32_t* indices, uint32_t* out_count_hash)
+{
+    for (size_t p = 0; p < (size_t) W * H; p++)
+    {
+        const uint32_t c = cluster_ref[p];
+        uint32_t h = 0;
+        for (uint32_t i = 0; i < counts[c]; i++) h ^= indices[offsets[c] + i];
+        out_count_hash[2 * p] = counts[c];
+        out_count_hash[2 * p + 1] = h;
+    }
+}
+
 } // extern "C"

@@ -12,6 +12,7 @@
 
 #include "vren/context.hpp"
 #include "vren/pipeline/clustered_shading.hpp"
+#include "vren/pipeline/depth_buffer_pyramid.hpp"
 
 static int g_failures = 0;
 #define EXPECT(cond, ...)                                            \
@@ -287,6 +288,48 @@ static void test_cluster_and_shade(vren::context& ctx)
     std::printf("ok cluster_and_shade (%u clusters, %llu assignments)\n", disp[0], (unsigned long long) total);
 }
 
+// depth pyramid: every level is the 2x2 max of the level below (depth_buffer_reduce.comp:20-31)
+static void test_depth_pyramid(vren::context& ctx)
+{
+    const uint32_t W = 333, H = 200;
+    std::mt19937 rng(6);
+    std::uniform_real_distribution<float> u(0, 1);
+    std::vector<float> depth((size_t) W * H);
+    for (auto& d : depth) d = u(rng);
+    vren::vk_utils::depth_buffer_t db{vren::vk_utils::alloc_device_only_buffer(ctx, depth.size() * 4)};
+    upload(db.m_image, depth);
+    vren::depth_buffer_pyramid pyramid(ctx, W, H);
+    vren::depth_buffer_reductor reductor(ctx);
+    vren::vk_utils::immediate_graphics_queue_submit(ctx, [&](VkCommandBuffer cmd, vren::resource_container&) {
+        reductor.copy_and_reduce(cmd, db, pyramid);
+    });
+    EXPECT(pyramid.get_level_count() == 9, "level count %u", pyramid.get_level_count());
+    auto all = download<float>(pyramid.m_image, pyramid.m_image.m_size / 4);
+    std::vector<float> prev = depth;
+    uint32_t pw = W, ph = H;
+    size_t off = (size_t) W * H;
+    EXPECT(std::equal(depth.begin(), depth.end(), all.begin()), "level 0 must be a copy");
+    for (uint32_t l = 1; l < pyramid.get_level_count(); l++)
+    {
+        const uint32_t w = pyramid.get_image_width(l), h = pyramid.get_image_height(l);
+        std::vector<float> cur((size_t) w * h);
+        for (uint32_t y = 0; y < h; y++)
+            for (uint32_t x = 0; x < w; x++)
+            {
+                float m = 0.0f;
+                for (uint32_t dx = 0; dx < 2; dx++)
+                    for (uint32_t dy = 0; dy < 2; dy++)
+                        if (2 * x + dx < pw && 2 * y + dy < ph) m = std::max(m, prev[(size_t) (2 * y + dy) * pw + 2 * x + dx]);
+                cur[(size_t) y * w + x] = m;
+                EXPECT(all[off + (size_t) y * w + x] == m, "pyramid level %u texel (%u,%u)", l, x, y);
+            }
+        off += cur.size();
+        prev.swap(cur);
+        pw = w; ph = h;
+    }
+    std::printf("ok depth_buffer_pyramid\n");
+}
+
 int main()
 {
     try
@@ -298,6 +341,7 @@ int main()
         test_bucket_sort(ctx);
         test_build_bvh(ctx);
         test_cluster_and_shade(ctx);
+        test_depth_pyramid(ctx);
     }
     catch (std::exception const& e)
     {

@@ -131,3 +131,19 @@ def test_cluster_chain_c5_full_size(vren):
     assert np.array_equal(counts, wcounts) and np.array_equal(offsets, woffsets)
     assert status[0] == wtotal and status[1] == 0
     assert np.array_equal(indices[:wtotal], windices[:wtotal])
+
+
+@pytest.mark.parametrize("w,h,L", [(96, 64, 50), (640, 360, 4000), (1920, 1080, 65536)])
+def test_light_list_consumer_n1(vren, w, h, L):
+    """per-pixel walk cluster_reference -> counts/offsets -> indices (shade.comp:101-105)"""
+    depth = synthetic.depth_buffer(w, h, seed=w * 3 + L)
+    pos, lights = synthetic.point_lights(L, seed=L + 1, aspect=w / h, intensity=(0.5, 3.0))
+    view = synthetic.view_matrix(0.0, 0.0, (0.0, 0.0, 0.0))
+    oc, vc = both_cameras(vren, w, h)
+    vp, bvh, idx = vren.construct_point_light_bvh(dev(pos), dev(lights), view.tolist())
+    keys, disp, ref = vren.find_unique_clusters(dev(depth), None, vc)
+    counts, offsets, indices, status = vren.assign_lights(w, h, vc, keys, disp, bvh, L, idx, vp)
+    got = host_u32(vren.light_list_hash(ref, disp, counts, offsets, indices)).reshape(h, w, 2)
+    want = oracle.light_list_hash(host_u32(ref).reshape(h, w), host_u32(counts), host_u32(offsets), host_u32(indices))
+    assert np.array_equal(got, want)
+    assert int(got[..., 0].max()) > 0

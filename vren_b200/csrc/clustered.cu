@@ -804,3 +804,64 @@ extern "C" int vrenb200_assign_lights(vrenb200_stream_t stream,
     }
 #undef VRENB200_ASSIGN
 }
+
+// ---- n1: the consumer side of the light lists ---------------------------------------------------------------
+// Per pixel: cluster = cluster_reference(x, y); walk indices[offsets[cluster] .. + counts[cluster]) — the access pattern of
+// shade.comp:101-105 — and emit {count, XOR of the light indices}, the integer core of the demo's list visualiser
+// (vren_demo/resources/shaders/show_clusters.comp:97-118).  The reference walks the list once per PIXEL; every pixel of
+// a cluster sees the same list, so here the XOR is folded once per CLUSTER (one warp each) and the per-pixel kernel is a
+// pure gather: 4 B/px read + 8 B/px written instead of ~count x 4 B/px of L2 traffic.
+namespace vrenb200 {
+namespace {
+
+__global__ void __launch_bounds__(256)
+cluster_list_hash_kernel(const uint32_t* __restrict__ dispatch_params, uint32_t max_keys, const uint32_t* __restrict__ counts,
+                         const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ indices, uint32_t max_assigned,
+                         uint32_t* __restrict__ cluster_hash)
+{
+    const uint32_t count = min(dispatch_params[0], max_keys);
+    const unsigned lane = threadIdx.x & 31;
+    for (uint32_t c = (blockIdx.x * 256u + threadIdx.x) >> 5; c < count; c += (gridDim.x * 256u) >> 5)
+    {
+        const uint32_t n = counts[c], off = offsets[c];
+        uint32_t h = 0;
+        for (uint32_t i = lane; i < n; i += 32)
+            if (off + i < max_assigned) h ^= indices[off + i];
+        h = __reduce_xor_sync(kFullMask, h);
+        if (lane == 0) cluster_hash[c] = h;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pixel_light_list_kernel(const uint32_t* __restrict__ cluster_ref, uint32_t pixels, uint32_t max_keys, const uint32_t* __restrict__ counts,
+                        const uint32_t* __restrict__ cluster_hash, uint2* __restrict__ out)
+{
+    for (uint32_t p = blockIdx.x * 256u + threadIdx.x; p < pixels; p += gridDim.x * 256u)
+    {
+        const uint32_t c = cluster_ref[p];
+        out[p] = c < max_keys ? make_uint2(counts[c], cluster_hash[c]) : make_uint2(0u, 0u);
+    }
+}
+
+} // namespace
+} // namespace vrenb200
+
+extern "C" size_t vrenb200_light_list_hash_scratch_bytes(uint32_t max_keys) { return align_up((size_t) max_keys * 4, 256); }
+
+extern "C" int vrenb200_light_list_hash(vrenb200_stream_t stream, uint32_t width, uint32_t height, const uint32_t* cluster_ref,
+                                        const uint32_t* dispatch_params, uint32_t max_keys, const uint32_t* counts,
+                                        const uint32_t* offsets, const uint32_t* indices, uint32_t max_assigned,
+                                        uint32_t* out_count_hash, void* scratch, size_t scratch_bytes)
+{
+    if (!cluster_ref || !dispatch_params || !counts || !offsets || !indices || !out_count_hash) return VRENB200_EINVAL_ARG;
+    if (width == 0 || height == 0 || max_keys == 0) return VRENB200_EINVAL_LENGTH;
+    if (scratch == nullptr || scratch_bytes < vrenb200_light_list_hash_scratch_bytes(max_keys)) return VRENB200_ESCRATCH;
+    if (reinterpret_cast<uintptr_t>(out_count_hash) & 7) return VRENB200_EALIGN;
+    cudaStream_t s = as_stream(stream);
+    uint32_t* cluster_hash = static_cast<uint32_t*>(scratch);
+    cluster_list_hash_kernel<<<kNumSMs * 8, 256, 0, s>>>(dispatch_params, max_keys, counts, offsets, indices, max_assigned, cluster_hash);
+    VRENB200_TRY(check_launch());
+    const uint32_t pixels = width * height;
+    pixel_light_list_kernel<<<kNumSMs * 16, 256, 0, s>>>(cluster_ref, pixels, max_keys, counts, cluster_hash, reinterpret_cast<uint2*>(out_count_hash));
+    return check_launch();
+}

@@ -258,7 +258,7 @@ struct onesweep_smem
     uint32_t tile;
 };
 
-enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8 }; // option bits of the MATCH template argument
+enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8, DEPHASE = 16 }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -661,6 +661,10 @@ onesweep_persistent_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __res
     }
     __syncthreads();
     uint32_t kphase = 0, vphase = 0;
+    // DEPHASE: statically strided CTAs start in lock-step, so the two CTAs of an SM would rank at the same time and write
+    // at the same time; delaying every other CTA by about half a tile keeps one of them in its ALU phase while the
+    // other is in its memory phase
+    if ((MATCH & DEPHASE) && (blockIdx.x & 1)) __nanosleep(4000);
 
     while (true)
     {
@@ -922,8 +926,8 @@ int launch_persistent(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const
 const sort_variant g_variants[] = {
     VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),   // 0: default (best of the sweeps in profiles/)
     PVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // persistent CTAs + key prefetch, static tile striding
+    PVARIANT(256, 32, TILE_BY_BLOCKIDX | DEPHASE, 2),
     PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent, tickets
-    PVARIANT(256, 24, TILE_BY_BLOCKIDX, 2),
     VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),
     VARIANT(256, 28, TILE_BY_BLOCKIDX, 2),
     VARIANT(256, 32, MATCH_BALLOT, 2),       // ticket instead of block index

@@ -38,8 +38,7 @@ __global__ void __launch_bounds__(kScanThreads)
 exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_state* state, uint32_t base)
 {
     __shared__ uint32_t s_warp_total[kScanWarps];
-    __shared__ uint32_t s_lb_sum[kScanWarps];
-    __shared__ uint32_t s_lb_found[kScanWarps];
+    __shared__ uint32_t s_tile_prefix;
 
     const uint32_t tile = blockIdx.x;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -95,49 +94,53 @@ exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_st
         tile_total += t;
     }
 
-    // decoupled look-back with a CTA-wide window: 256 predecessors per probe (thread i looks at tile-1-i), because
-    // with ~1000 tiles in flight a 32-wide window needs dozens of dependent L2 round trips per tile
-    uint64_t* status = state->status;
-    if (threadIdx.x == 0)
-        st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | tile_total);
-    uint32_t exclusive = 0;
-    if (tile > 0)
+    // decoupled look-back by warp 0: four 32-wide windows (128 predecessors) are fetched per L2 round trip and then
+    // consumed nearest first.  (A CTA-wide 256-lane window and a persistent TMA-prefetch variant were measured slower:
+    // profiles/r1g_*.)
+    if (warp == 0)
     {
-        int64_t window = (int64_t) tile - 1;
-        while (true)
+        uint64_t* status = state->status;
+        if (lane == 0)
+            st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | tile_total);
+        uint32_t exclusive = 0;
+        if (tile > 0)
         {
-            const int64_t t = window - threadIdx.x;
-            uint64_t s = kFlagInclusive; // virtual tile before tile 0: inclusive prefix 0
-            if (t >= 0)
+            constexpr int K = 2;
+            int64_t window = (int64_t) tile - 1;
+            bool done = false;
+            while (!done)
             {
-                do { s = ld_relaxed_u64(&status[t]); } while ((s >> 32) == 0);
-            }
-            const unsigned incl = __ballot_sync(kFullMask, (s >> 32) == 2);
-            uint32_t val = (uint32_t) s;
-            if (incl != 0 && lane > (unsigned) (__ffs(incl) - 1)) val = 0;
-            val = __reduce_add_sync(kFullMask, val);
-            if (lane == 0)
-            {
-                s_lb_sum[warp] = val;
-                s_lb_found[warp] = incl != 0;
-            }
-            __syncthreads();
-            bool found = false;
+                uint64_t s[K];
 #pragma unroll
-            for (int w = 0; w < kScanWarps; w++)
-            {
-                if (!found)
+                for (int k = 0; k < K; k++)
                 {
-                    exclusive += s_lb_sum[w];
-                    found = s_lb_found[w] != 0;
+                    const int64_t t = window - 32 * k - lane;
+                    s[k] = t >= 0 ? ld_relaxed_u64(&status[t]) : kFlagInclusive; // virtual tiles before tile 0: inclusive 0
                 }
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                {
+                    if (done) break;
+                    const int64_t t = window - 32 * k - lane;
+                    while ((s[k] >> 32) == 0)
+                    {
+                        __nanosleep(100);   // back off: hundreds of tiles poll the same few status lines in L2
+                        s[k] = ld_relaxed_u64(&status[t]);
+                    }
+                    const unsigned incl = __ballot_sync(kFullMask, (s[k] >> 32) == 2);
+                    uint32_t val = (uint32_t) s[k];
+                    if (incl != 0 && lane > (unsigned) (__ffs(incl) - 1)) val = 0;
+                    exclusive += __reduce_add_sync(kFullMask, val);
+                    done = incl != 0;
+                }
+                window -= 32 * K;
             }
-            __syncthreads();
-            if (found) break;
-            window -= kScanThreads;
+            if (lane == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (exclusive + tile_total));
         }
-        if (threadIdx.x == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (exclusive + tile_total));
+        if (lane == 0) s_tile_prefix = exclusive;
     }
+    __syncthreads();
+    const uint32_t exclusive = s_tile_prefix;
     const uint32_t prefix = exclusive + warp_prefix + base;
 
 #pragma unroll
@@ -154,170 +157,6 @@ exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_st
             if (idx + 2 < n) out[idx + 2] = x[v].z;
             if (idx + 3 < n) out[idx + 3] = x[v].w;
         }
-    }
-}
-
-// ---- persistent variant: the next tile is prefetched by a TMA bulk copy while the current one is scanned ----------
-// With one-tile-per-CTA the DRAM latency of the tile load and the L2 round trips of the look-back add up on every
-// tile.  Here a CTA loops over tiles (static striding, grid = what is resident at once), double-buffers the input in
-// shared memory (cp.async.bulk + mbarrier) and only ever exposes the look-back.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
-
-__global__ void __launch_bounds__(kScanThreads)
-exclusive_scan_u32_persistent_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_state* state, uint32_t base,
-                                     uint32_t num_tiles)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw);                       // [2][kScanTile]
-    __shared__ alignas(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_warp_total[kScanWarps];
-    __shared__ uint32_t s_lb_sum[kScanWarps];
-    __shared__ uint32_t s_lb_found[kScanWarps];
-
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t full_tiles = n / kScanTile;
-    const bool out_vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    uint64_t* status = state->status;
-
-    auto issue = [&](uint32_t t, int b) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&s_bar[b])), "r"(kScanTile * 4u) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_addr(stage + b * kScanTile)), "l"(in + (uint64_t) t * kScanTile), "r"(kScanTile * 4u), "r"(smem_addr(&s_bar[b])) : "memory");
-    };
-    if (threadIdx.x == 0)
-    {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_bar[0])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_bar[1])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (blockIdx.x < full_tiles) issue(blockIdx.x, 0);
-    }
-    __syncthreads();
-    uint32_t parity[2] = {0u, 0u};
-    int buf = 0;
-
-    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, buf ^= 1)
-    {
-        const uint32_t next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < full_tiles) issue(next, buf ^ 1);   // stage[buf^1] was consumed one iteration ago
-        const uint64_t warp_base = (uint64_t) tile * kScanTile + warp * kWarpChunk;
-        uint4 x[kScanVecs];
-        if (tile < full_tiles)
-        {
-            asm volatile(
-                "{\n"
-                ".reg .pred p;\n"
-                "W_%=:\n"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                "@p bra D_%=;\n"
-                "bra W_%=;\n"
-                "D_%=:\n"
-                "}\n" ::"r"(smem_addr(&s_bar[buf])), "r"(parity[buf]) : "memory");
-            parity[buf] ^= 1;
-            const uint4* src = reinterpret_cast<const uint4*>(stage + buf * kScanTile + warp * kWarpChunk);
-#pragma unroll
-            for (int v = 0; v < kScanVecs; v++) x[v] = src[v * 32 + lane];
-        }
-        else
-        {
-#pragma unroll
-            for (int v = 0; v < kScanVecs; v++)
-            {
-                const uint64_t idx = warp_base + v * 128 + lane * 4;
-                x[v].x = idx + 0 < n ? in[idx + 0] : 0u;
-                x[v].y = idx + 1 < n ? in[idx + 1] : 0u;
-                x[v].z = idx + 2 < n ? in[idx + 2] : 0u;
-                x[v].w = idx + 3 < n ? in[idx + 3] : 0u;
-            }
-        }
-
-        uint32_t carry = 0;
-#pragma unroll
-        for (int v = 0; v < kScanVecs; v++)
-        {
-            const uint32_t a = x[v].x, b = x[v].y, c = x[v].z, d = x[v].w;
-            const uint32_t total = a + b + c + d;
-            uint32_t inc = total;
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1)
-            {
-                const uint32_t t = __shfl_up_sync(kFullMask, inc, s);
-                if (lane >= (unsigned) s) inc += t;
-            }
-            const uint32_t vb = carry + inc - total;
-            carry += __shfl_sync(kFullMask, inc, 31);
-            x[v].x = vb;
-            x[v].y = vb + a;
-            x[v].z = vb + a + b;
-            x[v].w = vb + a + b + c;
-        }
-        if (lane == 31) s_warp_total[warp] = carry;
-        __syncthreads();
-        uint32_t warp_prefix = 0, tile_total = 0;
-#pragma unroll
-        for (int w = 0; w < kScanWarps; w++)
-        {
-            const uint32_t t = s_warp_total[w];
-            if (w < (int) warp) warp_prefix += t;
-            tile_total += t;
-        }
-
-        if (threadIdx.x == 0)
-            st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | tile_total);
-        uint32_t exclusive = 0;
-        if (tile > 0)
-        {
-            int64_t window = (int64_t) tile - 1;
-            while (true)
-            {
-                const int64_t t = window - threadIdx.x;
-                uint64_t s = kFlagInclusive;
-                if (t >= 0)
-                {
-                    do { s = ld_relaxed_u64(&status[t]); } while ((s >> 32) == 0);
-                }
-                const unsigned incl = __ballot_sync(kFullMask, (s >> 32) == 2);
-                uint32_t val = (uint32_t) s;
-                if (incl != 0 && lane > (unsigned) (__ffs(incl) - 1)) val = 0;
-                val = __reduce_add_sync(kFullMask, val);
-                if (lane == 0)
-                {
-                    s_lb_sum[warp] = val;
-                    s_lb_found[warp] = incl != 0;
-                }
-                __syncthreads();
-                bool found = false;
-#pragma unroll
-                for (int w = 0; w < kScanWarps; w++)
-                {
-                    if (!found)
-                    {
-                        exclusive += s_lb_sum[w];
-                        found = s_lb_found[w] != 0;
-                    }
-                }
-                __syncthreads();
-                if (found) break;
-                window -= kScanThreads;
-            }
-            if (threadIdx.x == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (exclusive + tile_total));
-        }
-        const uint32_t prefix = exclusive + warp_prefix + base;
-#pragma unroll
-        for (int v = 0; v < kScanVecs; v++)
-        {
-            const uint64_t idx = warp_base + v * 128 + lane * 4;
-            x[v].x += prefix; x[v].y += prefix; x[v].z += prefix; x[v].w += prefix;
-            if (out_vec_ok && idx + 4 <= n)
-                *reinterpret_cast<uint4*>(out + idx) = x[v];
-            else
-            {
-                if (idx + 0 < n) out[idx + 0] = x[v].x;
-                if (idx + 1 < n) out[idx + 1] = x[v].y;
-                if (idx + 2 < n) out[idx + 2] = x[v].z;
-                if (idx + 3 < n) out[idx + 3] = x[v].w;
-            }
-        }
-        __syncthreads();   // s_warp_total / stage[buf] are free for the iteration after next
     }
 }
 
@@ -381,27 +220,6 @@ extern "C" int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const 
     cudaStream_t s = as_stream(stream);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, need, s)));
     const uint32_t tiles = (uint32_t) (((size_t) n + kScanTile - 1) / kScanTile);
-    // persistent + TMA-prefetch kernel when the input allows bulk copies (16-byte aligned) and there is more than a
-    // wave of tiles; otherwise one tile per CTA
-    if ((reinterpret_cast<uintptr_t>(in) & 15) == 0 && tiles > 2u * kNumSMs)
-    {
-        constexpr size_t smem = 2 * kScanTile * sizeof(uint32_t);
-        static int per_sm = 0, sms = 0;
-        if (per_sm == 0)
-        {
-            int devid = 0;
-            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_u32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)));
-            VRENB200_TRY(check_cuda(cudaGetDevice(&devid)));
-            VRENB200_TRY(check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid)));
-            VRENB200_TRY(check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exclusive_scan_u32_persistent_kernel, kScanThreads, smem)));
-        }
-        if (per_sm >= 1)
-        {
-            const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t) (per_sm * sms));   // every CTA resident: static striding is safe
-            exclusive_scan_u32_persistent_kernel<<<grid, kScanThreads, smem, s>>>(in, out, n, static_cast<scan_state*>(scratch), base, tiles);
-            return check_launch();
-        }
-    }
     exclusive_scan_u32_kernel<<<tiles, kScanThreads, 0, s>>>(in, out, n, static_cast<scan_state*>(scratch), base);
     return check_launch();
 }

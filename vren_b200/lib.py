@@ -98,6 +98,14 @@ def load() -> C.CDLL:
 
 _vp, _u32, _sz, _i32 = C.c_void_p, C.c_uint32, C.c_size_t, C.c_int
 _LATE_SIGS = [
+    ("vrenb200_light_list_hash_scratch_bytes", _sz, (_u32,)),
+    ("vrenb200_light_list_hash", _i32, (_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _sz)),
+    ("vrenb200_depth_pyramid_level_count", _u32, (_u32, _u32)),
+    ("vrenb200_depth_pyramid_level_width", _u32, (_u32, _u32)),
+    ("vrenb200_depth_pyramid_level_height", _u32, (_u32, _u32)),
+    ("vrenb200_depth_pyramid_level_offset", _sz, (_u32, _u32, _u32)),
+    ("vrenb200_depth_pyramid_bytes", _sz, (_u32, _u32)),
+    ("vrenb200_depth_pyramid_build", _i32, (_vp, _vp, _u32, _u32, _vp)),
     ("vrenb200_radix_top_digit_histogram", _i32, (_vp, _vp, _u32, _vp)),
     ("vrenb200_radix_partition_scatter", _i32, (_vp, _vp, _vp, _u32, _vp, _vp, _sz)),
     ("vrenb200_exclusive_scan_u32_base", _i32, (_vp, _vp, _vp, _u32, _u32, _vp, _sz)),
@@ -290,3 +298,29 @@ def assign_lights(width: int, height: int, camera: Camera, keys, disp, bvh, ligh
                                      light_count, _ptr(index_buffer), _ptr(view_pos), _ptr(indices), max_assigned,
                                      _ptr(counts), _ptr(offsets), _ptr(status), _ptr(scratch), sb), "vrenb200_assign_lights")
     return counts, offsets, indices, status
+
+
+def depth_pyramid(depth):
+    """vren::depth_buffer_reductor::copy_and_reduce. depth: float32 [H,W] device tensor -> flat float32 pyramid (levels back to back)"""
+    import torch
+
+    lib = load()
+    H, W = depth.shape
+    out = torch.zeros(lib.vrenb200_depth_pyramid_bytes(W, H) // 4, dtype=torch.float32, device=depth.device)
+    check(lib.vrenb200_depth_pyramid_build(_stream(), _ptr(depth), W, H, _ptr(out)), "vrenb200_depth_pyramid_build")
+    return out
+
+
+def light_list_hash(cluster_ref, disp, counts, offsets, indices):
+    """per-pixel {light count, XOR of light indices} through the cluster reference image -> int32 [H,W,2]"""
+    import torch
+
+    lib = load()
+    H, W = cluster_ref.shape
+    max_keys, max_assigned = counts.numel(), indices.numel()
+    out = torch.zeros(H, W, 2, dtype=torch.int32, device=cluster_ref.device)
+    sb = lib.vrenb200_light_list_hash_scratch_bytes(max_keys)
+    scratch = _scratch(sb)
+    check(lib.vrenb200_light_list_hash(_stream(), W, H, _ptr(cluster_ref), _ptr(disp), max_keys, _ptr(counts), _ptr(offsets), _ptr(indices),
+                                       max_assigned, _ptr(out), _ptr(scratch), sb), "vrenb200_light_list_hash")
+    return out
