@@ -220,6 +220,18 @@ def secondary_metrics(lib, vlib, dev):
     out["light_assign_4k_65536_lights"] = {"ms_per_view": ms, "target_ms": 0.5, "clusters": int(cs.dispatch_params[0]),
                                            "assigned_lights": int(st[0]), "node_tests": int(st[2]), "leaf_tests": int(st[3]),
                                            "stages": "construct_point_light_bvh + find_unique_cluster_list + assign_lights"}
+    # SURVEY 8f rows on the same inputs: n1 per-pixel light-list walk, n2 depth-buffer pyramid
+    hb = lib.vrenb200_light_list_hash_scratch_bytes(cs.max_keys)
+    hscr = torch.empty(hb, dtype=torch.uint8, device=dev)
+    px = torch.empty(h, w, 2, dtype=torch.int32, device=dev)
+    ms = timed(lambda: vlib.check(lib.vrenb200_light_list_hash(stream, w, h, cs.cluster_ref.data_ptr(), cs.dispatch_params.data_ptr(), cs.max_keys,
+                                                               cs.counts.data_ptr(), cs.offsets.data_ptr(), cs.indices.data_ptr(), cs.max_assigned,
+                                                               px.data_ptr(), hscr.data_ptr(), hb), "light_list_hash"))
+    out["light_list_consumer_4k"] = {"ms": ms, "GB/s": 12 * w * h / ms / 1e6, "bytes_per_px": 12}
+    pyr = torch.empty(lib.vrenb200_depth_pyramid_bytes(w, h) // 4, dtype=torch.float32, device=dev)
+    ms = timed(lambda: vlib.check(lib.vrenb200_depth_pyramid_build(stream, depth.data_ptr(), w, h, pyr.data_ptr()), "depth_pyramid"))
+    out["depth_pyramid_4k"] = {"ms": ms, "GB/s": (4 + 16 / 3) * w * h / ms / 1e6, "bytes_per_px": 9.33,
+                               "note": "77 MB problem: launch/latency-bound"}
     return out
 
 

@@ -258,7 +258,7 @@ struct onesweep_smem
     uint32_t tile;
 };
 
-enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8, DEPHASE = 16 }; // option bits of the MATCH template argument
+enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8, DEPHASE = 16, LEADER_ATOMIC = 32 }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -419,11 +419,24 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     {
         const uint32_t d = digit_of(key[j], prmt_sel);
         const unsigned mask = match_digit<MATCH>(d);
-        const uint32_t prior = my_hist[d];
-        rank[j] = prior + __popc(mask & lt);
-        __syncwarp();
-        my_hist[d] = prior + __popc(mask);
-        __syncwarp();
+        if (MATCH & LEADER_ATOMIC)
+        {
+            // one shared atomic by the group's leader + a shuffle instead of a load and a store by every lane: fewer
+            // shared-memory wavefronts (the limiter), a few more instructions
+            const unsigned leader = __ffs(mask) - 1;
+            uint32_t prior = 0;
+            if (lane == leader) prior = atomicAdd(&my_hist[d], (uint32_t) __popc(mask));
+            prior = __shfl_sync(kFullMask, prior, leader);
+            rank[j] = prior + __popc(mask & lt);
+        }
+        else
+        {
+            const uint32_t prior = my_hist[d];
+            rank[j] = prior + __popc(mask & lt);
+            __syncwarp();
+            my_hist[d] = prior + __popc(mask);
+            __syncwarp();
+        }
     }
     __syncthreads();
 
@@ -925,11 +938,11 @@ int launch_persistent(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const
 #define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
 const sort_variant g_variants[] = {
     VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),   // 0: default (best of the sweeps in profiles/)
+    VARIANT(256, 32, TILE_BY_BLOCKIDX | LEADER_ATOMIC, 2),
     PVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // persistent CTAs + key prefetch, static tile striding
-    PVARIANT(256, 32, TILE_BY_BLOCKIDX | DEPHASE, 2),
     PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent, tickets
     VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),
-    VARIANT(256, 28, TILE_BY_BLOCKIDX, 2),
+    VARIANT(256, 24, TILE_BY_BLOCKIDX | LEADER_ATOMIC, 3),
     VARIANT(256, 32, MATCH_BALLOT, 2),       // ticket instead of block index
     VARIANT(256, 32, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 2),
 };
