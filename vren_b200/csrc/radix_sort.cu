@@ -133,6 +133,54 @@ radix_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, sort_contr
     }
 }
 
+// Conflict-free variant of the histogram: every lane owns a column of every counter (hist[pass][digit][lane], 128 KB of
+// the SM's shared memory, one 1024-thread CTA per SM), so the 32 shared atomics of a warp instruction always hit 32
+// different banks: one wavefront per instruction instead of ~3.4 for 32 random digits.  The shared-atomic pipe was the
+// limiter of the plain version (0.40 ms at 2^28 keys).
+constexpr int kHist2Threads = 1024;
+constexpr size_t kHist2Smem = (size_t) kPasses * kRadix * 32 * sizeof(uint32_t);
+
+__global__ void __launch_bounds__(kHist2Threads, 1)
+radix_histogram_columns_kernel(const uint32_t* __restrict__ keys, uint32_t n, sort_control* ctl)
+{
+    extern __shared__ __align__(128) uint32_t s_cols[];   // [kPasses][kRadix][32]
+    for (uint32_t i = threadIdx.x; i < kPasses * kRadix * 32; i += kHist2Threads) s_cols[i] = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t* col = s_cols + lane;
+    auto count = [&](uint32_t k) {
+        atomicAdd(&col[(0 * kRadix + (k & 0xFF)) * 32], 1u);
+        atomicAdd(&col[(1 * kRadix + ((k >> 8) & 0xFF)) * 32], 1u);
+        atomicAdd(&col[(2 * kRadix + ((k >> 16) & 0xFF)) * 32], 1u);
+        atomicAdd(&col[(3 * kRadix + (k >> 24)) * 32], 1u);
+    };
+    const uint32_t n4 = n / 4;
+    const uint4* keys4 = reinterpret_cast<const uint4*>(keys);
+    const uint32_t stride = gridDim.x * kHist2Threads;
+    uint32_t i = blockIdx.x * kHist2Threads + threadIdx.x;
+    for (; (uint64_t) i + stride < n4; i += 2 * stride)
+    {
+        const uint4 a = ldg_stream_u4(keys4 + i);
+        const uint4 b = ldg_stream_u4(keys4 + i + stride);
+        count(a.x); count(a.y); count(a.z); count(a.w);
+        count(b.x); count(b.y); count(b.z); count(b.w);
+    }
+    for (; i < n4; i += stride)
+    {
+        const uint4 a = ldg_stream_u4(keys4 + i);
+        count(a.x); count(a.y); count(a.z); count(a.w);
+    }
+    if (blockIdx.x == 0)
+        for (uint32_t t = n4 * 4 + threadIdx.x; t < n; t += kHist2Threads) count(keys[t]);
+    __syncthreads();
+    // thread t sums the 32 columns of counter t, starting at a rotated column so that a warp reads 32 different banks
+    const uint32_t t = threadIdx.x; // == pass * 256 + digit
+    uint32_t sum = 0;
+#pragma unroll 8
+    for (uint32_t k = 0; k < 32; k++) sum += s_cols[t * 32 + ((k + t) & 31)];
+    if (sum != 0) atomicAdd(&(&ctl->hist[0][0])[t], sum);
+}
+
 // bucket sort: uvec2 pairs, key = x & 0xFFFF -> two digit histograms + the 65536 bucket counters
 // (bucket_sort_count.comp:27-34) in the same read
 __global__ void __launch_bounds__(kHistThreads)
@@ -975,6 +1023,23 @@ struct vrenb200_sort_profile
 namespace vrenb200 {
 namespace {
 
+int launch_histogram(cudaStream_t s, const uint32_t* keys, uint32_t n, sort_control* ctl)
+{
+    if (n >= (1u << 20))
+    {
+        static bool configured = false;
+        if (!configured)
+        {
+            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(radix_histogram_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kHist2Smem)));
+            configured = true;
+        }
+        radix_histogram_columns_kernel<<<kNumSMs, kHist2Threads, kHist2Smem, s>>>(keys, n, ctl);
+    }
+    else
+        radix_histogram_kernel<<<kNumSMs * 4, kHistThreads, 0, s>>>(keys, n, ctl);
+    return check_launch();
+}
+
 // control + look-back live in `ctl_mem`; alt buffers given explicitly
 int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, uint32_t* alt_keys, uint32_t* alt_vals,
                     void* ctl_mem, vrenb200_sort_profile* prof = nullptr, int first_pass = 0, int num_passes = kPasses)
@@ -994,8 +1059,7 @@ int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, 
     const size_t clear = sizeof(sort_control) + (size_t) kPasses * tiles * kRadix * sizeof(uint32_t);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(ctl_mem, 0, clear, s)));
     if (prof) cudaEventRecord(prof->ev[0], s);
-    radix_histogram_kernel<<<kNumSMs * 4, kHistThreads, 0, s>>>(keys, n, ctl);
-    VRENB200_TRY(check_launch());
+    VRENB200_TRY(launch_histogram(s, keys, n, ctl));
     if (prof) cudaEventRecord(prof->ev[1], s);
     radix_scan_histograms_kernel<<<kPasses, kRadix, 0, s>>>(ctl);
     VRENB200_TRY(check_launch());
@@ -1104,8 +1168,7 @@ extern "C" int vrenb200_radix_digit_histograms(vrenb200_stream_t stream, const u
     if (n == 0) return VRENB200_OK;
     // the kernel addresses its output through sort_control::hist
     sort_control* fake = reinterpret_cast<sort_control*>(reinterpret_cast<char*>(hist_out) - offsetof(sort_control, hist));
-    radix_histogram_kernel<<<kNumSMs * 4, kHistThreads, 0, s>>>(keys, n, fake);
-    return check_launch();
+    return launch_histogram(s, keys, n, fake);
 }
 
 extern "C" size_t vrenb200_radix_sort_range_scratch_bytes(uint32_t n) { return control_bytes(n); }
