@@ -404,7 +404,8 @@ def run_ours(args):
                        ("partition kernel storing into peer receive buffers over NVLink" if (world > 1 and exchange is not None)
                         else "NCCL all-to-all-v") + " + local onesweep"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "onesweep_pass_kernel", "peak_source": peak_src,
+                         "traffic": ncu_traffic("onesweep_pass_kernel", args.log2n), "kernel": "onesweep_pass_kernel",
+                         "peak_source": peak_src,
                          "kernel_ms": pass_avg_ms, "histogram_ms": sum(hist_ms) / len(hist_ms),
                          "whole_sort_frac": BYTES_PER_PAIR_SORT * n / (ms_max * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
@@ -418,6 +419,15 @@ def run_ours(args):
     lib.vrenb200_sort_profile_destroy(prof)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel, log2n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture."""
+    try:
+        rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))[kernel]
+        return rec["dram_bytes_per_launch"] if rec["log2n"] == log2n else None
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def main():

@@ -306,7 +306,7 @@ struct onesweep_smem
     uint32_t tile;
 };
 
-enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8, DEPHASE = 16, LEADER_ATOMIC = 32 }; // option bits of the MATCH template argument
+enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8, DEPHASE = 16, LEADER_ATOMIC = 32, SPLIT_KV = 64 }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -533,23 +533,42 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     // in-tile destination of every item; fetch the staged values with the same striping
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) rank[j] += my_hist[digit_of(key[j], prmt_sel)];
-    uint32_t val[HAS_VALUES ? ITEMS : 1];
-    if (HAS_VALUES)
+    // SPLIT_KV (SOA only): keys and values are regrouped one after the other in their own halves of the staging buffer,
+    // so the key registers are dead before the values are fetched (a third fewer live registers: more resident warps)
+    constexpr bool SPLIT = (MATCH & SPLIT_KV) != 0 && LAYOUT == LAYOUT_SOA;
+    if (SPLIT)
     {
-        if (LAYOUT == LAYOUT_SOA && full) mbar_wait(&sm.bar_vals, 0);
+        // every warp passed the barriers above after loading its keys: the key half can be overwritten in place
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) val[j] = sm.kv[(warp_off + j * 32) * KSTRIDE + VOFF];
+        for (int j = 0; j < ITEMS; j++) sm.kv[rank[j]] = key[j];
+        if (full) mbar_wait(&sm.bar_vals, 0);
+        uint32_t val[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) val[j] = sm.kv[TILE + warp_off + j * 32];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) sm.kv[TILE + rank[j]] = val[j];
     }
-    __syncthreads(); // every warp has consumed the staged inputs: the buffers become the regroup area
+    else
+    {
+        uint32_t val[HAS_VALUES ? ITEMS : 1];
+        if (HAS_VALUES)
+        {
+            if (LAYOUT == LAYOUT_SOA && full) mbar_wait(&sm.bar_vals, 0);
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) val[j] = sm.kv[(warp_off + j * 32) * KSTRIDE + VOFF];
+        }
+        __syncthreads(); // every warp has consumed the staged inputs: the buffers become the regroup area
 
 #pragma unroll
-    for (int j = 0; j < ITEMS; j++)
-    {
-        // pairs are regrouped interleaved (one 64-bit shared store / load per pair) whatever the global layout
-        if (HAS_VALUES)
-            reinterpret_cast<uint2*>(sm.kv)[rank[j]] = make_uint2(key[j], val[j]);
-        else
-            sm.kv[rank[j]] = key[j];
+        for (int j = 0; j < ITEMS; j++)
+        {
+            // pairs are regrouped interleaved (one 64-bit shared store / load per pair) whatever the global layout
+            if (HAS_VALUES)
+                reinterpret_cast<uint2*>(sm.kv)[rank[j]] = make_uint2(key[j], val[j]);
+            else
+                sm.kv[rank[j]] = key[j];
+        }
     }
 
     // decoupled look-back, one thread per digit
@@ -615,7 +634,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
             const uint32_t p = j * THREADS + tid;
             if (HAS_VALUES)
             {
-                const uint2 e = reinterpret_cast<const uint2*>(sm.kv)[p];
+                const uint2 e = SPLIT ? make_uint2(sm.kv[p], sm.kv[TILE + p]) : reinterpret_cast<const uint2*>(sm.kv)[p];
                 const uint32_t g = sm.digit_base[digit_of(e.x, prmt_sel)] + p;
                 if (LAYOUT == LAYOUT_AOS)
                     reinterpret_cast<uint2*>(keys_out)[g] = e;
@@ -642,20 +661,21 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     {
         for (uint32_t p = tid; p < valid; p += THREADS)
         {
-            const uint32_t k = sm.kv[p * (HAS_VALUES ? 2 : 1)];
+            const uint32_t k = sm.kv[SPLIT ? p : p * (HAS_VALUES ? 2 : 1)];
+            const uint32_t v = HAS_VALUES ? sm.kv[SPLIT ? TILE + p : p * 2 + 1] : 0u;
             const uint32_t g = sm.digit_base[digit_of(k, prmt_sel)] + p;
             if (LAYOUT == LAYOUT_AOS)
-                reinterpret_cast<uint2*>(keys_out)[g] = make_uint2(k, sm.kv[p * 2 + 1]);
+                reinterpret_cast<uint2*>(keys_out)[g] = make_uint2(k, v);
             else if (MATCH & P2P_DEST)
             {
                 const uint32_t d = digit_of(k, prmt_sel);
                 reinterpret_cast<uint32_t*>(sm.dst_ptr[0][d])[g] = k;
-                reinterpret_cast<uint32_t*>(sm.dst_ptr[(MATCH & P2P_DEST) ? 1 : 0][d])[g] = sm.kv[p * 2 + 1];
+                reinterpret_cast<uint32_t*>(sm.dst_ptr[(MATCH & P2P_DEST) ? 1 : 0][d])[g] = v;
             }
             else
             {
                 keys_out[g] = k;
-                if (HAS_VALUES) vals_out[g] = sm.kv[p * 2 + 1];
+                if (HAS_VALUES) vals_out[g] = v;
             }
         }
     }
@@ -986,13 +1006,13 @@ int launch_persistent(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const
 #define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
 const sort_variant g_variants[] = {
     VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),   // 0: default (best of the sweeps in profiles/)
-    VARIANT(256, 32, TILE_BY_BLOCKIDX | LEADER_ATOMIC, 2),
+    VARIANT(256, 32, TILE_BY_BLOCKIDX | SPLIT_KV, 2),
     PVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // persistent CTAs + key prefetch, static tile striding
     PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent, tickets
-    VARIANT(256, 24, TILE_BY_BLOCKIDX, 3),
-    VARIANT(256, 24, TILE_BY_BLOCKIDX | LEADER_ATOMIC, 3),
+    VARIANT(512, 16, TILE_BY_BLOCKIDX | SPLIT_KV, 2),   // 32 warps/SM instead of 16: slower (profiles/r1k_*)
     VARIANT(256, 32, MATCH_BALLOT, 2),       // ticket instead of block index
     VARIANT(256, 32, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 2),
+    VARIANT(256, 32, TILE_BY_BLOCKIDX | LEADER_ATOMIC, 2),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile

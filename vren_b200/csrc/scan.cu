@@ -17,10 +17,8 @@ namespace vrenb200 {
 
 namespace {
 
-constexpr int kScanThreads = 256;
-constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kScanVecs = 8;                                        // uint4 per thread
-constexpr uint32_t kScanTile = kScanThreads * kScanVecs * 4;        // 8192 elements
+constexpr uint32_t kScanMinTile = 256 * kScanVecs * 4;              // smallest tile of any variant: sizes the status array
 constexpr uint32_t kWarpChunk = 32 * kScanVecs * 4;                 // 1024 contiguous elements per warp
 
 constexpr uint64_t kFlagAggregate = 1ull << 32;
@@ -34,9 +32,14 @@ struct scan_state
     uint64_t status[1];   // [tiles]
 };
 
-__global__ void __launch_bounds__(kScanThreads)
+// THREADS sets the tile (THREADS x 32 elements).  The look-back walk is as long as the number of older tiles still in
+// flight, so for a fixed number of bytes in flight larger tiles mean proportionally fewer L2 round trips per tile.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
 exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_state* state, uint32_t base)
 {
+    constexpr int kScanWarps = THREADS / 32;
+    constexpr uint32_t kScanTile = THREADS * kScanVecs * 4;
     __shared__ uint32_t s_warp_total[kScanWarps];
     __shared__ uint32_t s_tile_prefix;
 
@@ -196,9 +199,22 @@ inline int ilog2(uint32_t v) { int r = 0; while (v >>= 1) r++; return r; }
 
 using namespace vrenb200;
 
+namespace {
+int g_scan_variant = 0;
+constexpr int kScanVariantThreads[] = { 256, 512, 1024 };
+}
+
+// tuning hook (bench.py / tests): CTA size of the scan kernel, 0: 256, 1: 512, 2: 1024 threads
+extern "C" int vrenb200_scan_set_variant(int v)
+{
+    if (v < 0 || v >= (int) (sizeof(kScanVariantThreads) / sizeof(int))) return VRENB200_EINVAL_ARG;
+    g_scan_variant = v;
+    return VRENB200_OK;
+}
+
 extern "C" size_t vrenb200_scan_scratch_bytes(uint32_t n)
 {
-    const size_t tiles = ((size_t) n + kScanTile - 1) / kScanTile;
+    const size_t tiles = ((size_t) n + kScanMinTile - 1) / kScanMinTile;
     return align_up(offsetof(scan_state, status) + (tiles > 0 ? tiles : 1) * sizeof(uint64_t), 256);
 }
 
@@ -219,8 +235,13 @@ extern "C" int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const 
     if ((reinterpret_cast<uintptr_t>(scratch) & 7) != 0) return VRENB200_EALIGN;
     cudaStream_t s = as_stream(stream);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, need, s)));
-    const uint32_t tiles = (uint32_t) (((size_t) n + kScanTile - 1) / kScanTile);
-    exclusive_scan_u32_kernel<<<tiles, kScanThreads, 0, s>>>(in, out, n, static_cast<scan_state*>(scratch), base);
+    const uint32_t threads = kScanVariantThreads[g_scan_variant];
+    const uint32_t tile = threads * kScanVecs * 4;
+    const uint32_t tiles = (uint32_t) (((size_t) n + tile - 1) / tile);
+    scan_state* st = static_cast<scan_state*>(scratch);
+    if (threads == 256) exclusive_scan_u32_kernel<256><<<tiles, 256, 0, s>>>(in, out, n, st, base);
+    else if (threads == 512) exclusive_scan_u32_kernel<512><<<tiles, 512, 0, s>>>(in, out, n, st, base);
+    else exclusive_scan_u32_kernel<1024><<<tiles, 1024, 0, s>>>(in, out, n, st, base);
     return check_launch();
 }
 
