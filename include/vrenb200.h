@@ -127,7 +127,8 @@ int vrenb200_radix_partition_scatter(vrenb200_stream_t stream, const uint32_t* k
 
 /* tuning / measurement hooks (not part of the reference surface) */
 int vrenb200_radix_sort_set_variant(int variant);
-int vrenb200_scan_set_variant(int variant);   /* CTA size of the scan kernel: 0: 256, 1: 512, 2: 1024 threads */
+int vrenb200_scan_set_variant(int variant);
+int vrenb200_scan_set_runahead(int finalize_lag_tiles, int scan_lag_tiles);   /* run-ahead scan kernel with explicit distances */   /* CTA size of the scan kernel: 0: 256, 1: 512, 2: 1024 threads */
 int vrenb200_radix_sort_num_variants(void);
 const char* vrenb200_radix_sort_variant_name(int variant);
 typedef struct vrenb200_sort_profile vrenb200_sort_profile;   /* CUDA events around every kernel of one sort */

@@ -114,7 +114,7 @@ def test_scan_all_ones_pow2(vren, log2n):
     assert np.array_equal(got, oracle.exclusive_scan(x))
 
 
-@pytest.mark.parametrize("n", [3, 1000, 4096, 4097, 123457, (1 << 21) + 5])
+@pytest.mark.parametrize("n", [3, 1000, 4096, 4097, 123457, (1 << 21) + 5, (1 << 22) + 5, (1 << 24) + 3 * 16384 + 1])
 def test_scan_random_wraparound_any_length(vren, n):
     x = rand_u32(13, n)
     want = oracle.exclusive_scan(x)
@@ -125,6 +125,30 @@ def test_scan_random_wraparound_any_length(vren, n):
     dst = torch.zeros_like(src)
     vren.exclusive_scan(src, out=dst)                                                # out of place
     assert np.array_equal(host_u32(dst), want) and np.array_equal(host_u32(src), x)
+
+
+@pytest.mark.parametrize("n,offset", [(16384 * 700 + 77, 0), (16384 * 700 + 77, 3), ((1 << 22) + 16384, 1)])
+def test_scan_kernels_agree(vren, n, offset):
+    """every scan kernel behind the tuning hook (register tile, staged tile, run-ahead with and without L2 hints) gives
+    the oracle's result, also on views that are not 16-byte aligned (no bulk copy / vector path)"""
+    import torch
+
+    lib = vren.load()
+    x = rand_u32(29, n + 8)
+    want = oracle.exclusive_scan(x[offset:offset + n])
+    try:
+        for variant in (0, 1, 2, 3, 4, 8, 11, 12, 14, 15):
+            assert lib.vrenb200_scan_set_variant(variant) == 0
+            src = dev_u32(x)
+            dst = torch.zeros_like(src)
+            vren.exclusive_scan(src[offset:offset + n], out=dst[offset:offset + n])
+            got = host_u32(dst)
+            assert np.array_equal(got[offset:offset + n], want), variant
+            assert not got[:offset].any() and not got[offset + n:].any(), variant
+            vren.exclusive_scan(src[offset:offset + n])                      # in place
+            assert np.array_equal(host_u32(src)[offset:offset + n], want), variant
+    finally:
+        lib.vrenb200_scan_set_variant(0)
 
 
 def test_scan_full_size_c2(vren):

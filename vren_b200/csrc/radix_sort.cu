@@ -681,6 +681,229 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     }
 }
 
+// ---- 3a. count-first onesweep pass ------------------------------------------------------------------------------
+// Same contract as onesweep_pass_kernel, different order of work inside the tile:
+//   1. the warp-private digit counters are filled FIRST (one non-returning shared atomic per key),
+//   2. the tile's digit counts are published and the look-back loads of the first predecessors are issued,
+//   3. the counters are turned into the final in-tile offset of every (warp, digit) run,
+//   4. the ballot ranking then yields final in-tile positions, so every pair is stored to the regroup buffer as soon
+//      as it is ranked (no rank array in registers, no second counter lookup per item),
+//   5. the look-back finishes (its first round trip has been in flight during the whole ranking) and the tile is
+//      written out.
+// Successors see this tile's aggregate a ranking phase earlier, and this tile's own look-back latency hides behind
+// its ranking.
+template <int THREADS, int ITEMS, int LAYOUT, int MATCH, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
+                            const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
+                            uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t num_tiles)
+{
+    using smem_t = onesweep_smem<THREADS, ITEMS, LAYOUT, false>;
+    constexpr int WARPS = smem_t::WARPS;
+    constexpr int TILE = smem_t::TILE;
+    constexpr bool HAS_VALUES = LAYOUT != LAYOUT_KEYS;
+    constexpr int KSTRIDE = LAYOUT == LAYOUT_AOS ? 2 : 1;
+    constexpr int VOFF = LAYOUT == LAYOUT_AOS ? 1 : TILE;
+    constexpr uint32_t ELEM_BYTES = LAYOUT == LAYOUT_AOS ? 8 : 4;
+    static_assert(THREADS >= kRadix, "one thread per digit needed");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    smem_t& sm = *reinterpret_cast<smem_t*>(smem_raw);
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t prmt_sel = 0x4440u | (uint32_t) pass;
+    const uint32_t tile = blockIdx.x;
+    if (tid == 0)
+    {
+        mbar_init(&sm.bar_keys, 1);
+        mbar_init(&sm.bar_vals, 1);
+        mbar_fence_init();
+    }
+#pragma unroll
+    for (int i = lane; i < kRadix; i += 32) sm.warp_hist[warp][i] = 0;
+    __syncthreads();
+
+    const uint64_t tile_base = (uint64_t) tile * TILE;
+    const uint32_t valid = (n - tile_base) < (uint64_t) TILE ? (uint32_t) (n - tile_base) : (uint32_t) TILE;
+    const bool full = valid == (uint32_t) TILE;
+    if (full)
+    {
+        if (tid == 0)
+        {
+            mbar_arrive_expect_tx(&sm.bar_keys, TILE * ELEM_BYTES);
+            bulk_copy_g2s(sm.kv, keys_in + tile_base * KSTRIDE, TILE * ELEM_BYTES, &sm.bar_keys);
+            if (LAYOUT == LAYOUT_SOA)
+            {
+                mbar_arrive_expect_tx(&sm.bar_vals, TILE * 4);
+                bulk_copy_g2s(sm.kv + TILE, vals_in + tile_base, TILE * 4, &sm.bar_vals);
+            }
+        }
+        mbar_wait(&sm.bar_keys, 0);
+    }
+    else
+    {
+        for (uint32_t i = tid; i < (uint32_t) TILE; i += THREADS)
+        {
+            const bool in = i < valid;
+            sm.kv[i * KSTRIDE] = in ? keys_in[(tile_base + i) * KSTRIDE] : 0xFFFFFFFFu;
+            if (LAYOUT == LAYOUT_SOA) sm.kv[TILE + i] = in ? vals_in[tile_base + i] : 0u;
+            if (LAYOUT == LAYOUT_AOS) sm.kv[i * 2 + 1] = in ? keys_in[(tile_base + i) * 2 + 1] : 0u;
+        }
+        __syncthreads();
+    }
+
+    const uint32_t warp_off = warp * (ITEMS * 32) + lane;
+    uint32_t* my_hist = sm.warp_hist[warp];
+    uint32_t key[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) key[j] = sm.kv[(warp_off + j * 32) * KSTRIDE];
+    // 1. count
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) atomicAdd(&my_hist[digit_of(key[j], prmt_sel)], 1u);
+    __syncthreads();
+
+    // 2. publish the aggregate, start the look-back
+    constexpr int K = 4;
+    uint32_t* lb = lookback + ((size_t) pass * num_tiles + tile) * kRadix;
+    uint32_t cnt = 0, inc = 0, real_cnt = 0, lb_pre[K];
+    if (tid < kRadix)
+    {
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) cnt += sm.warp_hist[w][tid];
+        real_cnt = cnt - ((tid == kRadix - 1) ? (uint32_t) TILE - valid : 0u);
+        st_relaxed_u32(&lb[tid], (tile == 0 ? kLbFlagInclusive : kLbFlagAggregate) | real_cnt);
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            lb_pre[k] = ((int64_t) tile - 1 - k >= 0) ? ld_relaxed_u32(lb - (k + 1) * kRadix + tid) : kLbFlagInclusive;
+        inc = cnt;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(kFullMask, inc, s);
+            if (lane >= (unsigned) s) inc += t;
+        }
+        if (lane == 31) sm.scan_warp[warp] = inc;
+    }
+    __syncthreads();
+    // 3. counters -> in-tile offset of every (warp, digit) run
+    uint32_t tile_off = 0;
+    if (tid < kRadix)
+    {
+        uint32_t wp = 0;
+#pragma unroll
+        for (int w = 0; w < kRadix / 32; w++)
+            if (w < (int) warp) wp += sm.scan_warp[w];
+        tile_off = wp + inc - cnt;
+        uint32_t run = tile_off;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++)
+        {
+            const uint32_t c = sm.warp_hist[w][tid];
+            sm.warp_hist[w][tid] = run;
+            run += c;
+        }
+    }
+    uint32_t val[HAS_VALUES ? ITEMS : 1];
+    if (HAS_VALUES)
+    {
+        if (LAYOUT == LAYOUT_SOA && full) mbar_wait(&sm.bar_vals, 0);
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) val[j] = sm.kv[(warp_off + j * 32) * KSTRIDE + VOFF];
+    }
+    __syncthreads(); // offsets visible; every warp has consumed the staged inputs: the buffers become the regroup area
+
+    // 4. rank and regroup
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++)
+    {
+        const uint32_t d = digit_of(key[j], prmt_sel);
+        const unsigned mask = match_digit<MATCH>(d);
+        const uint32_t prior = my_hist[d];
+        const uint32_t r = prior + __popc(mask & lt);
+        __syncwarp();
+        my_hist[d] = prior + __popc(mask);
+        __syncwarp();
+        if (HAS_VALUES)
+            reinterpret_cast<uint2*>(sm.kv)[r] = make_uint2(key[j], val[j]);
+        else
+            sm.kv[r] = key[j];
+    }
+
+    // 5. finish the look-back
+    if (tid < kRadix)
+    {
+        uint32_t exclusive = 0;
+        if (tile > 0)
+        {
+            const uint32_t* p = lb - kRadix + tid;
+            int64_t t = (int64_t) tile - 1;
+            bool done = false, first = true;
+            while (!done)
+            {
+                uint32_t s[K];
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    s[k] = first ? lb_pre[k] : ((t - k >= 0) ? ld_relaxed_u32(p - k * kRadix) : kLbFlagInclusive);
+                first = false;
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                {
+                    if (done) break;
+                    while ((s[k] >> 30) == 0) s[k] = ld_relaxed_u32(p - k * kRadix);
+                    exclusive += s[k] & kLbValueMask;
+                    done = (s[k] >> 30) == 2;
+                }
+                t -= K;
+                p -= K * kRadix;
+            }
+            st_relaxed_u32(&lb[tid], kLbFlagInclusive | (exclusive + real_cnt));
+        }
+        sm.digit_base[tid] = ctl->hist[pass][tid] + exclusive - tile_off;
+    }
+    __syncthreads();
+
+    if (full)
+    {
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++)
+        {
+            const uint32_t p = j * THREADS + tid;
+            if (HAS_VALUES)
+            {
+                const uint2 e = reinterpret_cast<const uint2*>(sm.kv)[p];
+                const uint32_t g = sm.digit_base[digit_of(e.x, prmt_sel)] + p;
+                if (LAYOUT == LAYOUT_AOS)
+                    reinterpret_cast<uint2*>(keys_out)[g] = e;
+                else
+                {
+                    keys_out[g] = e.x;
+                    vals_out[g] = e.y;
+                }
+            }
+            else
+            {
+                const uint32_t k = sm.kv[p];
+                keys_out[sm.digit_base[digit_of(k, prmt_sel)] + p] = k;
+            }
+        }
+    }
+    else
+    {
+        for (uint32_t p = tid; p < valid; p += THREADS)
+        {
+            const uint32_t k = sm.kv[p * (HAS_VALUES ? 2 : 1)];
+            const uint32_t g = sm.digit_base[digit_of(k, prmt_sel)] + p;
+            if (LAYOUT == LAYOUT_AOS)
+                reinterpret_cast<uint2*>(keys_out)[g] = make_uint2(k, sm.kv[p * 2 + 1]);
+            else
+            {
+                keys_out[g] = k;
+                if (HAS_VALUES) vals_out[g] = sm.kv[p * 2 + 1];
+            }
+        }
+    }
+}
+
 // ---- 3b. persistent onesweep pass: CTAs loop over tiles, the next tile's keys are prefetched ---------------------
 // Same algorithm as onesweep_pass_kernel (LAYOUT_KEYS / LAYOUT_SOA only), restructured so that no tile waits for its
 // input: a CTA takes the ticket of its NEXT tile and starts the TMA bulk copy of that tile's keys into a second
@@ -1002,8 +1225,32 @@ int launch_persistent(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const
     return check_launch();
 }
 
+template <int THREADS, int ITEMS, int LAYOUT, int MATCH, int MIN_BLOCKS>
+int launch_count_first_one(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout,
+                           uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t tiles)
+{
+    auto kern = onesweep_count_first_kernel<THREADS, ITEMS, LAYOUT, MATCH, MIN_BLOCKS>;
+    constexpr size_t smem = sizeof(onesweep_smem<THREADS, ITEMS, LAYOUT, false>);
+    VRENB200_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)));
+    kern<<<tiles, THREADS, smem, s>>>(kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    return check_launch();
+}
+
+template <int THREADS, int ITEMS, int MATCH, int MIN_BLOCKS>
+int launch_count_first(cudaStream_t s, const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout,
+                       uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t tiles, int layout)
+{
+    switch (layout)
+    {
+    case LAYOUT_KEYS: return launch_count_first_one<THREADS, ITEMS, LAYOUT_KEYS, MATCH, MIN_BLOCKS>(s, kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    case LAYOUT_SOA:  return launch_count_first_one<THREADS, ITEMS, LAYOUT_SOA, MATCH, MIN_BLOCKS>(s, kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    default:          return launch_count_first_one<THREADS, ITEMS, LAYOUT_AOS, MATCH, MIN_BLOCKS>(s, kin, kout, vin, vout, n, pass, ctl, lookback, tiles);
+    }
+}
+
 #define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B> }
 #define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
+#define CVARIANT(T, I, M, B) { #T "x" #I "/count-first/occ" #B, (T) * (I), launch_count_first<T, I, M, B> }
 const sort_variant g_variants[] = {
     VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),   // 0: default (best of the sweeps in profiles/)
     VARIANT(256, 32, TILE_BY_BLOCKIDX | SPLIT_KV, 2),
@@ -1013,6 +1260,8 @@ const sort_variant g_variants[] = {
     VARIANT(256, 32, MATCH_BALLOT, 2),       // ticket instead of block index
     VARIANT(256, 32, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 2),
     VARIANT(256, 32, TILE_BY_BLOCKIDX | LEADER_ATOMIC, 2),
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // 8
+    CVARIANT(256, 24, TILE_BY_BLOCKIDX, 3),  // 9
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile

@@ -163,6 +163,435 @@ exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_st
     }
 }
 
+// ---- staged variant: the tile lives in shared memory, not in registers -------------------------------------------
+// ncu on the register-tile kernel above (profiles/r1l_ncu_scan.md): 63 % of the warp samples sit at the barrier behind
+// warp 0's look-back, and with 63 registers x 32 elements per thread only 4 CTAs (128 KB of loads) fit an SM, so
+// little is in flight while a CTA waits.  Here ONE bulk copy (TMA) brings a 64 KB tile (16384 elements) into shared
+// memory the moment the CTA starts; the tile is read twice from there (warp totals, then the scan itself), the
+// registers stay small, three CTAs = 192 KB of loads are in flight per SM, and the status chain is half as long.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kStagedThreads = 256;
+constexpr int kStagedWarps = kStagedThreads / 32;
+constexpr int kStagedVecs = 16;                                            // uint4 per thread
+constexpr uint32_t kStagedTile = kStagedThreads * kStagedVecs * 4;         // 16384 elements = 64 KB
+constexpr uint32_t kStagedWarpChunk = 32 * kStagedVecs * 4;                // 2048 contiguous elements per warp
+
+// MODE 0: the real thing.  Timing experiments only (wrong results, reachable through the tuning hook, never the default):
+// 1: no look-back, 2: only wait for the 32 nearest predecessors to publish, 3: full walk that never waits on a flag
+template <int MODE>
+__global__ void __launch_bounds__(kStagedThreads, 3)
+exclusive_scan_staged_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_state* state, uint32_t base)
+{
+    extern __shared__ __align__(128) uint32_t s_tile[];
+    __shared__ uint32_t s_warp_total[kStagedWarps];
+    __shared__ uint32_t s_tile_prefix;
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const uint32_t tile = blockIdx.x;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t tile_base = (uint64_t) tile * kStagedTile;
+    const uint32_t valid = (n - tile_base) < (uint64_t) kStagedTile ? (uint32_t) (n - tile_base) : kStagedTile;
+    const bool bulk = valid == kStagedTile && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+
+    if (bulk)
+    {
+        if (tid == 0)
+        {
+            mbar_init(&s_bar, 1);
+            mbar_arrive_expect_tx(&s_bar, kStagedTile * 4);
+            bulk_copy_g2s(s_tile, in + tile_base, kStagedTile * 4, &s_bar);
+        }
+        __syncthreads();      // the barrier word is initialised before anyone polls it
+        mbar_wait(&s_bar, 0);
+    }
+    else
+    {
+        for (uint32_t i = tid; i < kStagedTile; i += kStagedThreads) s_tile[i] = i < valid ? in[tile_base + i] : 0u;
+        __syncthreads();
+    }
+
+    // first read: warp totals
+    const uint4* mine = reinterpret_cast<const uint4*>(s_tile + warp * kStagedWarpChunk) + lane;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int v = 0; v < kStagedVecs; v++)
+    {
+        const uint4 x = mine[v * 32];
+        sum += x.x + x.y + x.z + x.w;
+    }
+    sum = __reduce_add_sync(kFullMask, sum);
+    if (lane == 0) s_warp_total[warp] = sum;
+    __syncthreads();
+    uint32_t warp_prefix = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kStagedWarps; w++)
+    {
+        const uint32_t t = s_warp_total[w];
+        if (w < (int) warp) warp_prefix += t;
+        tile_total += t;
+    }
+
+    if (warp == 0)
+    {
+        uint64_t* status = state->status;
+        if (lane == 0)
+            st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | tile_total);
+        uint32_t exclusive = 0;
+        if (MODE != 1 && tile > 0)
+        {
+            // 128 predecessors per L2 round trip, consumed nearest first
+            constexpr int K = 4;
+            int64_t window = (int64_t) tile - 1;
+            bool done = false;
+            while (!done)
+            {
+                uint64_t s0, s1, s2, s3;
+                {
+                    const int64_t t = window - lane;
+                    s0 = t >= 0 ? ld_relaxed_u64(&status[t]) : kFlagInclusive;
+                    s1 = t - 32 >= 0 ? ld_relaxed_u64(&status[t - 32]) : kFlagInclusive;
+                    s2 = t - 64 >= 0 ? ld_relaxed_u64(&status[t - 64]) : kFlagInclusive;
+                    s3 = t - 96 >= 0 ? ld_relaxed_u64(&status[t - 96]) : kFlagInclusive;
+                }
+                auto consume = [&](uint64_t sv, int k) {
+                    if (done) return;
+                    const int64_t t = window - 32 * k - lane;
+                    while (MODE != 3 && (sv >> 32) == 0)
+                    {
+                        __nanosleep(40);
+                        sv = ld_relaxed_u64(&status[t]);
+                    }
+                    if (MODE == 3 && window - 32 * k - 31 <= 0) sv = kFlagInclusive;   // the walk must end somewhere
+                    if (MODE == 2) sv = kFlagInclusive;
+                    const unsigned incl = __ballot_sync(kFullMask, (sv >> 32) == 2);
+                    uint32_t val = (uint32_t) sv;
+                    if (incl != 0 && lane > (unsigned) (__ffs(incl) - 1)) val = 0;
+                    exclusive += __reduce_add_sync(kFullMask, val);
+                    done = incl != 0;
+                };
+                consume(s0, 0);
+                consume(s1, 1);
+                consume(s2, 2);
+                consume(s3, 3);
+                window -= 32 * K;
+            }
+            if (lane == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (exclusive + tile_total));
+        }
+        if (lane == 0) s_tile_prefix = exclusive;
+    }
+    __syncthreads();
+
+    // second read: the scan itself, carried across the warp's 16 rounds
+    uint32_t carry = s_tile_prefix + warp_prefix + base;
+    const uint64_t warp_base = tile_base + warp * kStagedWarpChunk;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+#pragma unroll 4
+    for (int v = 0; v < kStagedVecs; v++)
+    {
+        const uint4 x = mine[v * 32];
+        const uint32_t total = x.x + x.y + x.z + x.w;
+        uint32_t inc = total;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(kFullMask, inc, s);
+            if (lane >= (unsigned) s) inc += t;
+        }
+        uint4 y;
+        y.x = carry + inc - total;
+        y.y = y.x + x.x;
+        y.z = y.y + x.y;
+        y.w = y.z + x.z;
+        carry += __shfl_sync(kFullMask, inc, 31);
+        const uint64_t idx = warp_base + v * 128 + lane * 4;
+        if (vec_ok && idx + 4 <= n)
+            *reinterpret_cast<uint4*>(out + idx) = y;
+        else
+        {
+            if (idx + 0 < n) out[idx + 0] = y.x;
+            if (idx + 1 < n) out[idx + 1] = y.y;
+            if (idx + 2 < n) out[idx + 2] = y.z;
+            if (idx + 3 < n) out[idx + 3] = y.w;
+        }
+    }
+}
+
+// ---- run-ahead variant --------------------------------------------------------------------------------------------
+// Timing experiments on the staged kernel (profiles/r1l_scan_lookback_experiments.md): with the look-back removed the
+// kernel runs at the HBM roofline (0.32 ms at 2^28), and merely WAITING for the 32 nearest predecessors to publish
+// their aggregates costs 0.18 ms: a tile holds 64 KB of shared memory while the slowest of its predecessors' loads
+// arrives, so the loads in flight drop.  The chain cannot be made faster; it is moved off the critical path instead.
+//
+// CTA c (512 threads, CTAs dispatched in index order) does three unrelated things:
+//   * warps 8-15 REDUCE tile c: read it from HBM (which also pulls it into the 126 MB L2) and publish its aggregate;
+//   * warp 8 then FINALIZES tile c - A: a look-back walk over aggregates published >= A CTAs ago (no waiting on
+//     stragglers), publishing the tile's inclusive prefix;
+//   * warps 0-7 SCAN tile c - A - B: one bulk copy re-reads the tile (an L2 hit: (A+B) x 64 KB is a fraction of the
+//     L2), the inclusive prefix of the previous tile was finalized >= B CTAs ago, two passes over shared memory, store.
+// Every dependency points to a CTA launched earlier.  HBM traffic stays 8 B/element; the second read is L2 traffic.
+constexpr int kRunaheadThreads = 512;
+
+// L2 residency hints: the tile must survive in L2 between the reduce role's read and the scan role's re-read
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ldg_u4_hint(const uint4* p, uint64_t policy)
+{
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void stg_u4_hint(uint4* p, uint4 v, uint64_t policy)
+{
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+__device__ __forceinline__ void named_barrier(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <bool HINTS>
+__global__ void __launch_bounds__(kRunaheadThreads, 3)
+exclusive_scan_runahead_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_state* state, uint32_t base,
+                               uint32_t tiles, uint32_t lag_finalize, uint32_t lag_scan)
+{
+    extern __shared__ __align__(128) uint32_t s_tile[];
+    __shared__ uint32_t s_warp_total[kStagedWarps];
+    __shared__ uint32_t s_reduce_total[kStagedWarps];
+    __shared__ uint32_t s_tile_prefix;
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const unsigned lane = threadIdx.x & 31;
+    uint64_t* status = state->status;
+    const int64_t c = blockIdx.x;
+    const bool in_aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+
+    if (threadIdx.x >= kStagedThreads)
+    {
+        // ---- reduce role: tile c ----
+        const unsigned tid = threadIdx.x - kStagedThreads, warp = tid >> 5;
+        if (c < (int64_t) tiles)
+        {
+            const uint64_t tile_base = (uint64_t) c * kStagedTile;
+            const uint32_t valid = (n - tile_base) < (uint64_t) kStagedTile ? (uint32_t) (n - tile_base) : kStagedTile;
+            uint32_t sum = 0;
+            if (valid == kStagedTile && in_aligned)
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(in + tile_base) + tid;
+                const uint64_t keep = HINTS ? l2_policy_evict_last() : 0;
+#pragma unroll 4
+                for (int v = 0; v < kStagedVecs; v++)
+                {
+                    const uint4 x = HINTS ? ldg_u4_hint(src + v * kStagedThreads, keep) : ldg_stream_u4(src + v * kStagedThreads);
+                    sum += x.x + x.y + x.z + x.w;
+                }
+            }
+            else
+                for (uint32_t i = tid; i < valid; i += kStagedThreads) sum += in[tile_base + i];
+            sum = __reduce_add_sync(kFullMask, sum);
+            if (lane == 0) s_reduce_total[warp] = sum;
+        }
+        named_barrier(1, kStagedThreads);
+        if (warp != 0) return;
+        if (c < (int64_t) tiles && lane == 0)
+        {
+            uint32_t tile_total = 0;
+#pragma unroll
+            for (int w = 0; w < kStagedWarps; w++) tile_total += s_reduce_total[w];
+            st_relaxed_u64(&status[c], kFlagAggregate | tile_total);
+        }
+        // ---- finalize role: tile f = c - lag_finalize ----
+        const int64_t f = c - (int64_t) lag_finalize;
+        if (f < 0 || f >= (int64_t) tiles) return;
+        uint32_t exclusive = 0;
+        constexpr int K = 4;
+        int64_t window = f - 1;
+        bool done = f == 0;
+        while (!done)
+        {
+            uint64_t s0, s1, s2, s3;
+            {
+                const int64_t t = window - lane;
+                s0 = t >= 0 ? ld_relaxed_u64(&status[t]) : kFlagInclusive;
+                s1 = t - 32 >= 0 ? ld_relaxed_u64(&status[t - 32]) : kFlagInclusive;
+                s2 = t - 64 >= 0 ? ld_relaxed_u64(&status[t - 64]) : kFlagInclusive;
+                s3 = t - 96 >= 0 ? ld_relaxed_u64(&status[t - 96]) : kFlagInclusive;
+            }
+            auto consume = [&](uint64_t sv, int k) {
+                if (done) return;
+                const int64_t t = window - 32 * k - lane;
+                while ((sv >> 32) == 0)
+                {
+                    __nanosleep(40);
+                    sv = ld_relaxed_u64(&status[t]);
+                }
+                const unsigned incl = __ballot_sync(kFullMask, (sv >> 32) == 2);
+                uint32_t val = (uint32_t) sv;
+                if (incl != 0 && lane > (unsigned) (__ffs(incl) - 1)) val = 0;
+                exclusive += __reduce_add_sync(kFullMask, val);
+                done = incl != 0;
+            };
+            consume(s0, 0);
+            consume(s1, 1);
+            consume(s2, 2);
+            consume(s3, 3);
+            window -= 32 * K;
+        }
+        if (lane == 0)
+        {
+            // the tile's own aggregate is in its status word (published >= lag_finalize CTAs ago)
+            uint64_t own = ld_relaxed_u64(&status[f]);
+            while ((own >> 32) == 0)
+            {
+                __nanosleep(40);
+                own = ld_relaxed_u64(&status[f]);
+            }
+            st_relaxed_u64(&status[f], kFlagInclusive | (uint32_t) (exclusive + (uint32_t) own));
+        }
+        return;
+    }
+
+    // ---- scan role: tile q = c - lag_finalize - lag_scan ----
+    const unsigned tid = threadIdx.x, warp = tid >> 5;
+    const int64_t q = c - (int64_t) lag_finalize - (int64_t) lag_scan;
+    if (q < 0 || q >= (int64_t) tiles) return;
+    const uint64_t tile_base = (uint64_t) q * kStagedTile;
+    const uint32_t valid = (n - tile_base) < (uint64_t) kStagedTile ? (uint32_t) (n - tile_base) : kStagedTile;
+    const bool bulk = valid == kStagedTile && in_aligned;
+    if (bulk && tid == 0)
+    {
+        mbar_init(&s_bar, 1);
+        mbar_arrive_expect_tx(&s_bar, kStagedTile * 4);
+        if (HINTS)
+            bulk_copy_g2s_hint(s_tile, in + tile_base, kStagedTile * 4, &s_bar, l2_policy_evict_first());
+        else
+            bulk_copy_g2s(s_tile, in + tile_base, kStagedTile * 4, &s_bar);
+    }
+    // the previous tile's inclusive prefix: one poller, its latency hides behind the copy
+    if (tid == 32)
+    {
+        uint32_t exclusive = 0;
+        if (q > 0)
+        {
+            uint64_t sv = ld_relaxed_u64(&status[q - 1]);
+            while ((sv >> 32) != 2)
+            {
+                __nanosleep(40);
+                sv = ld_relaxed_u64(&status[q - 1]);
+            }
+            exclusive = (uint32_t) sv;
+        }
+        s_tile_prefix = exclusive;
+    }
+    if (bulk)
+    {
+        named_barrier(2, kStagedThreads);   // the barrier word is initialised before anyone polls it
+        mbar_wait(&s_bar, 0);
+    }
+    else
+    {
+        for (uint32_t i = tid; i < kStagedTile; i += kStagedThreads) s_tile[i] = i < valid ? in[tile_base + i] : 0u;
+        named_barrier(2, kStagedThreads);
+    }
+
+    const uint4* mine = reinterpret_cast<const uint4*>(s_tile + warp * kStagedWarpChunk) + lane;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int v = 0; v < kStagedVecs; v++)
+    {
+        const uint4 x = mine[v * 32];
+        sum += x.x + x.y + x.z + x.w;
+    }
+    sum = __reduce_add_sync(kFullMask, sum);
+    if (lane == 0) s_warp_total[warp] = sum;
+    named_barrier(2, kStagedThreads);
+    uint32_t warp_prefix = 0;
+#pragma unroll
+    for (int w = 0; w < kStagedWarps; w++)
+        if (w < (int) warp) warp_prefix += s_warp_total[w];
+
+    uint32_t carry = s_tile_prefix + warp_prefix + base;
+    const uint64_t warp_base = tile_base + warp * kStagedWarpChunk;
+    const uint64_t drop = HINTS ? l2_policy_evict_first() : 0;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+#pragma unroll 4
+    for (int v = 0; v < kStagedVecs; v++)
+    {
+        const uint4 x = mine[v * 32];
+        const uint32_t total = x.x + x.y + x.z + x.w;
+        uint32_t inc = total;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(kFullMask, inc, s);
+            if (lane >= (unsigned) s) inc += t;
+        }
+        uint4 y;
+        y.x = carry + inc - total;
+        y.y = y.x + x.x;
+        y.z = y.y + x.y;
+        y.w = y.z + x.z;
+        carry += __shfl_sync(kFullMask, inc, 31);
+        const uint64_t idx = warp_base + v * 128 + lane * 4;
+        if (vec_ok && idx + 4 <= n)
+        {
+            if (HINTS) stg_u4_hint(reinterpret_cast<uint4*>(out + idx), y, drop);
+            else *reinterpret_cast<uint4*>(out + idx) = y;
+        }
+        else
+        {
+            if (idx + 0 < n) out[idx + 0] = y.x;
+            if (idx + 1 < n) out[idx + 1] = y.y;
+            if (idx + 2 < n) out[idx + 2] = y.z;
+            if (idx + 3 < n) out[idx + 3] = y.w;
+        }
+    }
+}
+
 // blelloch_scan_downsweep.comp:59-125 generalised to a strided logical array: logical element i lives at
 // buf[(i+1)*stride-1]; `levels` = min(10, log2(count)) down-sweep levels in shared memory.
 __global__ void __launch_bounds__(1024)
@@ -201,14 +630,30 @@ using namespace vrenb200;
 
 namespace {
 int g_scan_variant = 0;
-constexpr int kScanVariantThreads[] = { 256, 512, 1024 };
+constexpr int kScanAuto = 9999;
+constexpr int kScanVariantThreads[] = { kScanAuto, 256, 512, 1024, 0 /* staged 64 KB tile */, 1, 2, 3 /* staged, timing experiments (MODE) */,
+                                        -64, -128, -256, -512 /* run-ahead, both lags = -value tiles */,
+                                        -10064, -10128, -10256, -10512 /* same with L2 residency hints */ };
 }
 
-// tuning hook (bench.py / tests): CTA size of the scan kernel, 0: 256, 1: 512, 2: 1024 threads
+// tuning hook: explicit run-ahead distances (tiles of 16384 elements); selects the run-ahead kernel
+int g_lag_finalize = 0, g_lag_scan = 0;
+extern "C" int vrenb200_scan_set_runahead(int finalize_lag, int scan_lag)
+{
+    if (finalize_lag < 1 || scan_lag < 1 || finalize_lag > 4096 || scan_lag > 4096) return VRENB200_EINVAL_ARG;
+    g_lag_finalize = finalize_lag;
+    g_lag_scan = scan_lag;
+    g_scan_variant = 15;   // hinted run-ahead; the lags above override the table value
+    return VRENB200_OK;
+}
+
+// tuning hook (bench.py / tools): 0: default (auto), 1-3: register tile with 256 / 512 / 1024 threads, 4: staged 64 KB tile,
+// 5-7: timing experiments (wrong results), 8-11: run-ahead with distances 64..512, 12-15: same with L2 residency hints
 extern "C" int vrenb200_scan_set_variant(int v)
 {
     if (v < 0 || v >= (int) (sizeof(kScanVariantThreads) / sizeof(int))) return VRENB200_EINVAL_ARG;
     g_scan_variant = v;
+    g_lag_finalize = g_lag_scan = 0;
     return VRENB200_OK;
 }
 
@@ -235,8 +680,57 @@ extern "C" int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const 
     if ((reinterpret_cast<uintptr_t>(scratch) & 7) != 0) return VRENB200_EALIGN;
     cudaStream_t s = as_stream(stream);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, need, s)));
-    const uint32_t threads = kScanVariantThreads[g_scan_variant];
-    const uint32_t tile = threads * kScanVecs * 4;
+    int threads = kScanVariantThreads[g_scan_variant];
+    // default: the run-ahead kernel (256 + 256 tiles of distance, L2 residency hints) for arrays that fill the machine,
+    // the register-tile kernel (smaller tiles, no idle prologue CTAs) below that
+    if (threads == kScanAuto) threads = n >= (1u << 22) ? -10256 : 256;
+    if (threads < 0)
+    {
+        static bool configured = false;
+        if (!configured)
+        {
+            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_runahead_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int) (kStagedTile * 4))));
+            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_runahead_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int) (kStagedTile * 4))));
+            configured = true;
+        }
+        const uint32_t staged_tiles = (uint32_t) (((size_t) n + kStagedTile - 1) / kStagedTile);
+        const bool hints = -threads > 10000;
+        const uint32_t lag = (uint32_t) (-threads % 10000);    // finalize lag = scan lag = lag
+        const uint32_t la = g_lag_finalize > 0 ? (uint32_t) g_lag_finalize : lag, lb = g_lag_scan > 0 ? (uint32_t) g_lag_scan : lag;
+        scan_state* st = static_cast<scan_state*>(scratch);
+        if (hints)
+            exclusive_scan_runahead_kernel<true><<<staged_tiles + la + lb, kRunaheadThreads, kStagedTile * 4, s>>>(in, out, n, st, base, staged_tiles, la, lb);
+        else
+            exclusive_scan_runahead_kernel<false><<<staged_tiles + la + lb, kRunaheadThreads, kStagedTile * 4, s>>>(in, out, n, st, base, staged_tiles, la, lb);
+        return check_launch();
+    }
+    if (threads <= 3)
+    {
+        static bool configured = false;
+        if (!configured)
+        {
+            const int bytes = (int) (kStagedTile * 4);
+            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+            configured = true;
+        }
+        const uint32_t staged_tiles = (uint32_t) (((size_t) n + kStagedTile - 1) / kStagedTile);
+        scan_state* st = static_cast<scan_state*>(scratch);
+        const size_t smem = kStagedTile * 4;
+        switch (threads)
+        {
+        case 0: exclusive_scan_staged_kernel<0><<<staged_tiles, kStagedThreads, smem, s>>>(in, out, n, st, base); break;
+        case 1: exclusive_scan_staged_kernel<1><<<staged_tiles, kStagedThreads, smem, s>>>(in, out, n, st, base); break;
+        case 2: exclusive_scan_staged_kernel<2><<<staged_tiles, kStagedThreads, smem, s>>>(in, out, n, st, base); break;
+        default: exclusive_scan_staged_kernel<3><<<staged_tiles, kStagedThreads, smem, s>>>(in, out, n, st, base); break;
+        }
+        return check_launch();
+    }
+    const uint32_t tile = (uint32_t) threads * kScanVecs * 4;
     const uint32_t tiles = (uint32_t) (((size_t) n + tile - 1) / tile);
     scan_state* st = static_cast<scan_state*>(scratch);
     if (threads == 256) exclusive_scan_u32_kernel<256><<<tiles, 256, 0, s>>>(in, out, n, st, base);

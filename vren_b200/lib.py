@@ -111,6 +111,7 @@ _LATE_SIGS = [
     ("vrenb200_exclusive_scan_u32_base", _i32, (_vp, _vp, _vp, _u32, _u32, _vp, _sz)),
     ("vrenb200_radix_digit_histograms", _i32, (_vp, _vp, _u32, _vp)),
     ("vrenb200_scan_set_variant", _i32, (_i32,)),
+    ("vrenb200_scan_set_runahead", _i32, (_i32, _i32)),
     ("vrenb200_radix_sort_range_scratch_bytes", _sz, (_u32,)),
     ("vrenb200_radix_sort_pairs_range", _i32, (_vp, _vp, _vp, _vp, _vp, _u32, _i32, _i32, _vp, _sz, C.POINTER(C.c_int))),
     ("vrenb200_bucket_sort_output_bytes", _sz, (_u32,)),
