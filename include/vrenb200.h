@@ -230,6 +230,15 @@ size_t vrenb200_depth_pyramid_bytes(uint32_t width, uint32_t height);
 /* depth_buffer_reductor::copy_and_reduce (depth_buffer_pyramid.cpp:177-305): level 0 = copy, level l+1 = 2x2 max */
 int vrenb200_depth_pyramid_build(vrenb200_stream_t stream, const float* depth, uint32_t width, uint32_t height, float* pyramid);
 
+/* ---- n3: light animation producer ----------------------------------------------------------------------------------
+ * vren_demo::point_light_bouncer::bounce (vren_demo/vren_demo/point_light_bouncer.hpp:22-33,
+ * vren_demo/resources/shaders/bounce_point_lights.comp:33-73).  positions / directions: vec4 per light (16-byte aligned),
+ * updated in place: the light advances speed*dt along its direction inside [aabb_min, aabb_max] and reflects off the
+ * faces it reaches (<= 32 reflections per call); position.w := 1, direction.w := 0.  aabb_* are HOST pointers
+ * (push constants in the reference). */
+int vrenb200_bounce_point_lights(vrenb200_stream_t stream, float* positions, float* directions, uint32_t count,
+                                 const float aabb_min[3], const float aabb_max[3], float speed, float dt);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,7 @@ class Camera(C.Structure):
 _LATE: list = [
     ("oracle_light_list_hash", None, (C.c_uint32, C.c_uint32, u32p, u32p, u32p, u32p, u32p)),
     ("oracle_depth_pyramid", C.c_uint32, (f32p, C.c_uint32, C.c_uint32, f32p)),
+    ("oracle_bounce_point_lights", None, (f32p, f32p, C.c_uint32, f32p, f32p, C.c_float, C.c_float)),
     ("oracle_construct_point_light_bvh", None, (f32p, f32p, C.c_uint32, f32p, f32p, voidp, u32p)),
     ("oracle_find_unique_clusters", C.c_uint32, (f32p, voidp, C.c_uint32, C.c_uint32, C.POINTER(Camera), u32p, u32p)),
     ("oracle_assign_lights", C.c_uint64,
@@ -253,6 +254,15 @@ def depth_pyramid(depth: np.ndarray):
     out = np.zeros(total, np.float32)
     levels = lib.oracle_depth_pyramid(depth.reshape(-1), W, H, out)
     return out, int(levels)
+
+
+def bounce_point_lights(positions: np.ndarray, directions: np.ndarray, aabb_min, aabb_max, speed: float, dt: float):
+    """bounce_point_lights.comp:33-73 -> (positions, directions), float32 [L,4] copies"""
+    pos = np.ascontiguousarray(positions, dtype=np.float32).copy()
+    dirs = np.ascontiguousarray(directions, dtype=np.float32).copy()
+    lo, hi = np.asarray(aabb_min, np.float32).copy(), np.asarray(aabb_max, np.float32).copy()
+    load().oracle_bounce_point_lights(pos.reshape(-1), dirs.reshape(-1), pos.shape[0], lo, hi, np.float32(speed), np.float32(dt))
+    return pos, dirs
 
 
 def light_list_hash(cluster_ref: np.ndarray, counts: np.ndarray, offsets: np.ndarray, indices: np.ndarray) -> np.ndarray:

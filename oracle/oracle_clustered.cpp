@@ -435,3 +435,46 @@ void oracle_light_list_hash(uint32_t W, uint32_t H, const uint32_t* cluster_ref,
 }
 
 } // extern "C"
+
+// ---- n3: light animation producer ---------------------------------------------------------------------------------------
+// bounce_point_lights.comp:33-73, one light after the other.  GLSL min/max restated with fmin/fmax semantics (a NaN
+// operand loses; the shader leaves that case undefined), divisions and the p += step * d update as separate IEEE fp32
+// operations (this file is built with -ffp-contract=off).
+extern "C" void oracle_bounce_point_lights(float* positions, float* directions, uint32_t count, const float* lo, const float* hi,
+                                           float speed, float dt)
+{
+    const float INF = 1e35f, EPS = 1e-5f;
+    for (uint32_t i = 0; i < count; i++)
+    {
+        float p[3], d[3];
+        for (int a = 0; a < 3; a++)
+        {
+            p[a] = std::fmin(std::fmax(positions[i * 4 + a], lo[a]), hi[a]);
+            d[a] = directions[i * 4 + a];
+        }
+        float rem_t = speed * dt;
+        for (uint32_t j = 0; j < 32 && rem_t > 0; j++)
+        {
+            float t1[3], t2[3];
+            for (int a = 0; a < 3; a++)
+            {
+                t1[a] = (lo[a] - p[a]) / d[a]; t1[a] = t1[a] <= 0 ? INF : t1[a];
+                t2[a] = (hi[a] - p[a]) / d[a]; t2[a] = t2[a] <= 0 ? INF : t2[a];
+            }
+            const float min_t = std::fmin(t1[0], std::fmin(t2[0], std::fmin(t1[1], std::fmin(t2[1], std::fmin(t1[2], t2[2])))));
+            const float step = std::fmin(min_t - EPS, rem_t);
+            for (int a = 0; a < 3; a++)
+            {
+                const float sd = step * d[a];
+                p[a] = p[a] + sd;
+            }
+            if (min_t < rem_t)
+                for (int a = 0; a < 3; a++)
+                    if (t1[a] == min_t || t2[a] == min_t) d[a] = -d[a];
+            rem_t = rem_t - step;
+        }
+        for (int a = 0; a < 3; a++) { positions[i * 4 + a] = p[a]; directions[i * 4 + a] = d[a]; }
+        positions[i * 4 + 3] = 1.0f;
+        directions[i * 4 + 3] = 0.0f;
+    }
+}

@@ -3,6 +3,7 @@
 // tree reduce, linear AABB scan), run the primitive through immediate_graphics_queue_submit, compare element-wise.
 // Prints one line per test and exits non-zero on the first mismatch.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,6 +14,7 @@
 #include "vren/context.hpp"
 #include "vren/pipeline/clustered_shading.hpp"
 #include "vren/pipeline/depth_buffer_pyramid.hpp"
+#include "vren_demo/point_light_bouncer.hpp"
 
 static int g_failures = 0;
 #define EXPECT(cond, ...)                                            \
@@ -330,6 +332,25 @@ static void test_depth_pyramid(vren::context& ctx)
     std::printf("ok depth_buffer_pyramid\n");
 }
 
+static void test_point_light_bouncer(vren::context& ctx)
+{
+    // a light flying along +x in the unit box: 0.25 to the face, reflected, 0.25 back (minus the shader's EPS)
+    std::vector<float> pos = { 0.75f, 0.5f, 0.5f, 7.0f, 0.1f, 0.2f, 0.3f, 7.0f }, dir = { 1, 0, 0, 7.0f, 0, 0, 0, 7.0f };
+    auto pb = vren::vk_utils::alloc_device_only_buffer(ctx, pos.size() * 4);
+    auto dbuf = vren::vk_utils::alloc_device_only_buffer(ctx, dir.size() * 4);
+    upload(pb, pos);
+    upload(dbuf, dir);
+    vren_demo::point_light_bouncer bouncer(ctx);
+    vren::vk_utils::immediate_graphics_queue_submit(ctx, [&](VkCommandBuffer cmd, vren::resource_container& rc) {
+        bouncer.bounce(0, cmd, rc, pb, dbuf, 2, vren_demo::vec3{0, 0, 0}, vren_demo::vec3{1, 1, 1}, 1.0f, 0.5f);
+    });
+    auto p = download<float>(pb, 8), d = download<float>(dbuf, 8);
+    EXPECT(d[0] == -1.0f && d[3] == 0.0f && p[3] == 1.0f, "reflection: d.x %f d.w %f p.w %f", d[0], d[3], p[3]);
+    EXPECT(std::fabs(p[0] - 0.75f) < 1e-3f && p[1] == 0.5f && p[2] == 0.5f, "position after the bounce: %f %f %f", p[0], p[1], p[2]);
+    EXPECT(p[4] == 0.1f && p[5] == 0.2f && p[6] == 0.3f, "a light without direction stays where it is");
+    std::printf("ok point_light_bouncer\n");
+}
+
 int main()
 {
     try
@@ -342,6 +363,7 @@ int main()
         test_build_bvh(ctx);
         test_cluster_and_shade(ctx);
         test_depth_pyramid(ctx);
+        test_point_light_bouncer(ctx);
     }
     catch (std::exception const& e)
     {

@@ -223,6 +223,8 @@ def test_radix_all_variants_agree(vren):
     wk, wv = oracle.sort_pairs(k, v)
     try:
         for var in range(lib.vrenb200_radix_sort_num_variants()):
+            if b"FAKE" in lib.vrenb200_radix_sort_variant_name(var):
+                continue    # timing experiments that are wrong on purpose
             assert lib.vrenb200_radix_sort_set_variant(var) == 0
             gk, gv = vren.radix_sort_pairs(dev_u32(k), dev_u32(v))
             assert np.array_equal(host_u32(gk), wk), lib.vrenb200_radix_sort_variant_name(var)

@@ -306,7 +306,8 @@ struct onesweep_smem
     uint32_t tile;
 };
 
-enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8, DEPHASE = 16, LEADER_ATOMIC = 32, SPLIT_KV = 64 }; // option bits of the MATCH template argument
+enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8, DEPHASE = 16, LEADER_ATOMIC = 32, SPLIT_KV = 64,
+       FAKE_LOOKBACK = 128 /* timing experiment: no chain, approximate destinations (WRONG results) */ }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -575,7 +576,9 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     if (tid < kRadix)
     {
         uint32_t exclusive = 0;
-        if (tile > 0)
+        if (MATCH & FAKE_LOOKBACK)
+            exclusive = tile * (TILE / kRadix);
+        else if (tile > 0)
         {
             // K predecessors are fetched per round trip (independent loads), then consumed in order: with hundreds of
             // tiles in flight a one-at-a-time walk spends most of the tile's life in dependent L2 round trips
@@ -635,7 +638,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
             if (HAS_VALUES)
             {
                 const uint2 e = SPLIT ? make_uint2(sm.kv[p], sm.kv[TILE + p]) : reinterpret_cast<const uint2*>(sm.kv)[p];
-                const uint32_t g = sm.digit_base[digit_of(e.x, prmt_sel)] + p;
+                uint32_t g = sm.digit_base[digit_of(e.x, prmt_sel)] + p;
+                if ((MATCH & FAKE_LOOKBACK) && g >= n) g = n - 1;
                 if (LAYOUT == LAYOUT_AOS)
                     reinterpret_cast<uint2*>(keys_out)[g] = e;
                 else if (MATCH & P2P_DEST)
@@ -1262,6 +1266,7 @@ const sort_variant g_variants[] = {
     VARIANT(256, 32, TILE_BY_BLOCKIDX | LEADER_ATOMIC, 2),
     CVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // 8
     CVARIANT(256, 24, TILE_BY_BLOCKIDX, 3),  // 9
+    VARIANT(256, 32, TILE_BY_BLOCKIDX | FAKE_LOOKBACK, 2),  // 10: ceiling without the look-back chain (wrong results)
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile

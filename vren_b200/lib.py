@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parent.parent
 LIB_PATH = Path(__file__).resolve().parent / "libvrenb200.so"
 HEADER = ROOT / "include" / "vrenb200.h"
 
-OK = 0
+OK, EINVAL_LENGTH, EALIGN, ESCRATCH, ECUDA, EINVAL_ARG, ELIMIT = range(7)
 STATUS_NAMES = {0: "OK", 1: "EINVAL_LENGTH", 2: "EALIGN", 3: "ESCRATCH", 4: "ECUDA", 5: "EINVAL_ARG", 6: "ELIMIT"}
 U32, VEC4, F32 = 0, 1, 2
 ADD, MIN, MAX = 0, 1, 2
@@ -110,6 +110,7 @@ _LATE_SIGS = [
     ("vrenb200_radix_partition_scatter", _i32, (_vp, _vp, _vp, _u32, _vp, _vp, _sz)),
     ("vrenb200_exclusive_scan_u32_base", _i32, (_vp, _vp, _vp, _u32, _u32, _vp, _sz)),
     ("vrenb200_radix_digit_histograms", _i32, (_vp, _vp, _u32, _vp)),
+    ("vrenb200_bounce_point_lights", _i32, (_vp, _vp, _vp, _u32, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_float, C.c_float)),
     ("vrenb200_scan_set_variant", _i32, (_i32,)),
     ("vrenb200_scan_set_runahead", _i32, (_i32, _i32)),
     ("vrenb200_radix_sort_range_scratch_bytes", _sz, (_u32,)),
@@ -311,6 +312,16 @@ def depth_pyramid(depth):
     out = torch.zeros(lib.vrenb200_depth_pyramid_bytes(W, H) // 4, dtype=torch.float32, device=depth.device)
     check(lib.vrenb200_depth_pyramid_build(_stream(), _ptr(depth), W, H, _ptr(out)), "vrenb200_depth_pyramid_build")
     return out
+
+
+def bounce_point_lights(positions, directions, aabb_min, aabb_max, speed: float, dt: float, count: int | None = None):
+    """vren_demo::point_light_bouncer::bounce. positions / directions: float32 [L,4] device tensors, updated in place"""
+    lib = load()
+    count = positions.shape[0] if count is None else count
+    lo, hi = (C.c_float * 3)(*[float(v) for v in aabb_min]), (C.c_float * 3)(*[float(v) for v in aabb_max])
+    check(lib.vrenb200_bounce_point_lights(_stream(), _ptr(positions), _ptr(directions), count, C.byref(lo), C.byref(hi),
+                                           C.c_float(speed), C.c_float(dt)), "vrenb200_bounce_point_lights")
+    return positions, directions
 
 
 def light_list_hash(cluster_ref, disp, counts, offsets, indices):
