@@ -525,6 +525,10 @@ exclusive_scan_runahead_kernel(const uint32_t* in, uint32_t* out, uint32_t n, sc
             }
             exclusive = (uint32_t) sv;
         }
+        // in-place scans (out == in): this CTA's stores must not land before the reduce role of CTA q has read the
+        // tile; its aggregate being published proves it has.  (Nothing else orders the two: with fewer than
+        // lag_finalize + lag_scan CTAs of distance they can be resident together.)
+        while ((ld_relaxed_u64(&status[q]) >> 32) == 0) __nanosleep(40);
         s_tile_prefix = exclusive;
     }
     if (bulk)
