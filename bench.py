@@ -393,6 +393,8 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         pass_avg_ms = sum(pass_ms) / len(pass_ms)
+        variant_name = lib.vrenb200_radix_sort_variant_name(args.variant or 0).decode()
+        pass_kernel = "onesweep_count_first_kernel" if "count-first" in variant_name else "onesweep_pass_kernel"
         achieved = BYTES_PER_PAIR_PASS * n / (pass_avg_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -411,7 +413,7 @@ def run_ours(args):
                        ("partition kernel storing into peer receive buffers over NVLink" if (world > 1 and exchange is not None)
                         else "NCCL all-to-all-v") + " + local onesweep"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("onesweep_pass_kernel", args.log2n), "kernel": "onesweep_pass_kernel",
+                         "traffic": ncu_traffic(pass_kernel, args.log2n), "kernel": pass_kernel,
                          "peak_source": peak_src,
                          "kernel_ms": pass_avg_ms, "histogram_ms": sum(hist_ms) / len(hist_ms),
                          "whole_sort_frac": BYTES_PER_PAIR_SORT * n / (ms_max * 1e-3) / 1e9 / peak},

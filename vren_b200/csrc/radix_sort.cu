@@ -307,7 +307,8 @@ struct onesweep_smem
 };
 
 enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8, DEPHASE = 16, LEADER_ATOMIC = 32, SPLIT_KV = 64,
-       FAKE_LOOKBACK = 128 /* timing experiment: no chain, approximate destinations (WRONG results) */ }; // option bits of the MATCH template argument
+       FAKE_LOOKBACK = 128 /* timing experiment: no chain, approximate destinations (WRONG results) */,
+       DIRECT_LOAD = 256 /* count-first kernel: keys / values go from global memory straight to registers (no staging copy) */ }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -729,37 +730,71 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
     const uint64_t tile_base = (uint64_t) tile * TILE;
     const uint32_t valid = (n - tile_base) < (uint64_t) TILE ? (uint32_t) (n - tile_base) : (uint32_t) TILE;
     const bool full = valid == (uint32_t) TILE;
-    if (full)
-    {
-        if (tid == 0)
-        {
-            mbar_arrive_expect_tx(&sm.bar_keys, TILE * ELEM_BYTES);
-            bulk_copy_g2s(sm.kv, keys_in + tile_base * KSTRIDE, TILE * ELEM_BYTES, &sm.bar_keys);
-            if (LAYOUT == LAYOUT_SOA)
-            {
-                mbar_arrive_expect_tx(&sm.bar_vals, TILE * 4);
-                bulk_copy_g2s(sm.kv + TILE, vals_in + tile_base, TILE * 4, &sm.bar_vals);
-            }
-        }
-        mbar_wait(&sm.bar_keys, 0);
-    }
-    else
-    {
-        for (uint32_t i = tid; i < (uint32_t) TILE; i += THREADS)
-        {
-            const bool in = i < valid;
-            sm.kv[i * KSTRIDE] = in ? keys_in[(tile_base + i) * KSTRIDE] : 0xFFFFFFFFu;
-            if (LAYOUT == LAYOUT_SOA) sm.kv[TILE + i] = in ? vals_in[tile_base + i] : 0u;
-            if (LAYOUT == LAYOUT_AOS) sm.kv[i * 2 + 1] = in ? keys_in[(tile_base + i) * 2 + 1] : 0u;
-        }
-        __syncthreads();
-    }
-
+    constexpr bool DIRECT = (MATCH & DIRECT_LOAD) != 0;
     const uint32_t warp_off = warp * (ITEMS * 32) + lane;
     uint32_t* my_hist = sm.warp_hist[warp];
     uint32_t key[ITEMS];
+    uint32_t val[HAS_VALUES ? ITEMS : 1];
+    if (DIRECT)
+    {
+        // warp-striped loads straight into the register tile: one L1 wavefront per 32 keys instead of a staging write
+        // plus a shared load, no barrier word, and the shared buffer is only ever the regroup area
+        if (full)
+        {
 #pragma unroll
-    for (int j = 0; j < ITEMS; j++) key[j] = sm.kv[(warp_off + j * 32) * KSTRIDE];
+            for (int j = 0; j < ITEMS; j++)
+            {
+                if (LAYOUT == LAYOUT_AOS)
+                {
+                    const uint2 e = reinterpret_cast<const uint2*>(keys_in)[tile_base + warp_off + j * 32];
+                    key[j] = e.x;
+                    val[j] = e.y;
+                }
+                else
+                    key[j] = ldg_stream_u32(keys_in + tile_base + warp_off + j * 32);
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++)
+            {
+                const uint32_t i = warp_off + j * 32;
+                key[j] = i < valid ? keys_in[(tile_base + i) * KSTRIDE] : 0xFFFFFFFFu;
+                if (LAYOUT == LAYOUT_AOS) val[j] = i < valid ? keys_in[(tile_base + i) * 2 + 1] : 0u;
+            }
+        }
+    }
+    else
+    {
+        if (full)
+        {
+            if (tid == 0)
+            {
+                mbar_arrive_expect_tx(&sm.bar_keys, TILE * ELEM_BYTES);
+                bulk_copy_g2s(sm.kv, keys_in + tile_base * KSTRIDE, TILE * ELEM_BYTES, &sm.bar_keys);
+                if (LAYOUT == LAYOUT_SOA)
+                {
+                    mbar_arrive_expect_tx(&sm.bar_vals, TILE * 4);
+                    bulk_copy_g2s(sm.kv + TILE, vals_in + tile_base, TILE * 4, &sm.bar_vals);
+                }
+            }
+            mbar_wait(&sm.bar_keys, 0);
+        }
+        else
+        {
+            for (uint32_t i = tid; i < (uint32_t) TILE; i += THREADS)
+            {
+                const bool in = i < valid;
+                sm.kv[i * KSTRIDE] = in ? keys_in[(tile_base + i) * KSTRIDE] : 0xFFFFFFFFu;
+                if (LAYOUT == LAYOUT_SOA) sm.kv[TILE + i] = in ? vals_in[tile_base + i] : 0u;
+                if (LAYOUT == LAYOUT_AOS) sm.kv[i * 2 + 1] = in ? keys_in[(tile_base + i) * 2 + 1] : 0u;
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) key[j] = sm.kv[(warp_off + j * 32) * KSTRIDE];
+    }
     // 1. count
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) atomicAdd(&my_hist[digit_of(key[j], prmt_sel)], 1u);
@@ -806,12 +841,21 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
             run += c;
         }
     }
-    uint32_t val[HAS_VALUES ? ITEMS : 1];
-    if (HAS_VALUES)
+    if (HAS_VALUES && !DIRECT)
     {
         if (LAYOUT == LAYOUT_SOA && full) mbar_wait(&sm.bar_vals, 0);
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) val[j] = sm.kv[(warp_off + j * 32) * KSTRIDE + VOFF];
+    }
+    if (DIRECT && LAYOUT == LAYOUT_SOA)
+    {
+        // issued here, consumed by the regroup stores: the loads fly during the ranking of the first rows
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++)
+        {
+            const uint32_t i = warp_off + j * 32;
+            val[j] = full ? ldg_stream_u32(vals_in + tile_base + i) : (i < valid ? vals_in[tile_base + i] : 0u);
+        }
     }
     __syncthreads(); // offsets visible; every warp has consumed the staged inputs: the buffers become the regroup area
 
@@ -1254,9 +1298,9 @@ int launch_count_first(cudaStream_t s, const uint32_t* kin, uint32_t* kout, cons
 
 #define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B> }
 #define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
-#define CVARIANT(T, I, M, B) { #T "x" #I "/count-first/occ" #B, (T) * (I), launch_count_first<T, I, M, B> }
+#define CVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B, (T) * (I), launch_count_first<T, I, M, B> }
 const sort_variant g_variants[] = {
-    VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),   // 0: default (best of the sweeps in profiles/)
+    CVARIANT(256, 24, TILE_BY_BLOCKIDX, 3),  // 0: default (best of the sweeps in profiles/)
     VARIANT(256, 32, TILE_BY_BLOCKIDX | SPLIT_KV, 2),
     PVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // persistent CTAs + key prefetch, static tile striding
     PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent, tickets
@@ -1265,8 +1309,10 @@ const sort_variant g_variants[] = {
     VARIANT(256, 32, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 2),
     VARIANT(256, 32, TILE_BY_BLOCKIDX | LEADER_ATOMIC, 2),
     CVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // 8
-    CVARIANT(256, 24, TILE_BY_BLOCKIDX, 3),  // 9
+    VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),   // 9: rank-then-count order, the default until r1m
     VARIANT(256, 32, TILE_BY_BLOCKIDX | FAKE_LOOKBACK, 2),  // 10: ceiling without the look-back chain (wrong results)
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | DIRECT_LOAD, 2),   // 11
+    CVARIANT(256, 24, TILE_BY_BLOCKIDX | DIRECT_LOAD, 3),   // 12
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
