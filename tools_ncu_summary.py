@@ -74,9 +74,8 @@ def main():
             blocks.append(cur)
         elif cur is not None:
             cur['rows'].append(r)
-    mapping = {'exclusive_scan': ('scan', 'exclusive_scan_u32_kernel'), 'find_unique': ('clustered', 'find_unique_clusters_kernel'),
-               'assign_lights_walk': ('clustered', 'assign_lights_walk_kernel'), 'assign_lights_place': ('clustered', 'assign_lights_place_kernel'),
-               'onesweep': ('radix_sort', None)}
+    stems = {'exclusive_scan': 'scan', 'find_unique': 'clustered', 'assign_lights': 'clustered', 'onesweep': 'radix_sort',
+             'radix_histogram': 'radix_sort', 'depth_pyramid': 'depth_pyramid', 'build_bvh': 'bvh', 'reduce_': 'reduce'}
     for b in blocks:
         rows = b['rows']
         if not rows:
@@ -94,13 +93,20 @@ def main():
                 agg[c] += I(r[ci[c]])
         print('stall mix: ' + ', '.join(f'{k[6:]} {v / tot_s * 100:.0f}%' for k, v in agg.most_common(7)) + '\n')
         seq = None
-        for key, (stem, sub) in mapping.items():
-            if key in b['name']:
-                if sub is None:
-                    m = re.search(r'onesweep_pass_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>', b['name'])
-                    sub = 'onesweep_pass_kernelILi%sELi%sELi%sELi%sELi%sE' % m.groups() if m else 'onesweep_pass_kernel'
-                seq = line_map(stem, sub)
-                cu = Path(f'/root/repo/vren_b200/csrc/{stem}.cu').read_text().split('\n')
+        # demangled "ns::<unnamed>::kernel<(int)256, (int)24, ...>(" -> mangled fragment "kernelILi256ELi24E..."
+        m = re.search(r'(\w+_kernel)(?:<([^>]*)>)?\(', b['name'])
+        if m:
+            sub = m.group(1)
+            if m.group(2):
+                args = re.findall(r'\((?:int|bool)\)(\d+)', m.group(2))
+                bools = re.findall(r'\(bool\)', m.group(2))
+                if args and not bools:
+                    sub += 'I' + ''.join(f'Li{a}E' for a in args)
+            for key, stem in stems.items():
+                if key in b['name']:
+                    seq = line_map(stem, sub)
+                    cu = Path(f'/root/repo/vren_b200/csrc/{stem}.cu').read_text().split('\n')
+                    break
         if seq and len(seq) == len(data):
             per = collections.defaultdict(lambda: [0, 0, collections.Counter()])
             for ln, r in zip(seq, data):

@@ -308,7 +308,8 @@ struct onesweep_smem
 
 enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8, DEPHASE = 16, LEADER_ATOMIC = 32, SPLIT_KV = 64,
        FAKE_LOOKBACK = 128 /* timing experiment: no chain, approximate destinations (WRONG results) */,
-       DIRECT_LOAD = 256 /* count-first kernel: keys / values go from global memory straight to registers (no staging copy) */ }; // option bits of the MATCH template argument
+       DIRECT_LOAD = 256 /* count-first kernel: keys / values go from global memory straight to registers (no staging copy) */,
+       LB_INTERLEAVED = 512 /* count-first kernel: the look-back advances in non-blocking steps between ranking rows */ }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -804,15 +805,53 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
     constexpr int K = 4;
     uint32_t* lb = lookback + ((size_t) pass * num_tiles + tile) * kRadix;
     uint32_t cnt = 0, inc = 0, real_cnt = 0, lb_pre[K];
+    // look-back state of this thread's digit: window of K predecessors starting at tile lb_t, words in lb_pre[]
+    constexpr bool INTERLEAVED = (MATCH & LB_INTERLEAVED) != 0;
+    const uint32_t* lb_p = lb - kRadix + tid;
+    int32_t lb_t = (int32_t) tile - 1;
+    bool lb_done = tile == 0 || tid >= kRadix;
+    uint32_t exclusive = 0;
+    auto lb_load = [&]() {
+#pragma unroll
+        for (int k = 0; k < K; k++) lb_pre[k] = (lb_t - k >= 0) ? ld_relaxed_u32(lb_p - k * kRadix) : kLbFlagInclusive;
+    };
+    // non-blocking step: consume the window if all of it has been published (and open the next one), else re-poll the
+    // missing words; the loads complete while the ranking goes on
+    auto lb_try = [&]() {
+        if (lb_done) return;
+        bool ready = true;
+#pragma unroll
+        for (int k = 0; k < K; k++) ready = ready && (lb_pre[k] >> 30) != 0;
+        if (ready)
+        {
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (!lb_done)
+                {
+                    exclusive += lb_pre[k] & kLbValueMask;
+                    lb_done = (lb_pre[k] >> 30) == 2;
+                }
+            if (!lb_done)
+            {
+                lb_t -= K;
+                lb_p -= K * kRadix;
+                lb_load();
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if ((lb_pre[k] >> 30) == 0) lb_pre[k] = ld_relaxed_u32(lb_p - k * kRadix);
+        }
+    };
     if (tid < kRadix)
     {
 #pragma unroll
         for (int w = 0; w < WARPS; w++) cnt += sm.warp_hist[w][tid];
         real_cnt = cnt - ((tid == kRadix - 1) ? (uint32_t) TILE - valid : 0u);
         st_relaxed_u32(&lb[tid], (tile == 0 ? kLbFlagInclusive : kLbFlagAggregate) | real_cnt);
-#pragma unroll
-        for (int k = 0; k < K; k++)
-            lb_pre[k] = ((int64_t) tile - 1 - k >= 0) ? ld_relaxed_u32(lb - (k + 1) * kRadix + tid) : kLbFlagInclusive;
+        lb_load();
         inc = cnt;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1)
@@ -875,34 +914,30 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
             reinterpret_cast<uint2*>(sm.kv)[r] = make_uint2(key[j], val[j]);
         else
             sm.kv[r] = key[j];
+        if (INTERLEAVED && (j % 4) == 3 && j + 1 < ITEMS) lb_try();
     }
 
     // 5. finish the look-back
     if (tid < kRadix)
     {
-        uint32_t exclusive = 0;
         if (tile > 0)
         {
-            const uint32_t* p = lb - kRadix + tid;
-            int64_t t = (int64_t) tile - 1;
-            bool done = false, first = true;
-            while (!done)
+            while (!lb_done)
             {
-                uint32_t s[K];
 #pragma unroll
                 for (int k = 0; k < K; k++)
-                    s[k] = first ? lb_pre[k] : ((t - k >= 0) ? ld_relaxed_u32(p - k * kRadix) : kLbFlagInclusive);
-                first = false;
-#pragma unroll
-                for (int k = 0; k < K; k++)
+                    if (!lb_done)
+                    {
+                        while ((lb_pre[k] >> 30) == 0) lb_pre[k] = ld_relaxed_u32(lb_p - k * kRadix);
+                        exclusive += lb_pre[k] & kLbValueMask;
+                        lb_done = (lb_pre[k] >> 30) == 2;
+                    }
+                if (!lb_done)
                 {
-                    if (done) break;
-                    while ((s[k] >> 30) == 0) s[k] = ld_relaxed_u32(p - k * kRadix);
-                    exclusive += s[k] & kLbValueMask;
-                    done = (s[k] >> 30) == 2;
+                    lb_t -= K;
+                    lb_p -= K * kRadix;
+                    lb_load();
                 }
-                t -= K;
-                p -= K * kRadix;
             }
             st_relaxed_u32(&lb[tid], kLbFlagInclusive | (exclusive + real_cnt));
         }
@@ -1300,7 +1335,7 @@ int launch_count_first(cudaStream_t s, const uint32_t* kin, uint32_t* kout, cons
 #define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
 #define CVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B, (T) * (I), launch_count_first<T, I, M, B> }
 const sort_variant g_variants[] = {
-    CVARIANT(256, 24, TILE_BY_BLOCKIDX, 3),  // 0: default (best of the sweeps in profiles/)
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED, 2),  // 0: default (best of the sweeps in profiles/)
     VARIANT(256, 32, TILE_BY_BLOCKIDX | SPLIT_KV, 2),
     PVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // persistent CTAs + key prefetch, static tile striding
     PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent, tickets
@@ -1313,6 +1348,8 @@ const sort_variant g_variants[] = {
     VARIANT(256, 32, TILE_BY_BLOCKIDX | FAKE_LOOKBACK, 2),  // 10: ceiling without the look-back chain (wrong results)
     CVARIANT(256, 32, TILE_BY_BLOCKIDX | DIRECT_LOAD, 2),   // 11
     CVARIANT(256, 24, TILE_BY_BLOCKIDX | DIRECT_LOAD, 3),   // 12
+    CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED, 3),   // 13
+    CVARIANT(256, 24, TILE_BY_BLOCKIDX, 3),   // 14: default of r1m
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
