@@ -194,6 +194,38 @@ def secondary_metrics(lib, vlib, dev):
     out["reduce_u32_add_tree_2p28"] = {"ms": ms, "GB/s": 8 * n / ms / 1e6, "frac_hbm": 8 * n / ms / 1e6 / peak, "bytes_per_elt": 8}
     del x, y, xf, scr
 
+    # a3 as the reference ships it (keys only, 4 + 4x8 = 36 B/key) and a4 (bucket sort of uvec2, 8 + 2x16 = 40 B/pair).
+    # The sorts run in place, so every timed call after the first sees sorted input; onesweep's work does not depend on
+    # the key order (same histogram, same number of tiles and passes), the scatter just becomes more regular.
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    keys = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+    kb = lib.vrenb200_radix_sort_scratch_bytes(n, 0)
+    kscr = torch.empty(kb, dtype=torch.uint8, device=dev)
+    shuffled = keys.clone()
+
+    def sort_keys():
+        keys.copy_(shuffled)
+        vlib.check(lib.vrenb200_radix_sort_keys(stream, keys.data_ptr(), n, kscr.data_ptr(), kb), "radix_sort_keys")
+
+    def restore_only():
+        keys.copy_(shuffled)
+
+    ms = timed(sort_keys) - timed(restore_only)
+    out["radix_sort_keys_2p28"] = {"ms": ms, "Gkeys/s": n / ms / 1e6, "GB/s": 36 * n / ms / 1e6, "frac_hbm": 36 * n / ms / 1e6 / peak,
+                                   "bytes_per_key": 36, "note": "time of (restore + sort) minus time of restore"}
+    del keys, shuffled, kscr
+    nb = 1 << 26
+    pairs = torch.randint(0, 1 << 16, (nb, 2), dtype=torch.int32, device=dev, generator=g)
+    ob = lib.vrenb200_bucket_sort_output_bytes(nb)
+    bout = torch.empty(ob, dtype=torch.uint8, device=dev)
+    bb = lib.vrenb200_bucket_sort_scratch_bytes(nb)
+    bscr = torch.empty(bb, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: vlib.check(lib.vrenb200_bucket_sort(stream, pairs.data_ptr(), nb, bout.data_ptr(), bscr.data_ptr(), bb), "bucket_sort"))
+    out["bucket_sort_2p26_uvec2"] = {"ms": ms, "Gpairs/s": nb / ms / 1e6, "GB/s": 40 * nb / ms / 1e6, "frac_hbm": 40 * nb / ms / 1e6 / peak,
+                                     "bytes_per_pair": 40}
+    del pairs, bout, bscr
+
     # C4: BuildBVH over 2^20 pre-filled leaves (33 B/leaf)
     leaves = 1 << 20
     length = lib.vrenb200_calc_bvh_buffer_length(leaves)

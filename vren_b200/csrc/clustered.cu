@@ -137,16 +137,6 @@ struct cluster_key_params
     int use_tma, has_normals;
 };
 
-struct cluster_scan_state
-{
-    uint32_t ticket;
-    uint32_t _pad[63];
-    uint64_t status[1]; // [tiles] flag<<32 | value
-};
-
-constexpr uint64_t kFlagAggregate = 1ull << 32;
-constexpr uint64_t kFlagInclusive = 2ull << 32;
-
 // clustered_shading.glsl:7-43
 __device__ __forceinline__ uint32_t discretize_normal(float nx, float ny, float nz)
 {
@@ -181,18 +171,20 @@ __global__ void __launch_bounds__(kKeyThreads)
 find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const __grid_constant__ CUtensorMap normal_map,
                             const float* __restrict__ depth, const uint2* __restrict__ normals,
                             const float* __restrict__ thresholds, cluster_key_params prm,
-                            cluster_scan_state* state, uint32_t* keys_out, uint32_t* dispatch_params, uint32_t* cluster_ref)
+                            uint32_t* tile_count, uint32_t* cluster_ref, uint32_t* tile_keys)
 {
     __shared__ alignas(128) float s_depth[32 * 32];
     __shared__ alignas(128) uint2 s_normal[32 * 32];
     __shared__ uint32_t s_bitmap[2048];
     __shared__ uint32_t s_prefix[2048];
     __shared__ uint32_t s_warp[kKeyThreads / 32];
-    __shared__ uint32_t s_found[kKeyThreads / 32];
     __shared__ alignas(8) uint64_t s_bar;
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // tile id = block index: CTAs are dispatched in index order, so a tile only waits on tiles that already started
+    // Tiles are independent here: keys, TILE-LOCAL cluster numbers and the number of unique keys of the tile.  The global
+    // numbering (tile-major order) needs an exclusive prefix over the tiles; with a decoupled look-back inline, 46 % of the
+    // warp samples sat at the barrier behind it (profiles/r1d_ncu_clustered.md), and a deferred in-kernel finalize stage
+    // was slower still, so the prefix is a separate scan of the per-tile counts followed by finalize_clusters_kernel.
     const uint32_t tile = blockIdx.x;
     const uint32_t ti = tile % prm.tiles_x, tj = tile / prm.tiles_x;   // canonical tile-major order
     const bool interior = (ti << 5) + 32 <= prm.width && (tj << 5) + 32 <= prm.height;
@@ -284,49 +276,46 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
     const uint32_t excl = warp_prefix + inc - mine;
 #pragma unroll
     for (int i = 0; i < 8; i++) s_prefix[8 * tid + i] = excl + local[i];
+    __syncthreads();   // s_prefix complete
 
-    // decoupled look-back across tiles (tile-major order) with a CTA-wide window: thread i probes tile-1-i, so the
-    // ~1000 tiles in flight resolve in a handful of L2 round trips instead of dozens
-    uint64_t* status = state->status;
-    if (tid == 0) st_relaxed_u64(&status[tile], (tile == 0 ? kFlagInclusive : kFlagAggregate) | unique);
-    uint32_t base = 0;
-    if (tile > 0)
-    {
-        int64_t window = (int64_t) tile - 1;
-        while (true)
-        {
-            const int64_t t = window - tid;
-            uint64_t sv = kFlagInclusive;
-            if (t >= 0)
-            {
-                do { sv = ld_relaxed_u64(&status[t]); } while ((sv >> 32) == 0);
-            }
-            const unsigned incl = __ballot_sync(kFullMask, (sv >> 32) == 2);
-            uint32_t val = (uint32_t) sv;
-            if (incl != 0 && lane > (unsigned) (__ffs(incl) - 1)) val = 0;
-            val = __reduce_add_sync(kFullMask, val);
-            __syncthreads();                       // s_warp / s_found are free again
-            if (lane == 0)
-            {
-                s_warp[warp] = val;
-                s_found[warp] = incl != 0;
-            }
-            __syncthreads();
-            bool found = false;
+    // per-pixel cluster reference (imageStore, find_unique_clusters.comp:113-120), tile-local for now: the finalizer
+    // of this tile adds the tile's base.  Out-of-image pixels are dropped.
 #pragma unroll
-            for (int w = 0; w < kKeyThreads / 32; w++)
-            {
-                if (!found)
-                {
-                    base += s_warp[w];
-                    found = s_found[w] != 0;
-                }
-            }
-            if (found) break;
-            window -= kKeyThreads;
-        }
-        if (tid == 0) st_relaxed_u64(&status[tile], kFlagInclusive | (uint32_t) (base + unique));
+    for (int r = 0; r < 4; r++)
+    {
+        const uint32_t x = (ti << 5) + lane, y = (tj << 5) + warp + 8 * r;
+        const uint32_t word = s_bitmap[sub[r] >> 5];
+        const uint32_t ref = s_prefix[sub[r] >> 5] + __popc(word & ((1u << (sub[r] & 31)) - 1u));
+        if (x < prm.width && y < prm.height) cluster_ref[(size_t) y * prm.width + x] = ref;
     }
+
+    // unique keys, ascending inside the tile, parked in the tile's slot of the staging area
+    const uint32_t tile_bits = (ti & 0xFFu) | ((tj & 0xFFu) << 8);
+    uint32_t* parked = tile_keys + (size_t) tile * 1024;
+    uint32_t out = excl;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        uint32_t bits = words[i];
+        while (bits)
+        {
+            const uint32_t b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            parked[out++] = tile_bits | (((8 * tid + i) * 32 + b) << 16);
+        }
+    }
+    if (tid == 0) tile_count[tile] = unique;
+}
+
+// second half of a7: global cluster numbers and the key list, from the exclusive scan of the per-tile counts.
+// One CTA per tile, pure streaming (the tile's 4 KB of cluster numbers are read-modified-written, its parked keys copied).
+__global__ void __launch_bounds__(kKeyThreads)
+finalize_clusters_kernel(cluster_key_params prm, const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_base,
+                         const uint32_t* __restrict__ tile_keys, uint32_t* keys_out, uint32_t* dispatch_params, uint32_t* cluster_ref)
+{
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t base = tile_base[tile], unique = tile_count[tile];
     if (tid == 0)
     {
         if (base + unique > prm.max_keys) atomicOr(&dispatch_params[3], 1u);   // overflow, detected not silent
@@ -338,31 +327,24 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
             dispatch_params[2] = 1;
         }
     }
-    __syncthreads();   // s_prefix complete
-
-    // per-pixel cluster reference (imageStore, find_unique_clusters.comp:113-120); out-of-image pixels are dropped
-#pragma unroll
-    for (int r = 0; r < 4; r++)
+    const uint32_t* parked = tile_keys + (size_t) tile * 1024;
+    for (uint32_t i = tid; i < unique; i += kKeyThreads)
+        if (base + i < prm.max_keys) keys_out[base + i] = parked[i];
+    if (base != 0)
     {
-        const uint32_t x = (ti << 5) + lane, y = (tj << 5) + warp + 8 * r;
-        const uint32_t word = s_bitmap[sub[r] >> 5];
-        const uint32_t ref = base + s_prefix[sub[r] >> 5] + __popc(word & ((1u << (sub[r] & 31)) - 1u));
-        if (x < prm.width && y < prm.height) cluster_ref[(size_t) y * prm.width + x] = ref;
-    }
-
-    // unique keys, ascending inside the tile
-    const uint32_t tile_bits = (ti & 0xFFu) | ((tj & 0xFFu) << 8);
-    uint32_t out = base + excl;
+        const uint32_t ti = tile % prm.tiles_x, tj = tile / prm.tiles_x;
+        uint32_t v[4];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-    {
-        uint32_t bits = words[i];
-        while (bits)
+        for (int r = 0; r < 4; r++)
         {
-            const uint32_t b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (out < prm.max_keys) keys_out[out] = tile_bits | (((8 * tid + i) * 32 + b) << 16);
-            out++;
+            const uint32_t x = (ti << 5) + lane, y = (tj << 5) + warp + 8 * r;
+            v[r] = (x < prm.width && y < prm.height) ? cluster_ref[(size_t) y * prm.width + x] : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            const uint32_t x = (ti << 5) + lane, y = (tj << 5) + warp + 8 * r;
+            if (x < prm.width && y < prm.height) cluster_ref[(size_t) y * prm.width + x] = v[r] + base;
         }
     }
 }
@@ -688,7 +670,11 @@ using namespace vrenb200;
 extern "C" size_t vrenb200_find_unique_clusters_scratch_bytes(uint32_t width, uint32_t height)
 {
     const size_t tiles = (size_t) ((width + 31) / 32) * ((height + 31) / 32);
-    return align_up(offsetof(cluster_scan_state, status) + std::max<size_t>(tiles, 1) * 8, 256) + kMaxSlices * sizeof(float);
+    // slice thresholds | per-tile counts | per-tile bases | scan scratch | parked keys: 1024 slots per tile (a 32x32 tile
+    // cannot hold more distinct keys)
+    const size_t t = std::max<size_t>(tiles, 1);
+    return align_up(kMaxSlices * sizeof(float), 256) + 2 * align_up(t * 4, 256) + align_up(vrenb200_scan_scratch_bytes((uint32_t) t), 256) +
+           t * 1024 * sizeof(uint32_t);
 }
 
 extern "C" int vrenb200_find_unique_clusters(vrenb200_stream_t stream,
@@ -709,10 +695,13 @@ extern "C" int vrenb200_find_unique_clusters(vrenb200_stream_t stream,
     const float a = 1.0f + (2.0f * pc.tan_half) / (float) tiles_y;
     const slice_table& tab = get_slice_table(camera->near_plane, a);
 
-    const size_t state_bytes = align_up(offsetof(cluster_scan_state, status) + (size_t) tiles_x * tiles_y * 8, 256);
-    cluster_scan_state* state = static_cast<cluster_scan_state*>(scratch);
-    float* thresholds = reinterpret_cast<float*>(static_cast<char*>(scratch) + state_bytes);
-    VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, state_bytes, s)));
+    const uint32_t num_tiles = tiles_x * tiles_y;
+    char* cursor = static_cast<char*>(scratch);
+    float* thresholds = reinterpret_cast<float*>(cursor);               cursor += align_up(kMaxSlices * sizeof(float), 256);
+    uint32_t* tile_count = reinterpret_cast<uint32_t*>(cursor);         cursor += align_up((size_t) num_tiles * 4, 256);
+    uint32_t* tile_base = reinterpret_cast<uint32_t*>(cursor);          cursor += align_up((size_t) num_tiles * 4, 256);
+    void* scan_scratch = cursor;                                        cursor += align_up(vrenb200_scan_scratch_bytes(num_tiles), 256);
+    uint32_t* tile_keys = reinterpret_cast<uint32_t*>(cursor);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(dispatch_params, 0, 16, s)));                  // vkCmdUpdateBuffer {0,1,1}
     VRENB200_TRY(check_cuda(cudaMemcpyAsync(thresholds, tab.thresholds.data(), tab.thresholds.size() * sizeof(float),
                                             cudaMemcpyHostToDevice, s)));
@@ -730,8 +719,11 @@ extern "C" int vrenb200_find_unique_clusters(vrenb200_stream_t stream,
     std::memset(&nmap, 0, sizeof(nmap));
     prm.use_tma = make_tile_map(&dmap, depth, width, height, 4) &&
                   (!prm.has_normals || make_tile_map(&nmap, normals_rgba16f, width, height, 8));
-    find_unique_clusters_kernel<<<tiles_x * tiles_y, kKeyThreads, 0, s>>>(dmap, nmap, depth, static_cast<const uint2*>(normals_rgba16f),
-                                                                 thresholds, prm, state, keys_out, dispatch_params, cluster_ref);
+    find_unique_clusters_kernel<<<num_tiles, kKeyThreads, 0, s>>>(dmap, nmap, depth, static_cast<const uint2*>(normals_rgba16f), thresholds, prm,
+                                                         tile_count, cluster_ref, tile_keys);
+    VRENB200_TRY(check_launch());
+    VRENB200_TRY(vrenb200_exclusive_scan_u32(stream, tile_count, tile_base, num_tiles, scan_scratch, vrenb200_scan_scratch_bytes(num_tiles)));
+    finalize_clusters_kernel<<<num_tiles, kKeyThreads, 0, s>>>(prm, tile_count, tile_base, tile_keys, keys_out, dispatch_params, cluster_ref);
     return check_launch();
 }
 
