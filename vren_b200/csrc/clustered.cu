@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -77,6 +78,50 @@ struct slice_table
     float near_plane = 0, a = 0;
     std::vector<float> thresholds; // [0] = 0 (unused), [1..count)
 };
+
+// Device copies of the small per-camera tables (slice thresholds, near_k), keyed by (device, kind, two floats): the
+// tables only change with the camera, so a frame re-uses them instead of paying a host->device copy (and, for near_k,
+// 1024 powf calls) per call.  Filled with a synchronous copy; the oldest entry is freed when the cache is full
+// (cudaFree waits for the kernels that may still read it).
+struct device_table
+{
+    int device, kind;
+    float p0, p1;
+    float* data;
+    uint32_t count;
+};
+
+std::mutex g_table_mutex;
+std::vector<device_table> g_tables;
+
+const device_table* find_device_table(int kind, float p0, float p1)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (const device_table& t : g_tables)
+        if (t.device == dev && t.kind == kind && t.p0 == p0 && t.p1 == p1) return &t;
+    return nullptr;
+}
+
+const device_table* add_device_table(int kind, float p0, float p1, const float* host, uint32_t count)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (g_tables.size() >= 16)
+    {
+        cudaFree(g_tables.front().data);
+        g_tables.erase(g_tables.begin());
+    }
+    device_table t{dev, kind, p0, p1, nullptr, count};
+    if (cudaMalloc(&t.data, (size_t) count * sizeof(float)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(t.data, host, (size_t) count * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+    {
+        cudaFree(t.data);
+        return nullptr;
+    }
+    g_tables.push_back(t);
+    return &g_tables.back();
+}
 
 const slice_table& get_slice_table(float near_plane, float a)
 {
@@ -693,25 +738,36 @@ extern "C" int vrenb200_find_unique_clusters(vrenb200_stream_t stream,
 
     const proj_consts pc = make_proj(*camera);
     const float a = 1.0f + (2.0f * pc.tan_half) / (float) tiles_y;
-    const slice_table& tab = get_slice_table(camera->near_plane, a);
+    const float* thresholds = nullptr;
+    uint32_t table_len = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_table_mutex);
+        const device_table* cached = find_device_table(0, camera->near_plane, a);
+        if (cached == nullptr)
+        {
+            const slice_table& tab = get_slice_table(camera->near_plane, a);
+            cached = add_device_table(0, camera->near_plane, a, tab.thresholds.data(), (uint32_t) tab.thresholds.size());
+            if (cached == nullptr) return VRENB200_ECUDA;
+        }
+        thresholds = cached->data;
+        table_len = cached->count;
+    }
 
     const uint32_t num_tiles = tiles_x * tiles_y;
     char* cursor = static_cast<char*>(scratch);
-    float* thresholds = reinterpret_cast<float*>(cursor);               cursor += align_up(kMaxSlices * sizeof(float), 256);
+    cursor += align_up(kMaxSlices * sizeof(float), 256);                // (formerly the per-call copy of the thresholds)
     uint32_t* tile_count = reinterpret_cast<uint32_t*>(cursor);         cursor += align_up((size_t) num_tiles * 4, 256);
     uint32_t* tile_base = reinterpret_cast<uint32_t*>(cursor);          cursor += align_up((size_t) num_tiles * 4, 256);
     void* scan_scratch = cursor;                                        cursor += align_up(vrenb200_scan_scratch_bytes(num_tiles), 256);
     uint32_t* tile_keys = reinterpret_cast<uint32_t*>(cursor);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(dispatch_params, 0, 16, s)));                  // vkCmdUpdateBuffer {0,1,1}
-    VRENB200_TRY(check_cuda(cudaMemcpyAsync(thresholds, tab.thresholds.data(), tab.thresholds.size() * sizeof(float),
-                                            cudaMemcpyHostToDevice, s)));
 
     cluster_key_params prm{};
     prm.width = width; prm.height = height; prm.tiles_x = tiles_x; prm.tiles_y = tiles_y;
     prm.iB = pc.iB; prm.nAB = pc.nAB;
     prm.inv_near = 1.0f / camera->near_plane;
     prm.inv_log2a = (float) (1.0 / std::log2((double) a));
-    prm.table_len = (uint32_t) tab.thresholds.size();
+    prm.table_len = table_len;
     prm.max_keys = max_keys;
     prm.has_normals = normals_rgba16f != nullptr;
     CUtensorMap dmap, nmap;
@@ -769,16 +825,25 @@ extern "C" int vrenb200_assign_lights(vrenb200_stream_t stream,
     prm.max_keys = max_keys; prm.max_assigned = max_assigned;
 
     // near_k = near * pow(a, k), k < 1024 (clustered_shading.glsl:97) evaluated on the host with powf
-    float near_host[1024];
-    for (int k = 0; k < 1024; k++) near_host[k] = camera->near_plane * powf(prm.a, (float) k);
+    const float* near_table = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_table_mutex);
+        const device_table* cached = find_device_table(1, camera->near_plane, prm.a);
+        if (cached == nullptr)
+        {
+            float near_host[1024];
+            for (int k = 0; k < 1024; k++) near_host[k] = camera->near_plane * powf(prm.a, (float) k);
+            cached = add_device_table(1, camera->near_plane, prm.a, near_host, 1024);
+            if (cached == nullptr) return VRENB200_ECUDA;
+        }
+        near_table = cached->data;
+    }
     char* sp = static_cast<char*>(scratch);
-    float* near_table = reinterpret_cast<float*>(sp);
     assign_state* state = reinterpret_cast<assign_state*>(sp + 1024 * sizeof(float));
     uint32_t* alloc = reinterpret_cast<uint32_t*>(sp + 1024 * sizeof(float) + 256);
     void* scan_scratch = sp + 1024 * sizeof(float) + 256 + align_up((size_t) max_keys * 4, 256);
     const size_t scan_bytes = vrenb200_scan_scratch_bytes(max_keys);
     uint32_t* arena = reinterpret_cast<uint32_t*>(static_cast<char*>(scan_scratch) + scan_bytes);
-    VRENB200_TRY(check_cuda(cudaMemcpyAsync(near_table, near_host, sizeof(near_host), cudaMemcpyHostToDevice, s)));
     VRENB200_TRY(check_cuda(cudaMemsetAsync(state, 0, sizeof(assign_state), s)));
 
     const float4* bvh = static_cast<const float4*>(bvh_buffer);

@@ -210,53 +210,52 @@ bucket_histogram_kernel(const uint2* __restrict__ pairs, uint32_t n, sort_contro
     }
 }
 
-// counts -> bucket END offsets (inclusive prefix): what bucket_sort_write.comp:32 leaves behind. One CTA.
+// counts -> bucket END offsets (inclusive prefix): what bucket_sort_write.comp:32 leaves behind.  64 CTAs x 1024
+// counters: every CTA first sums the raw counts of the buckets before its slice (coalesced 128-bit reads, at most 252 KB
+// from L2), then scans its own 1024.  Out of place (raw counts live in the scratch), so CTAs never read what another one
+// has already rewritten.  (One CTA with 64 strided counters per thread took 22 us of the 0.4 ms light-assignment chain.)
+constexpr int kEndOffsetCtas = kBucketKeys / 1024;
+
 __global__ void __launch_bounds__(1024)
-bucket_end_offsets_kernel(uint32_t* counters)
+bucket_end_offsets_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ counters)
 {
     __shared__ uint32_t s_warp[32];
-    constexpr int PER = kBucketKeys / 1024; // 64 consecutive counters per thread
-    uint4* mine = reinterpret_cast<uint4*>(counters + threadIdx.x * PER);
-    uint4 v[PER / 4];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int i = 0; i < PER / 4; i++)
+    __shared__ uint32_t s_base;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // sum of all the buckets before this CTA's slice
+    uint32_t before = 0;
+    const uint4* raw4 = reinterpret_cast<const uint4*>(raw);
+    for (uint32_t i = tid; i < blockIdx.x * 256u; i += 1024)
     {
-        v[i] = mine[i];
-        sum += v[i].x + v[i].y + v[i].z + v[i].w;
+        const uint4 v = raw4[i];
+        before += v.x + v.y + v.z + v.w;
     }
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = sum;
+    before = __reduce_add_sync(kFullMask, before);
+    if (lane == 0) s_warp[warp] = before;
+    __syncthreads();
+    if (warp == 0)
+    {
+        const uint32_t t = __reduce_add_sync(kFullMask, s_warp[lane]);
+        if (lane == 0) s_base = t;
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+    const uint32_t mine = raw[blockIdx.x * 1024u + tid];
+    uint32_t inc = mine;
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1)
     {
         const uint32_t t = __shfl_up_sync(kFullMask, inc, s);
         if (lane >= (unsigned) s) inc += t;
     }
+    __syncthreads();   // s_warp is free again
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    if (warp == 0)
-    {
-        uint32_t w = s_warp[lane];
+    uint32_t wp = 0;
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1)
-        {
-            const uint32_t t = __shfl_up_sync(kFullMask, w, s);
-            if (lane >= (unsigned) s) w += t;
-        }
-        s_warp[lane] = w;
-    }
-    __syncthreads();
-    uint32_t run = inc - sum + (warp > 0 ? s_warp[warp - 1] : 0u);
-#pragma unroll
-    for (int i = 0; i < PER / 4; i++)
-    {
-        run += v[i].x; v[i].x = run;
-        run += v[i].y; v[i].y = run;
-        run += v[i].z; v[i].z = run;
-        run += v[i].w; v[i].w = run;
-        mine[i] = v[i];
-    }
+    for (int w = 0; w < 32; w++)
+        if (w < (int) warp) wp += s_warp[w];
+    counters[blockIdx.x * 1024u + tid] = base + wp + inc;
 }
 
 // ---- 2. exclusive scan of each 256-bin histogram (grid = passes, block = 256) ----------------------------
@@ -1655,7 +1654,7 @@ extern "C" size_t vrenb200_bucket_sort_output_bytes(uint32_t n)
 
 extern "C" size_t vrenb200_bucket_sort_scratch_bytes(uint32_t n)
 {
-    return align_up((size_t) n * 8, 256) + control_bytes(n);
+    return align_up((size_t) n * 8, 256) + control_bytes(n) + (size_t) kBucketKeys * sizeof(uint32_t);   // tmp | control | raw bucket counts
 }
 
 extern "C" int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pairs, uint32_t n, void* out,
@@ -1667,25 +1666,26 @@ extern "C" int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pai
         return VRENB200_EALIGN;
     cudaStream_t s = as_stream(stream);
     uint32_t* counters = reinterpret_cast<uint32_t*>(static_cast<char*>(out) + align_up((size_t) n * 8, 256)); // bucket_sort.cpp:86
-    VRENB200_TRY(check_cuda(cudaMemsetAsync(counters, 0, kBucketKeys * sizeof(uint32_t), s)));                 // bucket_sort.cpp:104
-    if (n == 0) return VRENB200_OK;
+    if (n == 0) return check_cuda(cudaMemsetAsync(counters, 0, kBucketKeys * sizeof(uint32_t), s));           // bucket_sort.cpp:104
     if (scratch == nullptr || scratch_bytes < vrenb200_bucket_sort_scratch_bytes(n)) return VRENB200_ESCRATCH;
     char* p = static_cast<char*>(scratch);
     uint32_t* tmp = reinterpret_cast<uint32_t*>(p);
     void* ctl_mem = p + align_up((size_t) n * 8, 256);
+    uint32_t* raw_counts = reinterpret_cast<uint32_t*>(p + align_up((size_t) n * 8, 256) + control_bytes(n));
     const sort_variant& var = g_variants[g_variant];
     const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
     sort_control* ctl = static_cast<sort_control*>(ctl_mem);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
     const size_t clear = sizeof(sort_control) + (size_t) 2 * tiles * kRadix * sizeof(uint32_t);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(ctl_mem, 0, clear, s)));
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(raw_counts, 0, kBucketKeys * sizeof(uint32_t), s)));
     const uint32_t hist_grid = (uint32_t) std::min<size_t>(kNumSMs * 2, ((size_t) n / 2 + kHistThreads - 1) / kHistThreads + 1);
-    bucket_histogram_kernel<<<hist_grid, kHistThreads, 0, s>>>(static_cast<const uint2*>(in_pairs), n, ctl, counters);
+    bucket_histogram_kernel<<<hist_grid, kHistThreads, 0, s>>>(static_cast<const uint2*>(in_pairs), n, ctl, raw_counts);
     VRENB200_TRY(check_launch());
     radix_scan_histograms_kernel<<<2, kRadix, 0, s>>>(ctl);
     VRENB200_TRY(check_launch());
     VRENB200_TRY(var.launch(s, static_cast<const uint32_t*>(in_pairs), tmp, nullptr, nullptr, n, 0, ctl, lookback, tiles, LAYOUT_AOS));
     VRENB200_TRY(var.launch(s, tmp, static_cast<uint32_t*>(out), nullptr, nullptr, n, 1, ctl, lookback, tiles, LAYOUT_AOS));
-    bucket_end_offsets_kernel<<<1, 1024, 0, s>>>(counters);
+    bucket_end_offsets_kernel<<<kEndOffsetCtas, 1024, 0, s>>>(raw_counts, counters);
     return check_launch();
 }
