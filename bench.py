@@ -249,7 +249,14 @@ def secondary_metrics(lib, vlib, dev):
     cs = ClusterAndShade(w, h, max_point_lights=L)
     ms = timed(lambda: cs(w, h, cam, view, depth, None, pos, lights, L), iters=20)
     st = cs.status.cpu().numpy()
-    out["light_assign_4k_65536_lights"] = {"ms_per_view": ms, "target_ms": 0.5, "clusters": int(cs.dispatch_params[0]),
+    graph_ms = None
+    try:
+        graph = cs.capture(w, h, cam, view, depth, None, pos, lights, L)
+        graph_ms = timed(graph.replay, iters=20)
+    except Exception as exc:  # noqa: BLE001 - the stream-launched number above stands on its own
+        graph_ms = f"capture failed: {exc}"
+    out["light_assign_4k_65536_lights"] = {"ms_per_view": ms, "ms_per_view_graph_replay": graph_ms, "target_ms": 0.5,
+                                           "clusters": int(cs.dispatch_params[0]),
                                            "assigned_lights": int(st[0]), "node_tests": int(st[2]), "leaf_tests": int(st[3]),
                                            "stages": "construct_point_light_bvh + find_unique_cluster_list + assign_lights"}
     # SURVEY 8f rows on the same inputs: n1 per-pixel light-list walk, n2 depth-buffer pyramid

@@ -124,6 +124,41 @@ def test_assign_lights_no_lights_and_overflow(vren):
     assert np.array_equal(counts, wcounts) and np.array_equal(indices, windices)
 
 
+def test_cluster_chain_graph_replay_follows_new_inputs(vren):
+    """ClusterAndShade.capture(): the chain recorded once in a CUDA graph gives the oracle's lists for whatever the
+    buffers hold at replay time (a new frame: different depth buffer and light positions, same buffers and camera)"""
+    import math
+
+    import torch
+
+    from vren_b200.pipeline import ClusterAndShade
+
+    w, h, L = 640, 360, 5000
+    oc, vc = both_cameras(vren, w, h)
+    view = synthetic.view_matrix(0.2, 0.0, (0.0, 0.0, 0.0))
+    depth = dev(synthetic.depth_buffer(w, h, seed=31))
+    pos0, lights0 = synthetic.point_lights(L, seed=32, aspect=w / h, intensity=(0.5, 3.0))
+    pos, lights = dev(pos0), dev(lights0)
+    cs = ClusterAndShade(w, h, max_point_lights=L)
+    graph = cs.capture(w, h, vc, view.tolist(), depth, None, pos, lights, L)
+    for frame_seed in (41, 57):
+        new_depth = synthetic.depth_buffer(w, h, seed=frame_seed)
+        new_pos, new_lights = synthetic.point_lights(L, seed=frame_seed + 1, aspect=w / h, intensity=(0.5, 3.0))
+        depth.copy_(dev(new_depth))
+        pos.copy_(dev(new_pos))
+        lights.copy_(dev(new_lights))
+        graph.replay()
+        torch.cuda.synchronize()
+        wvp, wnodes, wpairs = oracle.construct_point_light_bvh(new_pos, new_lights, view)
+        wkeys, _ = oracle.find_unique_clusters(new_depth, None, oc)
+        wcounts, woffsets, windices, wtotal = oracle.assign_lights(w, h, oc, wkeys, cs.max_keys, wnodes, L, wpairs, wvp, cs.max_assigned)
+        assert int(cs.dispatch_params[0]) == wkeys.size
+        assert np.array_equal(host_u32(cs.cluster_keys)[: wkeys.size], wkeys)
+        assert np.array_equal(host_u32(cs.counts), wcounts) and np.array_equal(host_u32(cs.offsets), woffsets)
+        assert int(host_u32(cs.status)[0]) == wtotal
+        assert np.array_equal(host_u32(cs.indices)[:wtotal], windices[:wtotal])
+
+
 def test_cluster_chain_c5_full_size(vren):
     """BASELINE C5: 3840x2160 depth, 65 536 lights (intensity 1.0), one view"""
     (wkeys, wcounts, woffsets, windices, wtotal), (keys, counts, offsets, indices, status) = run_chain(vren, 3840, 2160, 65536, seed=2024)

@@ -30,10 +30,33 @@ def main(w=3840, h=2160, L=65536, iters=20, intensity=1.0, normals=False):
         torch.cuda.synchronize()
         if it >= 3:
             times.append(e0.elapsed_time(e1))
+    # the same chain replayed from a CUDA graph (buffers and camera fixed, contents free to change between replays)
+    graph_ms = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            cs(w, h, cam, view, depth, nrm, pos, lights, L)      # warm-up on the capture stream
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                cs(w, h, cam, view, depth, nrm, pos, lights, L)
+        torch.cuda.current_stream().wait_stream(side)
+        gt = []
+        for it in range(iters + 3):
+            e0, e1 = ev(), ev()
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                gt.append(e0.elapsed_time(e1))
+        graph_ms = float(np.median(gt))
+    except Exception as exc:  # noqa: BLE001
+        graph_ms = f"capture failed: {exc}"
     st = cs.status.cpu().numpy()
     print(json.dumps({"w": w, "h": h, "lights": L, "intensity": intensity, "normals": normals, "clusters": int(cs.dispatch_params[0]),
                       "assigned": int(st[0]), "node_tests": int(st[2]), "leaf_tests": int(st[3]),
-                      "view_ms_median": float(np.median(times)), "view_ms_min": float(np.min(times))}))
+                      "view_ms_median": float(np.median(times)), "view_ms_min": float(np.min(times)), "graph_replay_ms_median": graph_ms}))
 
 
 if __name__ == "__main__":

@@ -50,3 +50,18 @@ class ClusterAndShade:
                                               self.view_pos.data_ptr(), self.indices.data_ptr(), self.max_assigned,
                                               self.counts.data_ptr(), self.offsets.data_ptr(), self.status.data_ptr(),
                                               self.scratch_assign.data_ptr(), self.scratch_assign.numel()), "assign_lights")
+
+    def capture(self, width, height, camera: vlib.Camera, view16, depth, normals, positions, lights, light_count):
+        """Records steps 1-3 once into a CUDA graph and returns it: `graph.replay()` re-runs the chain on the contents the
+        buffers hold at that moment (new depth / light positions every frame, same buffers, same camera and view matrix).
+        A dozen small launches and memsets per view become one graph launch."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            # first call outside the capture: one-time allocations (device copies of the camera tables, kernel attributes)
+            self(width, height, camera, view16, depth, normals, positions, lights, light_count)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self(width, height, camera, view16, depth, normals, positions, lights, light_count)
+        torch.cuda.current_stream().wait_stream(side)
+        return graph
