@@ -220,8 +220,8 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
 {
     __shared__ alignas(128) float s_depth[32 * 32];
     __shared__ alignas(128) uint2 s_normal[32 * 32];
-    __shared__ uint32_t s_bitmap[2048];
-    __shared__ uint32_t s_prefix[2048];
+    __shared__ alignas(16) uint32_t s_bitmap[2048];
+    __shared__ alignas(16) uint32_t s_prefix[2048];
     __shared__ uint32_t s_warp[kKeyThreads / 32];
     __shared__ alignas(8) uint64_t s_bar;
 
@@ -293,11 +293,16 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
     __syncthreads();
 
     // popcount prefix over the 2048 bitmap words: thread t owns words 8t .. 8t+7
+    // (two 128-bit accesses per thread: eight 32-bit ones at a stride of 8 words are 8-way bank conflicts)
     uint32_t words[8], local[8], mine = 0;
+    {
+        const uint4 wa = reinterpret_cast<const uint4*>(s_bitmap)[2 * tid], wb = reinterpret_cast<const uint4*>(s_bitmap)[2 * tid + 1];
+        words[0] = wa.x; words[1] = wa.y; words[2] = wa.z; words[3] = wa.w;
+        words[4] = wb.x; words[5] = wb.y; words[6] = wb.z; words[7] = wb.w;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++)
     {
-        words[i] = s_bitmap[8 * tid + i];
         local[i] = mine;
         mine += __popc(words[i]);
     }
@@ -319,8 +324,8 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
         unique += t;
     }
     const uint32_t excl = warp_prefix + inc - mine;
-#pragma unroll
-    for (int i = 0; i < 8; i++) s_prefix[8 * tid + i] = excl + local[i];
+    reinterpret_cast<uint4*>(s_prefix)[2 * tid] = make_uint4(excl + local[0], excl + local[1], excl + local[2], excl + local[3]);
+    reinterpret_cast<uint4*>(s_prefix)[2 * tid + 1] = make_uint4(excl + local[4], excl + local[5], excl + local[6], excl + local[7]);
     __syncthreads();   // s_prefix complete
 
     // per-pixel cluster reference (imageStore, find_unique_clusters.comp:113-120), tile-local for now: the finalizer

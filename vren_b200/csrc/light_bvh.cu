@@ -62,14 +62,26 @@ view_space_minmax_kernel(const float4* __restrict__ positions, float4* __restric
         mn[c] = __reduce_min_sync(kFullMask, mn[c]);
         mx[c] = __reduce_max_sync(kFullMask, mx[c]);
     }
-    if ((threadIdx.x & 31) == 0)
+    // one atomic per block and component (per-warp atomics on the same six words serialise in L2: 11 us at 65536 lights)
+    __shared__ uint32_t s_part[6][8];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
     {
 #pragma unroll
         for (int c = 0; c < 3; c++)
         {
-            atomicMin(&minmax_ord[c], mn[c]);
-            atomicMax(&minmax_ord[3 + c], mx[c]);
+            s_part[c][warp] = mn[c];
+            s_part[3 + c][warp] = mx[c];
         }
+    }
+    __syncthreads();
+    if (warp == 0 && lane < 6)
+    {
+        uint32_t v = s_part[lane][0];
+#pragma unroll
+        for (int w = 1; w < 8; w++) v = lane < 3 ? min(v, s_part[lane][w]) : max(v, s_part[lane][w]);
+        if (lane < 3) atomicMin(&minmax_ord[lane], v);
+        else atomicMax(&minmax_ord[lane], v);
     }
 }
 
