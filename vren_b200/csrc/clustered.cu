@@ -640,10 +640,33 @@ assign_lights_place_kernel(const uint32_t* __restrict__ cluster_keys, const uint
     const uint32_t total_warps = gridDim.x * kAssignWarps;
     if (!overflow)
     {
-        for (uint32_t c = blockIdx.x * kAssignWarps + warp; c < count; c += total_warps)
+        // four clusters per step: their (count, arena slot, offset) loads, then their first two 32-wide chunks, are
+        // independent and in flight together (one cluster at a time is three dependent L2 round trips per ~50 indices)
+        constexpr int U = 4;
+        for (uint32_t c0 = blockIdx.x * kAssignWarps + warp; c0 < count; c0 += U * total_warps)
         {
-            const uint32_t n = counts[c], src = alloc[c], dst = offsets[c];
-            for (uint32_t i = lane; i < n; i += 32) indices[dst + i] = arena[src + i];
+            uint32_t n[U], src[U], dst[U], a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                const uint32_t c = c0 + u * total_warps;
+                n[u] = c < count ? counts[c] : 0u;
+                src[u] = c < count ? alloc[c] : 0u;
+                dst[u] = c < count ? offsets[c] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                a[u] = lane < n[u] ? arena[src[u] + lane] : 0u;
+                b[u] = lane + 32 < n[u] ? arena[src[u] + lane + 32] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                if (lane < n[u]) indices[dst[u] + lane] = a[u];
+                if (lane + 32 < n[u]) indices[dst[u] + lane + 32] = b[u];
+                for (uint32_t i = lane + 64; i < n[u]; i += 32) indices[dst[u] + i] = arena[src[u] + i];
+            }
         }
         return;
     }
