@@ -343,7 +343,8 @@ def run_ours(args):
                                                               sbytes, prof if profile else None), "radix_sort_pairs")
         else:
             if exchange is not None:
-                last["k"], last["v"], last["plan"] = vdist.sharded_sort_pairs_p2p(keys, vals, exchange, ops=dops)
+                last["phases"] = {}
+                last["k"], last["v"], last["plan"] = vdist.sharded_sort_pairs_p2p(keys, vals, exchange, ops=dops, phases=last["phases"])
             else:
                 last["k"], last["v"], last["plan"] = vdist.sharded_sort_pairs(keys, vals, ops=dops)
         e1.record()
@@ -388,6 +389,7 @@ def run_ours(args):
             vlib.check(lib.vrenb200_sort_profile_read(prof, kern_ms), "profile_read")
             hist_ms.append(kern_ms[0])
             pass_ms.extend(kern_ms[2:6])
+        phases_last = last.get("phases")
         last.clear()
 
     ms = sum(step_ms) / len(step_ms)
@@ -398,31 +400,51 @@ def run_ours(args):
     value = world * n / (ms_max * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C ABI (pinned), H2D + sort + D2H timed, max over ranks -----------------
-    e2e_steps = max(1, min(args.steps, 3))
-    hk0 = keys0.cpu()
-    hv0 = vals0.cpu()
-    hk = torch.empty(n, dtype=torch.int32, pin_memory=True)
-    hv = torch.empty(n, dtype=torch.int32, pin_memory=True)
-    wbytes = lib.vrenb200_radix_sort_host_work_bytes(n, 1)
+    # Every step uploads its 2 x 4n input bytes and downloads its 2 x 4n result bytes.  A single call is upload ->
+    # sort -> download, one PCIe direction at a time; consecutive steps are issued on two streams (two device work
+    # buffers, vrenb200_radix_sort_pairs_host_async), so step i+1 uploads while step i downloads.
+    e2e_steps = max(2, min(args.steps, 12))
     del keys, vals, scratch
-    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-    e2e_ms = []
-    for it in range(1 + e2e_steps):
-        hk.copy_(hk0)
-        hv.copy_(hv0)
-        barrier()
-        t0 = time.perf_counter()
-        vlib.check(lib.vrenb200_radix_sort_pairs_host(stream, hk.data_ptr(), hv.data_ptr(), n, work.data_ptr(), wbytes),
-                   "radix_sort_pairs_host")
-        dt = (time.perf_counter() - t0) * 1e3   # the call ends with a stream sync: wall == device + copies
-        if it > 0:
-            e2e_ms.append(dt)
-    hkn = hk.numpy().view("uint32")
-    assert os.environ.get("VRENB200_BENCH_NOVERIFY") == "1" or bool((hkn[1:] >= hkn[:-1]).all()), "bench e2e: output not sorted"
-    te = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device=dev)
+    hk_in = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    hv_in = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    hk_in.copy_(keys0)
+    hv_in.copy_(vals0)
+    wbytes = lib.vrenb200_radix_sort_host_work_bytes(n, 1)
+    lanes = [{"stream": torch.cuda.Stream(device=dev), "hk": torch.empty(n, dtype=torch.int32, pin_memory=True),
+              "hv": torch.empty(n, dtype=torch.int32, pin_memory=True), "work": torch.empty(wbytes, dtype=torch.uint8, device=dev)}
+             for _ in range(2)]
+    torch.cuda.synchronize()
+
+    def issue(i):
+        lane = lanes[i % 2]
+        vlib.check(lib.vrenb200_radix_sort_pairs_host_async(lane["stream"].cuda_stream, hk_in.data_ptr(), hv_in.data_ptr(), lane["hk"].data_ptr(),
+                                                            lane["hv"].data_ptr(), n, lane["work"].data_ptr(), wbytes), "radix_sort_pairs_host_async")
+
+    def drain():
+        for lane in lanes:
+            lane["stream"].synchronize()
+
+    issue(0); issue(1); drain()                      # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    issue(0); drain()
+    single_ms = (time.perf_counter() - t0) * 1e3     # one call alone: upload, sort, download back to back
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        issue(i)
+    drain()
+    e2e_step_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    for lane in lanes:
+        hkn = lane["hk"].numpy().view("uint32")
+        assert os.environ.get("VRENB200_BENCH_NOVERIFY") == "1" or bool((hkn[1:] >= hkn[:-1]).all()), "bench e2e: output not sorted"
+    assert os.environ.get("VRENB200_BENCH_NOVERIFY") == "1" or bool(torch.equal(hk_in[lanes[0]["hv"].long()], lanes[0]["hk"])), "bench e2e: pairs broken"
+    te = torch.tensor([e2e_step_ms, single_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n / (float(te.item()) * 1e-3) / 1e9
+    e2e_value = world * n / (float(te[0].item()) * 1e-3) / 1e9
+    del lanes[1]["work"]
+    work = lanes[0].pop("work")
 
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
@@ -458,9 +480,12 @@ def run_ours(args):
                          "whole_sort_frac": BYTES_PER_PAIR_SORT * n / (ms_max * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-                    "ms_per_step": float(te.item())},
+                    "ms_per_step": float(te[0].item()), "steps": e2e_steps,
+                    "issue": "consecutive steps alternate between two streams / device work buffers (upload of step i+1 overlaps download of step i)",
+                    "single_call_ms": float(te[1].item()), "single_call_value": world * n / (float(te[1].item()) * 1e-3) / 1e9},
             "gpu_launches": (6 if world == 1 else (2 + 6 if exchange is not None else 1 + 1 + 2 + 6)) * args.steps,
             "secondary": secondary,
+            "phases_rank0_last_step": phases_last if world > 1 else None,
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

@@ -107,6 +107,11 @@ int vrenb200_radix_sort_compat(vrenb200_stream_t stream, uint32_t* keys, uint32_
 size_t vrenb200_radix_sort_host_work_bytes(uint32_t n, int with_values);
 int vrenb200_radix_sort_pairs_host(vrenb200_stream_t stream, uint32_t* keys_host, uint32_t* values_host,
                                    uint32_t n, void* dev_work, size_t dev_work_bytes);
+/* enqueue-only form: separate source / destination host buffers (equal pointers = in place), no synchronisation.  Calls on
+ * different streams, each with its own dev_work, overlap one call's upload with another's download (pinned memory). */
+int vrenb200_radix_sort_pairs_host_async(vrenb200_stream_t stream, const uint32_t* keys_in_host, const uint32_t* values_in_host,
+                                         uint32_t* keys_out_host, uint32_t* values_out_host, uint32_t n,
+                                         void* dev_work, size_t dev_work_bytes);
 
 /* building blocks of the multi-GPU sort: all four 256-bin digit histograms of the keys
  * (hist_out: device uint32[4][256]) and a stable sort restricted to the digits [first_pass, first_pass+num_passes) */

@@ -236,6 +236,42 @@ def test_radix_all_variants_agree(vren):
         lib.vrenb200_radix_sort_set_variant(0)
 
 
+@pytest.mark.parametrize("n", [1, 1000, 8192 * 3 + 5, (1 << 20) + 3])
+def test_radix_host_buffers_sync_and_async(vren, n):
+    """vrenb200_radix_sort_pairs_host (in place, synchronising) and _host_async (separate destination, two streams in
+    flight at once, each with its own device work buffer) against the oracle's stable sort by key"""
+    import torch
+
+    lib = vren.load()
+    k = rand_u32(41, n) % np.uint32(max(n // 3, 1))                       # plenty of duplicate keys: stability is visible
+    v = np.arange(n, dtype=np.uint32)
+    wk, wv = oracle.sort_pairs(k, v)
+    wb = lib.vrenb200_radix_sort_host_work_bytes(n, 1)
+    pin = lambda a: torch.from_numpy(a.view(np.int32).copy()).pin_memory()
+    # synchronous, in place
+    hk, hv = pin(k), pin(v)
+    work = torch.empty(wb, dtype=torch.uint8, device="cuda")
+    assert lib.vrenb200_radix_sort_pairs_host(None, hk.data_ptr(), hv.data_ptr(), n, work.data_ptr(), wb) == 0
+    assert np.array_equal(hk.numpy().view(np.uint32), wk) and np.array_equal(hv.numpy().view(np.uint32), wv)
+    # two asynchronous calls on two streams from the same read-only source
+    src_k, src_v = pin(k), pin(v)
+    lanes = []
+    for _ in range(2):
+        lanes.append((torch.cuda.Stream(), torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory(),
+                      torch.empty(wb, dtype=torch.uint8, device="cuda")))
+    for rep in range(2):
+        for st, ok, ov, wk_buf in lanes:
+            assert lib.vrenb200_radix_sort_pairs_host_async(st.cuda_stream, src_k.data_ptr(), src_v.data_ptr(), ok.data_ptr(), ov.data_ptr(),
+                                                            n, wk_buf.data_ptr(), wb) == 0
+    for st, ok, ov, _ in lanes:
+        st.synchronize()
+        assert np.array_equal(ok.numpy().view(np.uint32), wk) and np.array_equal(ov.numpy().view(np.uint32), wv)
+    assert np.array_equal(src_k.numpy().view(np.uint32), k)               # the source is not touched
+    # argument checks
+    assert lib.vrenb200_radix_sort_pairs_host_async(None, src_k.data_ptr(), None, hk.data_ptr(), hv.data_ptr(), n, work.data_ptr(), wb) == vren.EINVAL_ARG
+    assert lib.vrenb200_radix_sort_pairs_host_async(None, src_k.data_ptr(), src_v.data_ptr(), hk.data_ptr(), hv.data_ptr(), n, work.data_ptr(), 16) == vren.ESCRATCH
+
+
 def test_radix_compat_preconditions(vren):
     import torch
 

@@ -1621,12 +1621,17 @@ extern "C" size_t vrenb200_radix_sort_host_work_bytes(uint32_t n, int with_value
     return buf * (with_values ? 2 : 1) + vrenb200_radix_sort_scratch_bytes(n, with_values);
 }
 
-extern "C" int vrenb200_radix_sort_pairs_host(vrenb200_stream_t stream, uint32_t* keys_host, uint32_t* values_host,
-                                              uint32_t n, void* dev_work, size_t dev_work_bytes)
+// Enqueue-only form with separate source and destination host buffers (equal pointers = in place): H2D, sort, D2H on
+// `stream`, no synchronisation.  With pinned host memory, calls on different streams (each with its own device work
+// buffer) overlap one call's upload with another call's download: PCIe is full duplex, a single call is not.
+extern "C" int vrenb200_radix_sort_pairs_host_async(vrenb200_stream_t stream, const uint32_t* keys_in_host, const uint32_t* values_in_host,
+                                                    uint32_t* keys_out_host, uint32_t* values_out_host, uint32_t n,
+                                                    void* dev_work, size_t dev_work_bytes)
 {
     if (n == 0) return VRENB200_OK;
-    if (keys_host == nullptr || dev_work == nullptr) return VRENB200_EINVAL_ARG;
-    const int kv = values_host != nullptr;
+    if (keys_in_host == nullptr || keys_out_host == nullptr || dev_work == nullptr) return VRENB200_EINVAL_ARG;
+    if ((values_in_host == nullptr) != (values_out_host == nullptr)) return VRENB200_EINVAL_ARG;
+    const int kv = values_in_host != nullptr;
     if (dev_work_bytes < vrenb200_radix_sort_host_work_bytes(n, kv)) return VRENB200_ESCRATCH;
     cudaStream_t s = as_stream(stream);
     char* p = static_cast<char*>(dev_work);
@@ -1635,14 +1640,22 @@ extern "C" int vrenb200_radix_sort_pairs_host(vrenb200_stream_t stream, uint32_t
     uint32_t* dv = kv ? reinterpret_cast<uint32_t*>(p + buf) : nullptr;
     char* scratch = p + buf * (kv ? 2 : 1);
     const size_t scratch_bytes = dev_work_bytes - buf * (kv ? 2 : 1);
-    VRENB200_TRY(check_cuda(cudaMemcpyAsync(dk, keys_host, (size_t) n * 4, cudaMemcpyHostToDevice, s)));
-    if (kv) VRENB200_TRY(check_cuda(cudaMemcpyAsync(dv, values_host, (size_t) n * 4, cudaMemcpyHostToDevice, s)));
+    VRENB200_TRY(check_cuda(cudaMemcpyAsync(dk, keys_in_host, (size_t) n * 4, cudaMemcpyHostToDevice, s)));
+    if (kv) VRENB200_TRY(check_cuda(cudaMemcpyAsync(dv, values_in_host, (size_t) n * 4, cudaMemcpyHostToDevice, s)));
     int st = kv ? vrenb200_radix_sort_pairs(stream, dk, dv, n, scratch, scratch_bytes)
                 : vrenb200_radix_sort_keys(stream, dk, n, scratch, scratch_bytes);
     if (st != VRENB200_OK) return st;
-    VRENB200_TRY(check_cuda(cudaMemcpyAsync(keys_host, dk, (size_t) n * 4, cudaMemcpyDeviceToHost, s)));
-    if (kv) VRENB200_TRY(check_cuda(cudaMemcpyAsync(values_host, dv, (size_t) n * 4, cudaMemcpyDeviceToHost, s)));
-    return check_cuda(cudaStreamSynchronize(s));
+    VRENB200_TRY(check_cuda(cudaMemcpyAsync(keys_out_host, dk, (size_t) n * 4, cudaMemcpyDeviceToHost, s)));
+    if (kv) VRENB200_TRY(check_cuda(cudaMemcpyAsync(values_out_host, dv, (size_t) n * 4, cudaMemcpyDeviceToHost, s)));
+    return VRENB200_OK;
+}
+
+extern "C" int vrenb200_radix_sort_pairs_host(vrenb200_stream_t stream, uint32_t* keys_host, uint32_t* values_host,
+                                              uint32_t n, void* dev_work, size_t dev_work_bytes)
+{
+    if (n == 0) return VRENB200_OK;
+    VRENB200_TRY(vrenb200_radix_sort_pairs_host_async(stream, keys_host, values_host, keys_host, values_host, n, dev_work, dev_work_bytes));
+    return check_cuda(cudaStreamSynchronize(as_stream(stream)));
 }
 
 // ---- a4: bucket sort ------------------------------------------------------------------------------------------

@@ -173,13 +173,17 @@ class P2PExchange:
         self.hk.barrier()
 
 
-def sharded_sort_pairs_p2p(keys: torch.Tensor, vals: torch.Tensor, exchange: P2PExchange, ops=None, group=None):
+def sharded_sort_pairs_p2p(keys: torch.Tensor, vals: torch.Tensor, exchange: P2PExchange, ops=None, group=None, phases: dict | None = None):
     """same contract as sharded_sort_pairs, but the all-to-all is fused into the partition kernel: every rank's
     onesweep pass on the top digit stores its pairs directly into the destination ranks' receive buffers through
-    NVLink peer pointers (no NCCL on the data path, no send-side staging copy)."""
+    NVLink peer pointers (no NCCL on the data path, no send-side staging copy).
+    `phases` (optional dict): filled with CUDA-event milliseconds of {plan, exchange, local_sort} for this call."""
     ops = ops or CudaOps()
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if phases is not None else None
+    if ev:
+        ev[0].record()
     hist = ops.top_digit_histogram(keys).to(torch.int64)
     gathered = [torch.empty_like(hist) for _ in range(world)]
     dist.all_gather(gathered, hist, group=group)
@@ -196,12 +200,23 @@ def sharded_sort_pairs_p2p(keys: torch.Tensor, vals: torch.Tensor, exchange: P2P
     kp[:world] = torch.tensor(exchange.key_ptrs, dtype=torch.int64) + 4 * my_offset
     vp[:world] = torch.tensor(exchange.val_ptrs, dtype=torch.int64) + 4 * my_offset
     table = torch.cat([kp.view(torch.uint8), vp.view(torch.uint8), rank_of]).to(keys.device, non_blocking=True)
+    if ev:
+        ev[1].record()
     exchange.barrier()                       # every rank is done with the previous contents of the receive buffers
     ops.partition_scatter(keys, vals, table)
     exchange.barrier()                       # all remote stores into my buffers have completed
+    if ev:
+        ev[2].record()
     n_recv = recv_counts[rank]
     rk, rv = exchange.keys[:n_recv], exchange.vals[:n_recv]
     ops.sort_pairs(rk, rv)
+    if ev:
+        ev[3].record()
+        ev[3].synchronize()
+        phases["plan_ms"] = ev[0].elapsed_time(ev[1])
+        phases["exchange_ms"] = ev[1].elapsed_time(ev[2])
+        phases["local_sort_ms"] = ev[2].elapsed_time(ev[3])
+        phases["received_pairs"] = int(n_recv)
     plan = SortPlan(bounds, [int(v) for v in per_dest[rank]], [int(v) for v in per_dest[:, rank]])
     return rk, rv, plan
 

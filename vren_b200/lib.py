@@ -111,6 +111,7 @@ _LATE_SIGS = [
     ("vrenb200_exclusive_scan_u32_base", _i32, (_vp, _vp, _vp, _u32, _u32, _vp, _sz)),
     ("vrenb200_radix_digit_histograms", _i32, (_vp, _vp, _u32, _vp)),
     ("vrenb200_bounce_point_lights", _i32, (_vp, _vp, _vp, _u32, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_float, C.c_float)),
+    ("vrenb200_radix_sort_pairs_host_async", _i32, (_vp, _vp, _vp, _vp, _vp, _u32, _vp, _sz)),
     ("vrenb200_scan_set_variant", _i32, (_i32,)),
     ("vrenb200_scan_set_runahead", _i32, (_i32, _i32)),
     ("vrenb200_radix_sort_range_scratch_bytes", _sz, (_u32,)),
