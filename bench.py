@@ -277,6 +277,19 @@ def secondary_metrics(lib, vlib, dev):
     bdir = torch.cat([bdir, torch.zeros(L, 1, device=dev)], 1).contiguous()
     ms = timed(lambda: vlib.bounce_point_lights(bpos, bdir, (-10.0, -10.0, -10.0), (10.0, 10.0, 10.0), 3.0, 0.016))
     out["bounce_point_lights_65536"] = {"ms": ms, "GB/s": 64 * L / ms / 1e6, "bytes_per_light": 64, "note": "4 MB problem: launch-bound"}
+    # n4: debug lines of the 2^20-leaf BVH built above the C4 row's size (32 B read + 384 B written per node)
+    leaves = 1 << 20
+    levels = lib.vrenb200_calc_bvh_level_count(leaves)
+    length = lib.vrenb200_calc_bvh_buffer_length(leaves)
+    nodes = torch.zeros(length * 8, dtype=torch.float32, device=dev)
+    nv = nodes.view(length, 8)
+    nv[:leaves, 0:3] = torch.rand(leaves, 3, device=dev) * 100
+    nv[:leaves, 4:7] = nv[:leaves, 0:3] + torch.rand(leaves, 3, device=dev) * 10
+    nodes.view(torch.int32).view(length, 8)[:leaves, 3] = -1
+    vlib.check(lib.vrenb200_build_bvh(stream, nodes.data_ptr(), leaves), "build_bvh")
+    verts = torch.empty(lib.vrenb200_visualize_bvh_vertex_count(levels), 4, dtype=torch.float32, device=dev)
+    ms = timed(lambda: vlib.check(lib.vrenb200_visualize_bvh(stream, nodes.data_ptr(), levels, verts.data_ptr()), "visualize_bvh"))
+    out["visualize_bvh_2p20_leaves"] = {"ms": ms, "GB/s": 416 * length / ms / 1e6, "frac_hbm": 416 * length / ms / 1e6 / peak, "bytes_per_node": 416}
     return out
 
 

@@ -244,6 +244,14 @@ int vrenb200_depth_pyramid_build(vrenb200_stream_t stream, const float* depth, u
 int vrenb200_bounce_point_lights(vrenb200_stream_t stream, float* positions, float* directions, uint32_t count,
                                  const float aabb_min[3], const float aabb_max[3], float speed, float dt);
 
+/* ---- n4: BVH debug consumer ---------------------------------------------------------------------------------------
+ * vren_demo::visualize_bvh::write (vren_demo/vren_demo/visualize_bvh.cpp:59-94, show_bvh.comp:62-78): the 12 box edges of
+ * every node as 24 vertices {float position[3]; uint32 color} at vertices[node * 24], colour by level
+ * (colors[level_count - level + 2]), INVALID nodes as degenerate black lines.  level_count = log32(padded leaf count)
+ * (vrenb200_calc_bvh_level_count), at most 4.  vertices: vrenb200_visualize_bvh_vertex_count(level_count) x 16 bytes. */
+uint64_t vrenb200_visualize_bvh_vertex_count(uint32_t level_count);
+int vrenb200_visualize_bvh(vrenb200_stream_t stream, const void* bvh_nodes, uint32_t level_count, void* vertices);
+
 #ifdef __cplusplus
 }
 #endif

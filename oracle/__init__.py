@@ -88,6 +88,7 @@ _LATE: list = [
     ("oracle_light_list_hash", None, (C.c_uint32, C.c_uint32, u32p, u32p, u32p, u32p, u32p)),
     ("oracle_depth_pyramid", C.c_uint32, (f32p, C.c_uint32, C.c_uint32, f32p)),
     ("oracle_bounce_point_lights", None, (f32p, f32p, C.c_uint32, f32p, f32p, C.c_float, C.c_float)),
+    ("oracle_visualize_bvh", None, (u32p, C.c_uint32, u32p)),
     ("oracle_construct_point_light_bvh", None, (f32p, f32p, C.c_uint32, f32p, f32p, voidp, u32p)),
     ("oracle_find_unique_clusters", C.c_uint32, (f32p, voidp, C.c_uint32, C.c_uint32, C.POINTER(Camera), u32p, u32p)),
     ("oracle_assign_lights", C.c_uint64,
@@ -263,6 +264,16 @@ def bounce_point_lights(positions: np.ndarray, directions: np.ndarray, aabb_min,
     lo, hi = np.asarray(aabb_min, np.float32).copy(), np.asarray(aabb_max, np.float32).copy()
     load().oracle_bounce_point_lights(pos.reshape(-1), dirs.reshape(-1), pos.shape[0], lo, hi, np.float32(speed), np.float32(dt))
     return pos, dirs
+
+
+def visualize_bvh(nodes: np.ndarray, level_count: int) -> np.ndarray:
+    """visualize_bvh.cpp:59-94 + show_bvh.comp:62-78.  nodes: the BVH buffer viewed as uint32 [N, 8] -> uint32 [N * 24, 4]"""
+    nodes = np.ascontiguousarray(nodes).view(np.uint32).reshape(-1, 8)
+    count = sum(32 ** l for l in range(level_count + 1))
+    assert nodes.shape[0] >= count
+    out = np.zeros((count * 24, 4), np.uint32)
+    load().oracle_visualize_bvh(nodes.reshape(-1), level_count, out.reshape(-1))
+    return out
 
 
 def light_list_hash(cluster_ref: np.ndarray, counts: np.ndarray, offsets: np.ndarray, indices: np.ndarray) -> np.ndarray:

@@ -478,3 +478,43 @@ extern "C" void oracle_bounce_point_lights(float* positions, float* directions, 
         directions[i * 4 + 3] = 0.0f;
     }
 }
+
+// ---- n4: BVH debug consumer ----------------------------------------------------------------------------------------------
+// visualize_bvh.cpp:59-94 (one dispatch per level, leaves first) + show_bvh.comp:62-78 (12 lines per node, written with the
+// VREN_WRITE_DEBUG_DRAW_BUFFER_AABB macro, show_bvh.comp:46-60).  nodes: {min[3], next, max[3], pad} x N; vertices: {pos[3], color}.
+extern "C" void oracle_visualize_bvh(const uint32_t* nodes, uint32_t level_count, uint32_t* vertices)
+{
+    static const uint32_t colors[7] = {0xff0000, 0xffff00, 0x00ff00, 0x0000ff, 0x00ffff, 0xff00ff, 0xffffff};
+    uint32_t offset = 0;
+    for (int32_t level = (int32_t) level_count; level >= 0; level--)
+    {
+        const uint32_t node_count = 1u << (5 * level);
+        const uint32_t color = colors[level_count - level + 2];
+        for (uint32_t i = 0; i < node_count; i++)
+        {
+            const uint32_t node_idx = i + offset;
+            const uint32_t* n = nodes + (size_t) node_idx * 8;
+            uint32_t m[3] = {n[0], n[1], n[2]}, M[3] = {n[4], n[5], n[6]}, c = color;
+            if (n[3] == 0xFFFFFFFEu) { m[0] = m[1] = m[2] = M[0] = M[1] = M[2] = 0u; c = 0u; }   // float 0.0 bits
+            uint32_t* out = vertices + (size_t) node_idx * 24 * 4;
+            auto line = [&](uint32_t ax, uint32_t ay, uint32_t az, uint32_t bx, uint32_t by, uint32_t bz) {
+                out[0] = ax; out[1] = ay; out[2] = az; out[3] = c;
+                out[4] = bx; out[5] = by; out[6] = bz; out[7] = c;
+                out += 8;
+            };
+            line(m[0], m[1], m[2], M[0], m[1], m[2]);
+            line(M[0], m[1], m[2], M[0], m[1], M[2]);
+            line(M[0], m[1], M[2], m[0], m[1], M[2]);
+            line(m[0], m[1], M[2], m[0], m[1], m[2]);
+            line(m[0], M[1], m[2], M[0], M[1], m[2]);
+            line(M[0], M[1], m[2], M[0], M[1], M[2]);
+            line(M[0], M[1], M[2], m[0], M[1], M[2]);
+            line(m[0], M[1], M[2], m[0], M[1], m[2]);
+            line(m[0], m[1], m[2], m[0], M[1], m[2]);
+            line(M[0], m[1], m[2], M[0], M[1], m[2]);
+            line(M[0], m[1], M[2], M[0], M[1], M[2]);
+            line(m[0], m[1], M[2], m[0], M[1], M[2]);
+        }
+        offset += node_count;
+    }
+}

@@ -15,6 +15,7 @@
 #include "vren/pipeline/clustered_shading.hpp"
 #include "vren/pipeline/depth_buffer_pyramid.hpp"
 #include "vren_demo/point_light_bouncer.hpp"
+#include "vren_demo/visualize_bvh.hpp"
 
 static int g_failures = 0;
 #define EXPECT(cond, ...)                                            \
@@ -351,6 +352,43 @@ static void test_point_light_bouncer(vren::context& ctx)
     std::printf("ok point_light_bouncer\n");
 }
 
+static void test_visualize_bvh(vren::context& ctx)
+{
+    // 32 leaves (one level above the root): boxes [i, i+1]^3; the root box must span [0, 32]^3 and carry the second colour
+    const uint32_t leaves = 32, level_count = vren::calc_bvh_level_count(leaves);
+    std::vector<vren::bvh_node> nodes(vren::calc_bvh_buffer_length(leaves));
+    for (uint32_t i = 0; i < leaves; i++)
+    {
+        for (int c = 0; c < 3; c++)
+        {
+            nodes[i].m_min[c] = (float) i;
+            nodes[i].m_max[c] = (float) i + 1;
+        }
+        nodes[i].m_next = vren::bvh_node::k_leaf_node;
+    }
+    auto bvh = vren::vk_utils::alloc_device_only_buffer(ctx, nodes.size() * sizeof(vren::bvh_node));
+    upload(bvh, nodes);
+    vren_demo::visualize_bvh vis(ctx);
+    auto draw = vren::vk_utils::alloc_device_only_buffer(ctx, vren_demo::visualize_bvh::get_required_vertex_buffer_size(level_count));
+    vren::vk_utils::immediate_graphics_queue_submit(ctx, [&](VkCommandBuffer cmd, vren::resource_container& rc) {
+        ctx.m_toolbox->m_build_bvh(cmd, rc, bvh, leaves);
+        vis.write(cmd, bvh, level_count, draw);
+    });
+    auto v = download<vren_demo::debug_draw_vertex>(draw, 33 * 24);
+    EXPECT(level_count == 1, "level count %u", level_count);
+    EXPECT(v[0].color == 0x00ff00u && v[32 * 24].color == 0x0000ffu, "level colours %06x %06x", v[0].color, v[32 * 24].color);
+    float lo = 1e30f, hi = -1e30f;
+    for (int k = 0; k < 24; k++)
+        for (int a = 0; a < 3; a++)
+        {
+            lo = std::min(lo, v[32 * 24 + k].position[a]);
+            hi = std::max(hi, v[32 * 24 + k].position[a]);
+        }
+    EXPECT(lo == 0.0f && hi == 32.0f, "root box %f %f", lo, hi);
+    EXPECT(v[5 * 24].position[0] == 5.0f && v[5 * 24 + 1].position[0] == 6.0f, "first edge of leaf 5: %f -> %f", v[5 * 24].position[0], v[5 * 24 + 1].position[0]);
+    std::printf("ok visualize_bvh\n");
+}
+
 int main()
 {
     try
@@ -364,6 +402,7 @@ int main()
         test_cluster_and_shade(ctx);
         test_depth_pyramid(ctx);
         test_point_light_bouncer(ctx);
+        test_visualize_bvh(ctx);
     }
     catch (std::exception const& e)
     {

@@ -112,6 +112,8 @@ _LATE_SIGS = [
     ("vrenb200_radix_digit_histograms", _i32, (_vp, _vp, _u32, _vp)),
     ("vrenb200_bounce_point_lights", _i32, (_vp, _vp, _vp, _u32, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_float, C.c_float)),
     ("vrenb200_radix_sort_pairs_host_async", _i32, (_vp, _vp, _vp, _vp, _vp, _u32, _vp, _sz)),
+    ("vrenb200_visualize_bvh_vertex_count", C.c_uint64, (_u32,)),
+    ("vrenb200_visualize_bvh", _i32, (_vp, _vp, _u32, _vp)),
     ("vrenb200_scan_set_variant", _i32, (_i32,)),
     ("vrenb200_scan_set_runahead", _i32, (_i32, _i32)),
     ("vrenb200_radix_sort_range_scratch_bytes", _sz, (_u32,)),
@@ -323,6 +325,17 @@ def bounce_point_lights(positions, directions, aabb_min, aabb_max, speed: float,
     check(lib.vrenb200_bounce_point_lights(_stream(), _ptr(positions), _ptr(directions), count, C.byref(lo), C.byref(hi),
                                            C.c_float(speed), C.c_float(dt)), "vrenb200_bounce_point_lights")
     return positions, directions
+
+
+def visualize_bvh(nodes_u8, level_count: int):
+    """vren_demo::visualize_bvh::write -> float32 [vertices, 4] device tensor {x, y, z, color bits}"""
+    import torch
+
+    lib = load()
+    count = lib.vrenb200_visualize_bvh_vertex_count(level_count)
+    out = torch.empty(count, 4, dtype=torch.float32, device=nodes_u8.device)
+    check(lib.vrenb200_visualize_bvh(_stream(), _ptr(nodes_u8), level_count, _ptr(out)), "vrenb200_visualize_bvh")
+    return out
 
 
 def light_list_hash(cluster_ref, disp, counts, offsets, indices):
