@@ -188,7 +188,7 @@ def test_radix_reference_case_reversed_iota_1024(vren):
 
 
 @pytest.mark.parametrize("pattern", ["uniform", "reversed", "mod100", "equal", "top_digit_only"])
-@pytest.mark.parametrize("n", [1, 2, 31, 1000, 6144, 6145, 1 << 16, (1 << 20), (1 << 20) + 4097])
+@pytest.mark.parametrize("n", [1, 2, 31, 1000, 6144, 6145, 8191, 8192, 8193, 1 << 16, (1 << 20), (1 << 20) + 4097])
 def test_radix_keys_vs_std_sort(vren, pattern, n):
     if pattern == "uniform":
         x = rand_u32(1, n)
@@ -203,7 +203,7 @@ def test_radix_keys_vs_std_sort(vren, pattern, n):
     assert np.array_equal(host_u32(vren.radix_sort_keys(dev_u32(x))), oracle.sort_keys(x))
 
 
-@pytest.mark.parametrize("n", [1, 77, 6144, 1 << 14, (1 << 20), (1 << 20) + 1234])
+@pytest.mark.parametrize("n", [1, 77, 6144, 8191, 8193, 1 << 14, 3 * 8192 + 1, (1 << 20), (1 << 20) + 1234])
 def test_radix_pairs_stable(vren, n):
     # few distinct keys -> stability is observable through the values
     k = (rand_u32(21, n) % np.uint32(1000) * np.uint32(0x00410041)).astype(np.uint32)
