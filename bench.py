@@ -310,6 +310,8 @@ def run_ours(args):
     lib = vlib.load()
     if args.variant is not None:
         vlib.check(lib.vrenb200_radix_sort_set_variant(args.variant), "set_variant")
+    if args.partition_shape is not None:
+        vlib.check(lib.vrenb200_radix_partition_set_shape(args.partition_shape), "set_partition_shape")
 
     n = 1 << args.log2n
     dev = torch.device("cuda", local_rank)
@@ -524,6 +526,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=28)
     ap.add_argument("--variant", type=int, default=None)
+    ap.add_argument("--partition-shape", type=int, default=None, help="N>1: tile shape of the exchange pass (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use the NCCL all-to-all-v exchange instead of the fused P2P one")

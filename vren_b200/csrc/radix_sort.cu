@@ -1355,6 +1355,7 @@ constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 constexpr uint32_t kMinTile = 256 * 16;
 
 int g_variant = 0;
+int g_partition_shape = 0;   // 0: 256x32 (2 CTAs/SM), 1: 256x16 (4 CTAs/SM), 2: 512x16 (2 CTAs/SM)
 
 size_t lookback_words(uint32_t n)
 {
@@ -1576,14 +1577,28 @@ extern "C" int vrenb200_radix_partition_scatter(vrenb200_stream_t stream, const 
     if (scratch == nullptr || scratch_bytes < control_bytes(n)) return VRENB200_ESCRATCH;
     if ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(values) | reinterpret_cast<uintptr_t>(scratch)) & 15) return VRENB200_EALIGN;
     cudaStream_t s = as_stream(stream);
-    constexpr int T = 256, I = 32;
-    const uint32_t tiles = (uint32_t) (((size_t) n + T * I - 1) / (T * I));
+    // tile shape of the exchange pass (tuning hook): remote stores back-pressure the CTAs, so more, smaller CTAs per SM
+    // keep more loads in flight while some CTAs drain into NVLink
+    const int shape = g_partition_shape;
+    const uint32_t tile = shape == 1 ? 256 * 16 : (shape == 2 ? 512 * 16 : 256 * 32);
+    const uint32_t tiles = (uint32_t) (((size_t) n + tile - 1) / tile);
     sort_control* ctl = static_cast<sort_control*>(scratch);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
     const size_t clear = sizeof(sort_control) + (size_t) kPasses * tiles * kRadix * sizeof(uint32_t);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, clear, s)));
-    return launch_one<T, I, LAYOUT_SOA, TILE_BY_BLOCKIDX | P2P_DEST, 2>(
-        s, keys, reinterpret_cast<uint32_t*>(const_cast<uint64_t*>(dest_table)), values, nullptr, n, kPasses - 1, ctl, lookback, tiles);
+    uint32_t* table = reinterpret_cast<uint32_t*>(const_cast<uint64_t*>(dest_table));
+    if (shape == 1)
+        return launch_one<256, 16, LAYOUT_SOA, TILE_BY_BLOCKIDX | P2P_DEST, 4>(s, keys, table, values, nullptr, n, kPasses - 1, ctl, lookback, tiles);
+    if (shape == 2)
+        return launch_one<512, 16, LAYOUT_SOA, TILE_BY_BLOCKIDX | P2P_DEST, 2>(s, keys, table, values, nullptr, n, kPasses - 1, ctl, lookback, tiles);
+    return launch_one<256, 32, LAYOUT_SOA, TILE_BY_BLOCKIDX | P2P_DEST, 2>(s, keys, table, values, nullptr, n, kPasses - 1, ctl, lookback, tiles);
+}
+
+extern "C" int vrenb200_radix_partition_set_shape(int shape)
+{
+    if (shape < 0 || shape > 2) return VRENB200_EINVAL_ARG;
+    g_partition_shape = shape;
+    return VRENB200_OK;
 }
 
 // stable sort by the digits [first_pass, first_pass + num_passes) only (8 bits each, pass 0 = least significant).
