@@ -299,6 +299,7 @@ struct onesweep_smem
     // P2P_DEST: per-digit destination base pointers (keys, values), possibly in a peer GPU's memory
     alignas(8) unsigned long long dst_ptr[P2P ? 2 : 1][P2P ? kMaxRanks : 1];
     uint8_t rank_of[P2P ? kRadix : 4];    // P2P_DEST: destination rank of every most-significant byte
+    uint32_t run_start[P2P ? kMaxRanks : 1], run_len[P2P ? kMaxRanks : 1], run_g[P2P ? kMaxRanks : 1];   // P2P_DEST: per-destination run of the tile
     uint32_t scan_warp[kRadix / 32];
     alignas(8) uint64_t bar_keys;
     alignas(8) uint64_t bar_vals;
@@ -623,14 +624,45 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
                 sm.dst_ptr[(MATCH & P2P_DEST) ? 1 : 0][(MATCH & P2P_DEST) ? tid : 0] = table->vptr[tid];
             }
             sm.digit_base[tid] = exclusive - tile_off;
+            if (tid < kMaxRanks)
+            {
+                sm.run_start[(MATCH & P2P_DEST) ? tid : 0] = tile_off;
+                sm.run_len[(MATCH & P2P_DEST) ? tid : 0] = real_cnt;
+                sm.run_g[(MATCH & P2P_DEST) ? tid : 0] = exclusive;
+            }
         }
         else
             sm.digit_base[tid] = ctl->hist[pass][tid] + exclusive - tile_off;
     }
     __syncthreads();
 
-    // coalesced write-out: in-tile position p -> digit run -> global slot
-    if (full)
+    if ((MATCH & P2P_DEST) && LAYOUT == LAYOUT_SOA)
+    {
+        // exchange mode: one run per destination rank, written in chunks that start on 128-byte lines of the DESTINATION
+        // (a warp store that straddles two lines becomes two partial NVLink write packets; the flat position loop below
+        // reached only ~55 % of the measured peer-store bandwidth, profiles/r1s_*)
+        constexpr int NR = (MATCH & P2P_DEST) ? kMaxRanks : 1;
+        for (int d = 0; d < NR; d++)
+        {
+            const uint32_t len = sm.run_len[d];
+            if (len == 0) continue;
+            const uint32_t s0 = sm.run_start[d], g0 = sm.run_g[d];
+            uint32_t* kdst = reinterpret_cast<uint32_t*>(sm.dst_ptr[0][d]) + g0;
+            uint32_t* vdst = reinterpret_cast<uint32_t*>(sm.dst_ptr[(MATCH & P2P_DEST) ? 1 : 0][d]) + g0;
+            const int32_t mis = (int32_t) ((reinterpret_cast<uintptr_t>(kdst) >> 2) & 31);   // elements past a 128-byte line
+            for (int32_t i = -mis + 32 * (int32_t) warp; i < (int32_t) len; i += 32 * WARPS)
+            {
+                const int32_t e = i + (int32_t) lane;
+                if (e >= 0 && e < (int32_t) len)
+                {
+                    const uint2 kv = reinterpret_cast<const uint2*>(sm.kv)[s0 + e];
+                    kdst[e] = kv.x;
+                    vdst[e] = kv.y;
+                }
+            }
+        }
+    }
+    else if (full)
     {
 #pragma unroll
         for (int j = 0; j < ITEMS; j++)
