@@ -685,9 +685,9 @@ extern "C" int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const 
     cudaStream_t s = as_stream(stream);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, need, s)));
     int threads = kScanVariantThreads[g_scan_variant];
-    // default: the run-ahead kernel (256 + 256 tiles of distance, L2 residency hints) for arrays that fill the machine,
-    // the register-tile kernel (smaller tiles, no idle prologue CTAs) below that
-    if (threads == kScanAuto) threads = n >= (1u << 22) ? -10256 : 256;
+    // default (profiles/r1v_scan_mid_sizes.log): the run-ahead kernel (256 + 256 tiles of distance, L2 residency hints)
+    // from 2^24 elements, the register-tile kernel below that (no idle prologue CTAs), with 1024-thread CTAs from 2^22
+    if (threads == kScanAuto) threads = n >= (1u << 24) ? -10256 : (n >= (1u << 22) ? 1024 : 256);
     if (threads < 0)
     {
         static bool configured = false;
