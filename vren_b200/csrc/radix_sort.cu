@@ -309,7 +309,8 @@ struct onesweep_smem
 enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 4, P2P_DEST = 8, DEPHASE = 16, LEADER_ATOMIC = 32, SPLIT_KV = 64,
        FAKE_LOOKBACK = 128 /* timing experiment: no chain, approximate destinations (WRONG results) */,
        DIRECT_LOAD = 256 /* count-first kernel: keys / values go from global memory straight to registers (no staging copy) */,
-       LB_INTERLEAVED = 512 /* count-first kernel: the look-back advances in non-blocking steps between ranking rows */ }; // option bits of the MATCH template argument
+       LB_INTERLEAVED = 512 /* count-first kernel: the look-back advances in non-blocking steps between ranking rows */,
+       LB_STEP2 = 1024, LB_STEP8 = 2048 /* ... every 2 / every 8 rows instead of every 4 */ }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -945,7 +946,8 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
             reinterpret_cast<uint2*>(sm.kv)[r] = make_uint2(key[j], val[j]);
         else
             sm.kv[r] = key[j];
-        if (INTERLEAVED && (j % 4) == 3 && j + 1 < ITEMS) lb_try();
+        constexpr int LB_EVERY = (MATCH & LB_STEP2) ? 2 : ((MATCH & LB_STEP8) ? 8 : 4);
+        if (INTERLEAVED && (j % LB_EVERY) == LB_EVERY - 1 && j + 1 < ITEMS) lb_try();
     }
 
     // 5. finish the look-back
@@ -1381,6 +1383,8 @@ const sort_variant g_variants[] = {
     CVARIANT(256, 24, TILE_BY_BLOCKIDX | DIRECT_LOAD, 3),   // 12
     CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED, 3),   // 13
     CVARIANT(256, 24, TILE_BY_BLOCKIDX, 3),   // 14: default of r1m
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP2, 2),   // 15
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8, 2),   // 16
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
