@@ -68,7 +68,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("CUDA build failed")
-    cmd = [_nvcc(), "-shared", "-o", str(LIB)] + [str(o) for o in objs] + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + [str(o) for o in objs] + ["-lcudart"]
     subprocess.run(cmd, check=True)
     return LIB
 
