@@ -41,8 +41,14 @@ def _worker(rank, world, port, sizes, skew, out_dir, p2p=False):
         tv = torch.from_numpy(vals.view(np.int32).copy()).cuda()
         if p2p:
             ex = vdist.P2PExchange(int(sum(sizes) * 1.5) + 4096, torch.device("cuda", rank))
+            sentinel = 0x5EED5EED
+            ex.keys.fill_(sentinel)
+            ex.vals.fill_(sentinel)
             for _ in range(2):      # twice: the receive buffers are reused
                 rk, rv, plan = vdist.sharded_sort_pairs_p2p(tk, tv, ex)
+            # nothing may be stored beyond the pairs this rank receives (the padding keys of a ragged last tile of a
+            # sender would land in the block of the next sender, or here)
+            assert bool((ex.keys[rk.numel():] == sentinel).all()) and bool((ex.vals[rk.numel():] == sentinel).all())
             rk, rv = rk.clone(), rv.clone()
         else:
             rk, rv, plan = vdist.sharded_sort_pairs(tk, tv)

@@ -503,7 +503,10 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 #pragma unroll
             for (int w = 0; w < WARPS; w++) cnt += sm.warp_hist[w][tid];
         }
-        real_cnt = cnt - ((tid == kRadix - 1) ? (uint32_t) TILE - valid : 0u);
+        // the padding keys (0xFFFFFFFF) of a ragged last tile carry the last digit; in exchange mode their "digit" is the
+        // destination rank of the top byte 0xFF
+        const uint32_t pad_digit = (MATCH & P2P_DEST) ? (uint32_t) sm.rank_of[kRadix - 1] : (uint32_t) kRadix - 1;
+        real_cnt = cnt - ((tid == pad_digit) ? (uint32_t) TILE - valid : 0u);
         if (!(MATCH & EARLY_HIST)) st_relaxed_u32(&lb[tid], (tile == 0 ? kLbFlagInclusive : kLbFlagAggregate) | real_cnt);
         inc = cnt;
 #pragma unroll
@@ -1620,8 +1623,9 @@ extern "C" int vrenb200_radix_partition_scatter(vrenb200_stream_t stream, const 
     const uint32_t tiles = (uint32_t) (((size_t) n + tile - 1) / tile);
     sort_control* ctl = static_cast<sort_control*>(scratch);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
-    const size_t clear = sizeof(sort_control) + (size_t) kPasses * tiles * kRadix * sizeof(uint32_t);
-    VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, clear, s)));
+    // the exchange pass runs as "pass kPasses - 1": only that region of the look-back words is touched
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, sizeof(sort_control), s)));
+    VRENB200_TRY(check_cuda(cudaMemsetAsync(lookback + (size_t) (kPasses - 1) * tiles * kRadix, 0, (size_t) tiles * kRadix * sizeof(uint32_t), s)));
     uint32_t* table = reinterpret_cast<uint32_t*>(const_cast<uint64_t*>(dest_table));
     if (shape == 1)
         return launch_one<256, 16, LAYOUT_SOA, TILE_BY_BLOCKIDX | P2P_DEST, 4>(s, keys, table, values, nullptr, n, kPasses - 1, ctl, lookback, tiles);

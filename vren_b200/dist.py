@@ -184,6 +184,9 @@ def sharded_sort_pairs_p2p(keys: torch.Tensor, vals: torch.Tensor, exchange: P2P
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if phases is not None else None
     if ev:
         ev[0].record()
+    # every rank has entered this call, i.e. is done with the previous contents of the receive buffers; issued first so
+    # that it completes under the planning below instead of in front of the exchange pass
+    exchange.barrier()
     hist = ops.top_digit_histogram(keys).to(torch.int64)
     gathered = [torch.empty_like(hist) for _ in range(world)]
     dist.all_gather(gathered, hist, group=group)
@@ -202,7 +205,6 @@ def sharded_sort_pairs_p2p(keys: torch.Tensor, vals: torch.Tensor, exchange: P2P
     table = torch.cat([kp.view(torch.uint8), vp.view(torch.uint8), rank_of]).to(keys.device, non_blocking=True)
     if ev:
         ev[1].record()
-    exchange.barrier()                       # every rank is done with the previous contents of the receive buffers
     ops.partition_scatter(keys, vals, table)
     exchange.barrier()                       # all remote stores into my buffers have completed
     if ev:
