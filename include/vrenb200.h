@@ -253,6 +253,29 @@ int vrenb200_bounce_point_lights(vrenb200_stream_t stream, float* positions, flo
 uint64_t vrenb200_visualize_bvh_vertex_count(uint32_t level_count);
 int vrenb200_visualize_bvh(vrenb200_stream_t stream, const void* bvh_nodes, uint32_t level_count, void* vertices);
 
+/* ---- n4: kd-tree (vren/vren/base/kd_tree.hpp:12-45) ------------------------------------------------------------------
+ * Pre-order node array: an inner node {split, axis 0..2, right_child_distance} is followed by its left subtree; a leaf is a
+ * run of nodes {point index, axis 3, run length in the first node / 0x3FFFFFFF in the others}.  axis = axis_and_link & 3,
+ * link = axis_and_link >> 2.  The tree needs at most 2 * count nodes. */
+typedef struct vrenb200_kd_tree_node
+{
+    union { float split; uint32_t index; };
+    uint32_t axis_and_link;
+} vrenb200_kd_tree_node;
+/* host: vren::kd_tree_build (kd_tree.cpp:5-75).  indices[count] (a permutation of the point indices to organise) is
+ * reordered in place; returns the number of nodes written (0 on bad arguments). */
+size_t vrenb200_kd_tree_build(const float* points, size_t point_stride, uint32_t* indices, size_t count,
+                              vrenb200_kd_tree_node* nodes, size_t max_leaf_point_count);
+/* host: vren::kd_tree_search (kd_tree.cpp:77-129): best_point / best_distance_squared are in-out (start with +inf);
+ * filter may be NULL (k_kd_tree_default_search_filter) */
+void vrenb200_kd_tree_search(const float* points, size_t point_stride, const vrenb200_kd_tree_node* nodes, const float sample[3],
+                             int (*filter)(uint32_t point, void* user), void* user, uint32_t* best_point, float* best_distance_squared);
+/* device: the same search for sample_count queries at once (points, nodes, samples[sample_count][3] and the outputs are
+ * device pointers); no reference counterpart */
+int vrenb200_kd_tree_search_batch(vrenb200_stream_t stream, const float* points, uint32_t point_stride,
+                                  const vrenb200_kd_tree_node* nodes, const float* samples, uint32_t sample_count,
+                                  uint32_t* best_point, float* best_distance_squared);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@
 #include <random>
 #include <vector>
 
+#include "vren/base/kd_tree.hpp"
 #include "vren/context.hpp"
 #include "vren/pipeline/clustered_shading.hpp"
 #include "vren/pipeline/depth_buffer_pyramid.hpp"
@@ -389,10 +390,41 @@ static void test_visualize_bvh(vren::context& ctx)
     std::printf("ok visualize_bvh\n");
 }
 
+// TEST(KDTree, NearestNeigborSearch), vren_test/vren_test/kd_tree.cpp:29: tree search == linear search
+static void test_kd_tree()
+{
+    std::mt19937 rng(11);
+    std::uniform_real_distribution<float> u(-50, 50);
+    const size_t n = 100000;
+    std::vector<float> pts(n * 3);
+    for (auto& v : pts) v = u(rng);
+    std::vector<uint32_t> indices(n);
+    std::iota(indices.begin(), indices.end(), 0u);
+    std::vector<vren::kd_tree_node> tree(2 * n);
+    const size_t nodes = vren::kd_tree_build(pts.data(), 3, indices.data(), n, tree.data(), 0, 32);
+    EXPECT(nodes > 0 && nodes <= 2 * n, "node count %zu", nodes);
+    for (int q = 0; q < 100; q++)
+    {
+        const float s[3] = {u(rng), u(rng), u(rng)};
+        uint32_t best = ~0u, lin = ~0u;
+        float best_d2 = INFINITY, lin_d2 = INFINITY;
+        vren::kd_tree_search(pts.data(), 3, indices.data(), n, tree.data(), 0, s, vren::k_kd_tree_default_search_filter, best, best_d2);
+        for (uint32_t i = 0; i < n; i++)
+        {
+            const float dx = s[0] - pts[3 * i], dy = s[1] - pts[3 * i + 1], dz = s[2] - pts[3 * i + 2];
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < lin_d2) { lin_d2 = d2; lin = i; }
+        }
+        EXPECT(best == lin, "kd-tree query %d: %u vs %u", q, best, lin);
+    }
+    std::printf("ok kd_tree\n");
+}
+
 int main()
 {
     try
     {
+        test_kd_tree();
         vren::context ctx(0);
         test_reduce(ctx);
         test_scan(ctx);

@@ -115,6 +115,9 @@ _LATE_SIGS = [
     ("vrenb200_visualize_bvh_vertex_count", C.c_uint64, (_u32,)),
     ("vrenb200_visualize_bvh", _i32, (_vp, _vp, _u32, _vp)),
     ("vrenb200_radix_partition_set_shape", _i32, (_i32,)),
+    ("vrenb200_kd_tree_build", _sz, (_vp, _sz, _vp, _sz, _vp, _sz)),
+    ("vrenb200_kd_tree_search", None, (_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp)),
+    ("vrenb200_kd_tree_search_batch", _i32, (_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp)),
     ("vrenb200_scan_set_variant", _i32, (_i32,)),
     ("vrenb200_scan_set_runahead", _i32, (_i32, _i32)),
     ("vrenb200_radix_sort_range_scratch_bytes", _sz, (_u32,)),
