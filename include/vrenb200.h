@@ -132,6 +132,7 @@ int vrenb200_radix_partition_scatter(vrenb200_stream_t stream, const uint32_t* k
 
 /* tuning / measurement hooks (not part of the reference surface) */
 int vrenb200_radix_sort_set_variant(int variant);
+int vrenb200_radix_sort_set_prefetch_tiles(uint32_t tiles);   /* PREFETCH_L2 variants: distance of the L2 prefetch, in tiles */
 int vrenb200_radix_partition_set_shape(int shape);   /* exchange pass tile: 0: 256x32, 1: 256x16, 2: 512x16 */
 int vrenb200_scan_set_variant(int variant);
 int vrenb200_scan_set_runahead(int finalize_lag_tiles, int scan_lag_tiles);   /* run-ahead scan kernel with explicit distances */   /* CTA size of the scan kernel: 0: 256, 1: 512, 2: 1024 threads */

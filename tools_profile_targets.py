@@ -1,5 +1,6 @@
 """launches each secondary kernel a few times so that ncu can capture them (scan, reduce, clustered chain, sort)"""
 import math
+import os
 import sys
 
 import numpy as np
@@ -13,11 +14,12 @@ lib = vlib.load()
 dev = torch.device("cuda")
 stream = torch.cuda.current_stream().cuda_stream
 n = 1 << 28
+ONLY = os.environ.get("VREN_PROFILE_ONLY", "")   # "sort": skip the scan and the clustered chain
 x = torch.ones(n, dtype=torch.int32, device=dev)
 y = torch.empty_like(x)
 sb = lib.vrenb200_scan_scratch_bytes(n)
 scr = torch.empty(sb, dtype=torch.uint8, device=dev)
-for _ in range(3):
+for _ in range(0 if ONLY == "sort" else 3):
     vlib.check(lib.vrenb200_exclusive_scan_u32(stream, x.data_ptr(), y.data_ptr(), n, scr.data_ptr(), sb), "scan")
 torch.cuda.synchronize()
 del x, y
@@ -28,13 +30,17 @@ pos, lights = torch.from_numpy(pos).to(dev), torch.from_numpy(lights).to(dev)
 view = synthetic.view_matrix(0.0, 0.0, (0, 0, 0)).tolist()
 cam = vlib.Camera(np.float32(math.radians(45.0)), np.float32(w / h), np.float32(0.01), np.float32(1000.0))
 cs = ClusterAndShade(w, h, max_point_lights=L)
-for _ in range(3):
+for _ in range(0 if ONLY == "sort" else 3):
     cs(w, h, cam, view, depth, None, pos, lights, L)
 torch.cuda.synchronize()
 g = torch.Generator(device=dev)
 g.manual_seed(1)
 keys = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
 vals = torch.arange(n, dtype=torch.int32, device=dev)
+if "VREN_SORT_VARIANT" in os.environ:
+    vlib.check(lib.vrenb200_radix_sort_set_variant(int(os.environ["VREN_SORT_VARIANT"])), "variant")
+if "VREN_PREFETCH_TILES" in os.environ:
+    vlib.check(lib.vrenb200_radix_sort_set_prefetch_tiles(int(os.environ["VREN_PREFETCH_TILES"])), "prefetch distance")
 for _ in range(2):
     vlib.radix_sort_pairs(keys, vals)
 torch.cuda.synchronize()

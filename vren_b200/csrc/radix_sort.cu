@@ -80,6 +80,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -301,6 +305,7 @@ struct onesweep_smem
     uint8_t rank_of[P2P ? kRadix : 4];    // P2P_DEST: destination rank of every most-significant byte
     uint32_t run_start[P2P ? kMaxRanks : 1], run_len[P2P ? kMaxRanks : 1], run_g[P2P ? kMaxRanks : 1];   // P2P_DEST: per-destination run of the tile
     uint32_t scan_warp[kRadix / 32];
+    uint32_t lane_dummy[WARPS][32];   // RANK_LEADER_ATOMIC: where the lanes that do not lead a match group add
     alignas(8) uint64_t bar_keys;
     alignas(8) uint64_t bar_vals;
     uint32_t tile;
@@ -310,7 +315,12 @@ enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 
        FAKE_LOOKBACK = 128 /* timing experiment: no chain, approximate destinations (WRONG results) */,
        DIRECT_LOAD = 256 /* count-first kernel: keys / values go from global memory straight to registers (no staging copy) */,
        LB_INTERLEAVED = 512 /* count-first kernel: the look-back advances in non-blocking steps between ranking rows */,
-       LB_STEP2 = 1024, LB_STEP8 = 2048 /* ... every 2 / every 8 rows instead of every 4 */ }; // option bits of the MATCH template argument
+       LB_STEP2 = 1024, LB_STEP8 = 2048 /* ... every 2 / every 8 rows instead of every 4 */,
+       PREFETCH_L2 = 4096 /* count-first kernel: a CTA asks L2 for the tile of the CTA that will take its place on the SM */,
+       RANK_LEADER_ATOMIC = 8192 /* count-first kernel: one returning shared atomic by the leader of every match group + shuffle,
+                                    instead of a counter load and store by every lane */,
+       EARLY_TMA = 32768 /* count-first kernel: the staging copies are issued before the counters are cleared */
+     }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
 // MATCH_BALLOT: hand-scheduled, 4 instructions per bit (bit test -> predicate, vote, two predicated LOP3);
@@ -722,6 +732,9 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     }
 }
 
+// PREFETCH_L2: how many tiles ahead a CTA prefetches (default: the CTAs resident at once at 2 per SM); tuning hook below
+__device__ uint32_t g_prefetch_tiles = kNumSMs * 2;
+
 // ---- 3a. count-first onesweep pass ------------------------------------------------------------------------------
 // Same contract as onesweep_pass_kernel, different order of work inside the tile:
 //   1. the warp-private digit counters are filled FIRST (one non-returning shared atomic per key),
@@ -753,20 +766,46 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t prmt_sel = 0x4440u | (uint32_t) pass;
     const uint32_t tile = blockIdx.x;
+    const uint64_t tile_base = (uint64_t) tile * TILE;
+    const uint32_t valid = (n - tile_base) < (uint64_t) TILE ? (uint32_t) (n - tile_base) : (uint32_t) TILE;
+    const bool full = valid == (uint32_t) TILE;
+    constexpr bool DIRECT = (MATCH & DIRECT_LOAD) != 0;
+    constexpr bool EARLY = (MATCH & EARLY_TMA) != 0 && !DIRECT;
     if (tid == 0)
     {
         mbar_init(&sm.bar_keys, 1);
         mbar_init(&sm.bar_vals, 1);
         mbar_fence_init();
+        if (EARLY && full)
+        {
+            // the copies start before the counters are cleared (the staging area is not touched by anyone else yet)
+            mbar_arrive_expect_tx(&sm.bar_keys, TILE * ELEM_BYTES);
+            bulk_copy_g2s(sm.kv, keys_in + tile_base * KSTRIDE, TILE * ELEM_BYTES, &sm.bar_keys);
+            if (LAYOUT == LAYOUT_SOA)
+            {
+                mbar_arrive_expect_tx(&sm.bar_vals, TILE * 4);
+                bulk_copy_g2s(sm.kv + TILE, vals_in + tile_base, TILE * 4, &sm.bar_vals);
+            }
+        }
     }
+    if ((MATCH & PREFETCH_L2) && tid == 32)
+    {
+        // the CTA that takes this one's place on the SM is about (resident CTAs) tiles ahead: have its input
+        // waiting in L2 by the time it starts
+        const uint64_t next_base = tile_base + (uint64_t) g_prefetch_tiles * TILE;
+        if (next_base + TILE <= (uint64_t) n)
+        {
+            bulk_prefetch_l2(keys_in + next_base * KSTRIDE, TILE * ELEM_BYTES);
+            if (LAYOUT == LAYOUT_SOA) bulk_prefetch_l2(vals_in + next_base, TILE * 4);
+        }
+    }
+    // global offset of this thread's digit: needed at the very end, fetched now
+    uint32_t pass_base = 0;
+    if ((MATCH & EARLY_TMA) && tid < kRadix) pass_base = ctl->hist[pass][tid];
 #pragma unroll
     for (int i = lane; i < kRadix; i += 32) sm.warp_hist[warp][i] = 0;
     __syncthreads();
 
-    const uint64_t tile_base = (uint64_t) tile * TILE;
-    const uint32_t valid = (n - tile_base) < (uint64_t) TILE ? (uint32_t) (n - tile_base) : (uint32_t) TILE;
-    const bool full = valid == (uint32_t) TILE;
-    constexpr bool DIRECT = (MATCH & DIRECT_LOAD) != 0;
     const uint32_t warp_off = warp * (ITEMS * 32) + lane;
     uint32_t* my_hist = sm.warp_hist[warp];
     uint32_t key[ITEMS];
@@ -805,7 +844,7 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
     {
         if (full)
         {
-            if (tid == 0)
+            if (!EARLY && tid == 0)
             {
                 mbar_arrive_expect_tx(&sm.bar_keys, TILE * ELEM_BYTES);
                 bulk_copy_g2s(sm.kv, keys_in + tile_base * KSTRIDE, TILE * ELEM_BYTES, &sm.bar_keys);
@@ -935,16 +974,57 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
 
     // 4. rank and regroup
     const unsigned lt = lanemask_lt();
+    // RANK_LEADER_ATOMIC: the highest lane of every match group adds the group's size to the run counter with ONE
+    // returning shared atomic (predicated, no branch) and the group reads the old value from it by shuffle; the atomic
+    // of row j+1 is issued before row j's result is consumed, so its latency hides behind a ranking.  Rows stay
+    // ordered: same warp, program order, __syncwarp() between the rows.
+    const uint32_t hist_addr = smem_u32(my_hist);
+    // (lanes that are not the leader add to a private dummy word instead: ptxas turns a predicated atom into a
+    // divergent branch, which costs more than the ~2 extra lanes per row)
+    const uint32_t dummy_addr = smem_u32(&sm.lane_dummy[warp][lane]);
+    auto leader_atomic = [&](uint32_t d, unsigned mask) {
+        uint32_t old;
+        const bool leader = lane == 31u - (uint32_t) __clz(mask);
+        asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+                     : "=r"(old) : "r"(leader ? hist_addr + d * 4u : dummy_addr), "r"((uint32_t) __popc(mask)) : "memory");
+        return old;
+    };
+    uint32_t d_nxt = 0, old_nxt = 0;
+    unsigned mask_nxt = 0;
+    if (MATCH & RANK_LEADER_ATOMIC)
+    {
+        d_nxt = digit_of(key[0], prmt_sel);
+        mask_nxt = match_digit<MATCH>(d_nxt);
+        old_nxt = leader_atomic(d_nxt, mask_nxt);
+    }
 #pragma unroll
     for (int j = 0; j < ITEMS; j++)
     {
-        const uint32_t d = digit_of(key[j], prmt_sel);
-        const unsigned mask = match_digit<MATCH>(d);
-        const uint32_t prior = my_hist[d];
-        const uint32_t r = prior + __popc(mask & lt);
-        __syncwarp();
-        my_hist[d] = prior + __popc(mask);
-        __syncwarp();
+        uint32_t r;
+        if (MATCH & RANK_LEADER_ATOMIC)
+        {
+            const unsigned mask = mask_nxt;
+            const uint32_t old = old_nxt;
+            if (j + 1 < ITEMS)
+            {
+                d_nxt = digit_of(key[j + 1], prmt_sel);
+                mask_nxt = match_digit<MATCH>(d_nxt);
+                __syncwarp();
+                old_nxt = leader_atomic(d_nxt, mask_nxt);
+            }
+            const uint32_t prior = __shfl_sync(kFullMask, old, 31 - __clz(mask));
+            r = prior + __popc(mask & lt);
+        }
+        else
+        {
+            const uint32_t d = digit_of(key[j], prmt_sel);
+            const unsigned mask = match_digit<MATCH>(d);
+            const uint32_t prior = my_hist[d];
+            r = prior + __popc(mask & lt);
+            __syncwarp();
+            my_hist[d] = prior + __popc(mask);
+            __syncwarp();
+        }
         if (HAS_VALUES)
             reinterpret_cast<uint2*>(sm.kv)[r] = make_uint2(key[j], val[j]);
         else
@@ -977,7 +1057,8 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
             }
             st_relaxed_u32(&lb[tid], kLbFlagInclusive | (exclusive + real_cnt));
         }
-        sm.digit_base[tid] = ctl->hist[pass][tid] + exclusive - tile_off;
+        if (!(MATCH & EARLY_TMA)) pass_base = ctl->hist[pass][tid];
+        sm.digit_base[tid] = pass_base + exclusive - tile_off;
     }
     __syncthreads();
 
@@ -1371,7 +1452,9 @@ int launch_count_first(cudaStream_t s, const uint32_t* kin, uint32_t* kout, cons
 #define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
 #define CVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B, (T) * (I), launch_count_first<T, I, M, B> }
 const sort_variant g_variants[] = {
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED, 2),  // 0: default (best of the sweeps in profiles/)
+    // 0: default (best of the sweeps in profiles/): 24 warps per SM, staging copies issued first, L2 prefetch for the
+    // successor CTA, leader-atomic ranking, interleaved look-back
+    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),
     VARIANT(256, 32, TILE_BY_BLOCKIDX | SPLIT_KV, 2),
     PVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // persistent CTAs + key prefetch, static tile striding
     PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent, tickets
@@ -1388,6 +1471,17 @@ const sort_variant g_variants[] = {
     CVARIANT(256, 24, TILE_BY_BLOCKIDX, 3),   // 14: default of r1m
     CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP2, 2),   // 15
     CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8, 2),   // 16
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | PREFETCH_L2, 2),   // 17
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | RANK_LEADER_ATOMIC, 2),   // 18
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | PREFETCH_L2 | EARLY_TMA, 2),   // 19
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA, 2),   // 20
+    CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2, 3),   // 21
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 22
+    CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 3),   // 23
+    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2, 2),   // 24
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED, 2),   // 25: default until r1w
+    CVARIANT(512, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 26
+    CVARIANT(320, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 27
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
@@ -1484,6 +1578,11 @@ extern "C" int vrenb200_radix_sort_set_variant(int v)
     g_variant = v;
     return VRENB200_OK;
 }
+extern "C" int vrenb200_radix_sort_set_prefetch_tiles(uint32_t tiles)
+{
+    return check_cuda(cudaMemcpyToSymbol(g_prefetch_tiles, &tiles, sizeof(tiles)));
+}
+
 extern "C" int vrenb200_radix_sort_num_variants(void) { return kNumVariants; }
 extern "C" const char* vrenb200_radix_sort_variant_name(int v)
 {

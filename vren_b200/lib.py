@@ -83,6 +83,7 @@ def load() -> C.CDLL:
     sig("vrenb200_radix_sort_host_work_bytes", sz, u32, i32)
     sig("vrenb200_radix_sort_pairs_host", i32, vp, vp, vp, u32, vp, sz)
     sig("vrenb200_radix_sort_set_variant", i32, i32)
+    sig("vrenb200_radix_sort_set_prefetch_tiles", i32, u32)
     sig("vrenb200_radix_sort_num_variants", i32)
     sig("vrenb200_radix_sort_variant_name", C.c_char_p, i32)
     sig("vrenb200_sort_profile_create", vp)
