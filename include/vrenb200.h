@@ -132,6 +132,7 @@ int vrenb200_radix_partition_scatter(vrenb200_stream_t stream, const uint32_t* k
 
 /* tuning / measurement hooks (not part of the reference surface) */
 int vrenb200_radix_sort_set_variant(int variant);
+int vrenb200_radix_sort_set_dephase(uint32_t ns, uint32_t rule);   /* DEPHASE variants: start delay of the second CTA of every SM (first wave only) */
 int vrenb200_radix_sort_set_prefetch_tiles(uint32_t tiles);   /* PREFETCH_L2 variants: distance of the L2 prefetch, in tiles */
 int vrenb200_radix_partition_set_shape(int shape);   /* exchange pass tile: 0: 256x32, 1: 256x16, 2: 512x16 */
 int vrenb200_scan_set_variant(int variant);
@@ -154,6 +155,9 @@ size_t vrenb200_bucket_sort_scratch_bytes(uint32_t n);
  * (bucket_sort.cpp:86, bucket_sort_write.comp:32). Ties keep input order (canonical choice). */
 int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pairs, uint32_t n, void* out,
                          void* scratch, size_t scratch_bytes);
+/* tuning hook: from n_min pairs on, the END offsets are found by a search in the sorted output instead of per-key
+ * global atomics (default 2^20; 0 = always search, 0xFFFFFFFF = never). Results are identical either way. */
+int vrenb200_bucket_sort_set_search_min(uint32_t n_min);
 
 /* ---- a5: 32-ary implicit BVH ------------------------------------------------------------------- */
 typedef struct vrenb200_bvh_node {   /* == vren::bvh_node (build_bvh.hpp:8-18), 32 bytes */

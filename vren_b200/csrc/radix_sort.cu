@@ -214,6 +214,63 @@ bucket_histogram_kernel(const uint2* __restrict__ pairs, uint32_t n, sort_contro
     }
 }
 
+// Large inputs: the two digit histograms only (shared atomics, no global ones).  The 65536 global atomics-per-key of the
+// kernel above cost more than both scatter passes together at 2^26 pairs (0.58 of 1.13 ms); the END offsets are then
+// read off the sorted output by bucket_end_offsets_search_kernel.  Two pairs per 128-bit load, two loads in flight.
+__global__ void __launch_bounds__(kHistThreads)
+bucket_digit_histogram_kernel(const uint2* __restrict__ pairs, uint32_t n, sort_control* ctl)
+{
+    __shared__ uint32_t s_hist[2][kRadix];
+    for (int i = threadIdx.x; i < 2 * kRadix; i += kHistThreads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t n2 = n / 2;
+    const uint4* pairs2 = reinterpret_cast<const uint4*>(pairs);
+    auto count = [&](uint32_t x) {
+        atomicAdd(&s_hist[0][x & 0xFF], 1u);
+        atomicAdd(&s_hist[1][(x >> 8) & 0xFF], 1u);
+    };
+    const uint32_t stride = gridDim.x * kHistThreads;
+    uint32_t i = blockIdx.x * kHistThreads + threadIdx.x;
+    for (; i + stride < n2; i += 2 * stride)
+    {
+        const uint4 a = ldg_stream_u4(pairs2 + i);
+        const uint4 b = ldg_stream_u4(pairs2 + i + stride);
+        count(a.x); count(a.z); count(b.x); count(b.z);
+    }
+    if (i < n2)
+    {
+        const uint4 a = ldg_stream_u4(pairs2 + i);
+        count(a.x); count(a.z);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) count(pairs[n - 1].x);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * kRadix; t += kHistThreads)
+    {
+        const uint32_t c = (&s_hist[0][0])[t];
+        if (c != 0) atomicAdd(&(&ctl->hist[0][0])[t], c);
+    }
+}
+
+// END offset of bucket b = number of pairs whose 16-bit key is <= b = upper bound of b in the SORTED output
+// (bucket_sort_write.comp:32 leaves exactly that behind; an empty bucket repeats its predecessor's END).  One thread per
+// bucket, log2(n) dependent reads each; the top levels of the search are shared by all threads and stay in L2.
+__global__ void __launch_bounds__(256)
+bucket_end_offsets_search_kernel(const uint2* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ counters)
+{
+    const uint32_t b = blockIdx.x * 256u + threadIdx.x;
+    uint32_t lo = 0, hi = n;    // first index whose key is > b lies in [lo, hi]
+    while (lo < hi)
+    {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const uint32_t key = __ldg(&sorted[mid].x) & (kBucketKeys - 1);
+        if (key <= b)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    counters[b] = lo;
+}
+
 // counts -> bucket END offsets (inclusive prefix): what bucket_sort_write.comp:32 leaves behind.  64 CTAs x 1024
 // counters: every CTA first sums the raw counts of the buckets before its slice (coalesced 128-bit reads, at most 252 KB
 // from L2), then scans its own 1024.  Out of place (raw counts live in the scratch), so CTAs never read what another one
@@ -308,6 +365,7 @@ struct onesweep_smem
     uint32_t lane_dummy[WARPS][32];   // RANK_LEADER_ATOMIC: where the lanes that do not lead a match group add
     alignas(8) uint64_t bar_keys;
     alignas(8) uint64_t bar_vals;
+    alignas(8) uint64_t bar_chunk[4];   // KEYS_CHUNKED: one barrier per quarter of the staged keys
     uint32_t tile;
 };
 
@@ -319,7 +377,14 @@ enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 
        PREFETCH_L2 = 4096 /* count-first kernel: a CTA asks L2 for the tile of the CTA that will take its place on the SM */,
        RANK_LEADER_ATOMIC = 8192 /* count-first kernel: one returning shared atomic by the leader of every match group + shuffle,
                                     instead of a counter load and store by every lane */,
-       EARLY_TMA = 32768 /* count-first kernel: the staging copies are issued before the counters are cleared */
+       EARLY_TMA = 32768 /* count-first kernel: the staging copies are issued before the counters are cleared */,
+       VALS_DIRECT = 65536 /* count-first kernel, SOA: the values go from global memory straight to registers (issued at the
+                              start of the tile, consumed by the regroup stores); only the keys are staged */,
+       REG_COUNTS = 131072 /* count-first kernel: the per-warp digit counts stay in registers between the publish and the
+                              offset step instead of being read from shared memory twice */,
+       VALS_LATE = 524288 /* VALS_DIRECT: the value loads are issued after the counting step instead of before the wait for the keys */,
+       KEYS_CHUNKED = 262144 /* count-first kernel: the key staging copy is split in four, every warp waits only for the
+                                quarter that holds its own keys */
      }; // option bits of the MATCH template argument
 
 // lanes of the warp holding the same 8-bit digit.
@@ -734,6 +799,10 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
 
 // PREFETCH_L2: how many tiles ahead a CTA prefetches (default: the CTAs resident at once at 2 per SM); tuning hook below
 __device__ uint32_t g_prefetch_tiles = kNumSMs * 2;
+// DEPHASE (count-first kernel): the CTAs of the first wave that arrive second on their SM start g_dephase_ns late, so that
+// the two CTAs of an SM do not run the same step (counting / ranking / write-out) at the same time.  The offset is
+// inherited by the CTAs that replace them.  rule 0: CTA i shares its SM with CTA i + 148; rule 1: with CTA i ^ 1.
+__device__ uint32_t g_dephase_ns = 5000, g_dephase_rule = 0;
 
 // ---- 3a. count-first onesweep pass ------------------------------------------------------------------------------
 // Same contract as onesweep_pass_kernel, different order of work inside the tile:
@@ -766,27 +835,55 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t prmt_sel = 0x4440u | (uint32_t) pass;
     const uint32_t tile = blockIdx.x;
+    if ((MATCH & DEPHASE) && tile < (uint32_t) (MIN_BLOCKS * kNumSMs))
+    {
+        const uint32_t slot = g_dephase_rule == 0 ? tile / (uint32_t) kNumSMs : tile % (uint32_t) MIN_BLOCKS;
+        if (slot) __nanosleep(slot * g_dephase_ns);
+    }
     const uint64_t tile_base = (uint64_t) tile * TILE;
     const uint32_t valid = (n - tile_base) < (uint64_t) TILE ? (uint32_t) (n - tile_base) : (uint32_t) TILE;
     const bool full = valid == (uint32_t) TILE;
     constexpr bool DIRECT = (MATCH & DIRECT_LOAD) != 0;
     constexpr bool EARLY = (MATCH & EARLY_TMA) != 0 && !DIRECT;
+    constexpr bool VDIRECT = (MATCH & VALS_DIRECT) != 0 && LAYOUT == LAYOUT_SOA && !DIRECT;
+    constexpr bool VLATE = (MATCH & VALS_LATE) != 0;
+    constexpr bool CHUNKED = (MATCH & KEYS_CHUNKED) != 0 && !DIRECT && WARPS % 4 == 0;
+    constexpr bool KEEP_COUNTS = (MATCH & REG_COUNTS) != 0;
+    // staging copies of a full tile (one thread): keys (whole or in quarters), then the values unless they are loaded directly
+    auto issue_copies = [&]() {
+        if (CHUNKED)
+        {
+            constexpr uint32_t Q = TILE / 4;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+            {
+                mbar_arrive_expect_tx(&sm.bar_chunk[c], Q * ELEM_BYTES);
+                bulk_copy_g2s(sm.kv + c * Q * KSTRIDE, keys_in + (tile_base + c * Q) * KSTRIDE, Q * ELEM_BYTES, &sm.bar_chunk[c]);
+            }
+        }
+        else
+        {
+            mbar_arrive_expect_tx(&sm.bar_keys, TILE * ELEM_BYTES);
+            bulk_copy_g2s(sm.kv, keys_in + tile_base * KSTRIDE, TILE * ELEM_BYTES, &sm.bar_keys);
+        }
+        if (LAYOUT == LAYOUT_SOA && !VDIRECT)
+        {
+            mbar_arrive_expect_tx(&sm.bar_vals, TILE * 4);
+            bulk_copy_g2s(sm.kv + TILE, vals_in + tile_base, TILE * 4, &sm.bar_vals);
+        }
+    };
     if (tid == 0)
     {
         mbar_init(&sm.bar_keys, 1);
         mbar_init(&sm.bar_vals, 1);
-        mbar_fence_init();
-        if (EARLY && full)
+        if (CHUNKED)
         {
-            // the copies start before the counters are cleared (the staging area is not touched by anyone else yet)
-            mbar_arrive_expect_tx(&sm.bar_keys, TILE * ELEM_BYTES);
-            bulk_copy_g2s(sm.kv, keys_in + tile_base * KSTRIDE, TILE * ELEM_BYTES, &sm.bar_keys);
-            if (LAYOUT == LAYOUT_SOA)
-            {
-                mbar_arrive_expect_tx(&sm.bar_vals, TILE * 4);
-                bulk_copy_g2s(sm.kv + TILE, vals_in + tile_base, TILE * 4, &sm.bar_vals);
-            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) mbar_init(&sm.bar_chunk[c], 1);
         }
+        mbar_fence_init();
+        // EARLY: the copies start before the counters are cleared (the staging area is not touched by anyone else yet)
+        if (EARLY && full) issue_copies();
     }
     if ((MATCH & PREFETCH_L2) && tid == 32)
     {
@@ -810,6 +907,15 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
     uint32_t* my_hist = sm.warp_hist[warp];
     uint32_t key[ITEMS];
     uint32_t val[HAS_VALUES ? ITEMS : 1];
+    // VALS_DIRECT: warp-striped value loads into the register tile (no staging copy, no shared load)
+    auto load_vals_direct = [&]() {
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++)
+        {
+            const uint32_t i = warp_off + j * 32;
+            val[j] = full ? ldg_stream_u32(vals_in + tile_base + i) : (i < valid ? vals_in[tile_base + i] : 0u);
+        }
+    };
     if (DIRECT)
     {
         // warp-striped loads straight into the register tile: one L1 wavefront per 32 keys instead of a staging write
@@ -844,17 +950,9 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
     {
         if (full)
         {
-            if (!EARLY && tid == 0)
-            {
-                mbar_arrive_expect_tx(&sm.bar_keys, TILE * ELEM_BYTES);
-                bulk_copy_g2s(sm.kv, keys_in + tile_base * KSTRIDE, TILE * ELEM_BYTES, &sm.bar_keys);
-                if (LAYOUT == LAYOUT_SOA)
-                {
-                    mbar_arrive_expect_tx(&sm.bar_vals, TILE * 4);
-                    bulk_copy_g2s(sm.kv + TILE, vals_in + tile_base, TILE * 4, &sm.bar_vals);
-                }
-            }
-            mbar_wait(&sm.bar_keys, 0);
+            if (!EARLY && tid == 0) issue_copies();
+            if (VDIRECT && !VLATE) load_vals_direct();   // before the wait for the keys
+            mbar_wait(CHUNKED ? &sm.bar_chunk[warp / (WARPS / 4)] : &sm.bar_keys, 0);
         }
         else
         {
@@ -862,9 +960,10 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
             {
                 const bool in = i < valid;
                 sm.kv[i * KSTRIDE] = in ? keys_in[(tile_base + i) * KSTRIDE] : 0xFFFFFFFFu;
-                if (LAYOUT == LAYOUT_SOA) sm.kv[TILE + i] = in ? vals_in[tile_base + i] : 0u;
+                if (LAYOUT == LAYOUT_SOA && !VDIRECT) sm.kv[TILE + i] = in ? vals_in[tile_base + i] : 0u;
                 if (LAYOUT == LAYOUT_AOS) sm.kv[i * 2 + 1] = in ? keys_in[(tile_base + i) * 2 + 1] : 0u;
             }
+            if (VDIRECT && !VLATE) load_vals_direct();
             __syncthreads();
         }
 #pragma unroll
@@ -874,11 +973,13 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) atomicAdd(&my_hist[digit_of(key[j], prmt_sel)], 1u);
     __syncthreads();
+    if (VDIRECT && VLATE) load_vals_direct();   // the loads complete under the publish and offset steps
 
     // 2. publish the aggregate, start the look-back
     constexpr int K = 4;
     uint32_t* lb = lookback + ((size_t) pass * num_tiles + tile) * kRadix;
     uint32_t cnt = 0, inc = 0, real_cnt = 0, lb_pre[K];
+    uint32_t cw[KEEP_COUNTS ? WARPS : 1];   // REG_COUNTS: this thread's digit, count per warp
     // look-back state of this thread's digit: window of K predecessors starting at tile lb_t, words in lb_pre[]
     constexpr bool INTERLEAVED = (MATCH & LB_INTERLEAVED) != 0;
     const uint32_t* lb_p = lb - kRadix + tid;
@@ -922,7 +1023,12 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
     if (tid < kRadix)
     {
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) cnt += sm.warp_hist[w][tid];
+        for (int w = 0; w < WARPS; w++)
+        {
+            const uint32_t c = sm.warp_hist[w][tid];
+            if (KEEP_COUNTS) cw[w] = c;
+            cnt += c;
+        }
         real_cnt = cnt - ((tid == kRadix - 1) ? (uint32_t) TILE - valid : 0u);
         st_relaxed_u32(&lb[tid], (tile == 0 ? kLbFlagInclusive : kLbFlagAggregate) | real_cnt);
         lb_load();
@@ -949,12 +1055,12 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
 #pragma unroll
         for (int w = 0; w < WARPS; w++)
         {
-            const uint32_t c = sm.warp_hist[w][tid];
+            const uint32_t c = KEEP_COUNTS ? cw[w] : sm.warp_hist[w][tid];
             sm.warp_hist[w][tid] = run;
             run += c;
         }
     }
-    if (HAS_VALUES && !DIRECT)
+    if (HAS_VALUES && !DIRECT && !VDIRECT)
     {
         if (LAYOUT == LAYOUT_SOA && full) mbar_wait(&sm.bar_vals, 0);
 #pragma unroll
@@ -1482,12 +1588,21 @@ const sort_variant g_variants[] = {
     CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED, 2),   // 25: default until r1w
     CVARIANT(512, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 26
     CVARIANT(320, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 27
+    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT, 2),   // 28
+    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | REG_COUNTS, 2),   // 29
+    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | KEYS_CHUNKED, 2),   // 30
+    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT | KEYS_CHUNKED, 2),   // 31
+    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT | KEYS_CHUNKED | REG_COUNTS, 2),   // 32
+    CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT | KEYS_CHUNKED, 3),   // 33
+    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | DEPHASE, 2),   // 34
+    CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | DEPHASE, 3),   // 35
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
 constexpr uint32_t kMinTile = 256 * 16;
 
 int g_variant = 0;
+uint32_t g_bucket_search_min = 1u << 20;   // bucket sort: from this many pairs on, END offsets come from a search in the sorted output
 int g_partition_shape = 0;   // 0: 256x32 (2 CTAs/SM), 1: 256x16 (4 CTAs/SM), 2: 512x16 (2 CTAs/SM)
 
 size_t lookback_words(uint32_t n)
@@ -1578,6 +1693,12 @@ extern "C" int vrenb200_radix_sort_set_variant(int v)
     g_variant = v;
     return VRENB200_OK;
 }
+extern "C" int vrenb200_radix_sort_set_dephase(uint32_t ns, uint32_t rule)
+{
+    VRENB200_TRY(check_cuda(cudaMemcpyToSymbol(g_dephase_ns, &ns, sizeof(ns))));
+    return check_cuda(cudaMemcpyToSymbol(g_dephase_rule, &rule, sizeof(rule)));
+}
+
 extern "C" int vrenb200_radix_sort_set_prefetch_tiles(uint32_t tiles)
 {
     return check_cuda(cudaMemcpyToSymbol(g_prefetch_tiles, &tiles, sizeof(tiles)));
@@ -1845,14 +1966,29 @@ extern "C" int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pai
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
     const size_t clear = sizeof(sort_control) + (size_t) 2 * tiles * kRadix * sizeof(uint32_t);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(ctl_mem, 0, clear, s)));
-    VRENB200_TRY(check_cuda(cudaMemsetAsync(raw_counts, 0, kBucketKeys * sizeof(uint32_t), s)));
-    const uint32_t hist_grid = (uint32_t) std::min<size_t>(kNumSMs * 2, ((size_t) n / 2 + kHistThreads - 1) / kHistThreads + 1);
-    bucket_histogram_kernel<<<hist_grid, kHistThreads, 0, s>>>(static_cast<const uint2*>(in_pairs), n, ctl, raw_counts);
+    // small inputs (the light Morton sort of the clustered chain): bucket counts by global atomics in the histogram read,
+    // prefix by bucket_end_offsets_kernel; large inputs: no global atomics, END offsets by search in the sorted output
+    const bool by_search = n >= g_bucket_search_min;
+    if (!by_search) VRENB200_TRY(check_cuda(cudaMemsetAsync(raw_counts, 0, kBucketKeys * sizeof(uint32_t), s)));
+    const uint32_t hist_grid = (uint32_t) std::min<size_t>(kNumSMs * (by_search ? 4 : 2), ((size_t) n / 2 + kHistThreads - 1) / kHistThreads + 1);
+    if (by_search)
+        bucket_digit_histogram_kernel<<<hist_grid, kHistThreads, 0, s>>>(static_cast<const uint2*>(in_pairs), n, ctl);
+    else
+        bucket_histogram_kernel<<<hist_grid, kHistThreads, 0, s>>>(static_cast<const uint2*>(in_pairs), n, ctl, raw_counts);
     VRENB200_TRY(check_launch());
     radix_scan_histograms_kernel<<<2, kRadix, 0, s>>>(ctl);
     VRENB200_TRY(check_launch());
     VRENB200_TRY(var.launch(s, static_cast<const uint32_t*>(in_pairs), tmp, nullptr, nullptr, n, 0, ctl, lookback, tiles, LAYOUT_AOS));
     VRENB200_TRY(var.launch(s, tmp, static_cast<uint32_t*>(out), nullptr, nullptr, n, 1, ctl, lookback, tiles, LAYOUT_AOS));
-    bucket_end_offsets_kernel<<<kEndOffsetCtas, 1024, 0, s>>>(raw_counts, counters);
+    if (by_search)
+        bucket_end_offsets_search_kernel<<<kBucketKeys / 256, 256, 0, s>>>(static_cast<const uint2*>(out), n, counters);
+    else
+        bucket_end_offsets_kernel<<<kEndOffsetCtas, 1024, 0, s>>>(raw_counts, counters);
     return check_launch();
+}
+
+extern "C" int vrenb200_bucket_sort_set_search_min(uint32_t n_min)
+{
+    g_bucket_search_min = n_min;
+    return VRENB200_OK;
 }

@@ -84,6 +84,7 @@ def load() -> C.CDLL:
     sig("vrenb200_radix_sort_pairs_host", i32, vp, vp, vp, u32, vp, sz)
     sig("vrenb200_radix_sort_set_variant", i32, i32)
     sig("vrenb200_radix_sort_set_prefetch_tiles", i32, u32)
+    sig("vrenb200_radix_sort_set_dephase", i32, u32, u32)
     sig("vrenb200_radix_sort_num_variants", i32)
     sig("vrenb200_radix_sort_variant_name", C.c_char_p, i32)
     sig("vrenb200_sort_profile_create", vp)
@@ -126,6 +127,7 @@ _LATE_SIGS = [
     ("vrenb200_bucket_sort_output_bytes", _sz, (_u32,)),
     ("vrenb200_bucket_sort_scratch_bytes", _sz, (_u32,)),
     ("vrenb200_bucket_sort", _i32, (_vp, _vp, _u32, _vp, _vp, _sz)),
+    ("vrenb200_bucket_sort_set_search_min", _i32, (_u32,)),
     ("vrenb200_calc_bvh_padded_leaf_count", _u32, (_u32,)),
     ("vrenb200_calc_bvh_buffer_length", _u32, (_u32,)),
     ("vrenb200_calc_bvh_buffer_size", _sz, (_u32,)),
