@@ -58,7 +58,7 @@ if os.environ.get("VREN_SWEEP_DISTANCES"):
         vlib.check(lib.vrenb200_radix_sort_set_prefetch_tiles(dist), "prefetch distance")
         ok, med, mn = run(1 << 28, 0, 7)
         print(json.dumps({"variant": 0, "prefetch_tiles": dist, "ok_2p28": ok, "sort_ms_median": round(med, 4), "sort_ms_min": round(mn, 4)}), flush=True)
-vlib.check(lib.vrenb200_radix_sort_set_prefetch_tiles(int(os.environ.get("VREN_PREFETCH_TILES", "296"))), "prefetch distance")
+vlib.check(lib.vrenb200_radix_sort_set_prefetch_tiles(int(os.environ.get("VREN_PREFETCH_TILES", "148"))), "prefetch distance")
 
 # variants interleaved round-robin on the same buffers, so that clock / thermal drift hits all of them alike
 n = 1 << 28

@@ -797,8 +797,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     }
 }
 
-// PREFETCH_L2: how many tiles ahead a CTA prefetches (default: the CTAs resident at once at 2 per SM); tuning hook below
-__device__ uint32_t g_prefetch_tiles = kNumSMs * 2;
+// PREFETCH_L2: how many tiles ahead a CTA prefetches (half of the CTAs resident at 2 per SM); tuning hook below
+__device__ uint32_t g_prefetch_tiles = kNumSMs;   // 74-148 tiles ahead measured best for the default tile (profiles/r1x_prefetch_distance.log)
 // DEPHASE (count-first kernel): the CTAs of the first wave that arrive second on their SM start g_dephase_ns late, so that
 // the two CTAs of an SM do not run the same step (counting / ranking / write-out) at the same time.  The offset is
 // inherited by the CTAs that replace them.  rule 0: CTA i shares its SM with CTA i + 148; rule 1: with CTA i ^ 1.
@@ -1558,9 +1558,10 @@ int launch_count_first(cudaStream_t s, const uint32_t* kin, uint32_t* kout, cons
 #define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
 #define CVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B, (T) * (I), launch_count_first<T, I, M, B> }
 const sort_variant g_variants[] = {
-    // 0: default (best of the sweeps in profiles/): 24 warps per SM, staging copies issued first, L2 prefetch for the
-    // successor CTA, leader-atomic ranking, interleaved look-back
-    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),
+    // 0: default (best of the sweeps in profiles/): 11776-pair tiles (256 threads x 46 rows, 2 CTAs = 16 warps per SM, 128
+    // registers per thread: the per-tile steps are amortised over more pairs), staging copies issued first, L2 prefetch for
+    // the successor CTA, leader-atomic ranking, interleaved look-back
+    CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),
     VARIANT(256, 32, TILE_BY_BLOCKIDX | SPLIT_KV, 2),
     PVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // persistent CTAs + key prefetch, static tile striding
     PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent, tickets
@@ -1596,12 +1597,35 @@ const sort_variant g_variants[] = {
     CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT | KEYS_CHUNKED, 3),   // 33
     CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | DEPHASE, 2),   // 34
     CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | DEPHASE, 3),   // 35
+    CVARIANT(256, 36, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 36: 16 warps/SM, more rows per thread
+    CVARIANT(256, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 37
+    CVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 38
+    CVARIANT(320, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 39
+    CVARIANT(512, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 1),   // 40: one CTA per SM, 20480-pair tiles
+    CVARIANT(512, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 1),   // 41
+    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 42: default of r1w
+    CVARIANT(288, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 43
+    CVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | LB_STEP8, 2),   // 44
+    CVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2, 2),   // 45: without the leader atomic
+    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 46: the largest tile two CTAs fit
+    CVARIANT(256, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | RANK_LEADER_ATOMIC, 3),   // 47: 4096-pair tiles for mid-size inputs
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
 constexpr uint32_t kMinTile = 256 * 16;
 
 int g_variant = 0;
+// Variant 0 means "automatic": inputs below 2^20 pairs take the 4096-pair tile (more CTAs than SMs from 2^19 on, and the
+// per-tile steps are shorter: 44 vs 63 us at 2^16 pairs, equal at 2^20, profiles/r1x_sort_size_variants.log)
+constexpr int kSmallTileVariant = 47;
+constexpr uint32_t kSmallTileBelow = 1u << 20;
+static_assert(kNumVariants > kSmallTileVariant, "variant table changed");
+
+const sort_variant& pick_variant(uint32_t n)
+{
+    if (g_variant == 0 && n < kSmallTileBelow) return g_variants[kSmallTileVariant];
+    return g_variants[g_variant];
+}
 uint32_t g_bucket_search_min = 1u << 20;   // bucket sort: from this many pairs on, END offsets come from a search in the sorted output
 int g_partition_shape = 0;   // 0: 256x32 (2 CTAs/SM), 1: 256x16 (4 CTAs/SM), 2: 512x16 (2 CTAs/SM)
 
@@ -1656,7 +1680,7 @@ int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, 
          reinterpret_cast<uintptr_t>(ctl_mem)) & 15)
         return VRENB200_EALIGN;
     const int layout = vals != nullptr ? LAYOUT_SOA : LAYOUT_KEYS;
-    const sort_variant& var = g_variants[g_variant];
+    const sort_variant& var = pick_variant(n);
     const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
     sort_control* ctl = static_cast<sort_control*>(ctl_mem);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
@@ -1960,7 +1984,7 @@ extern "C" int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pai
     uint32_t* tmp = reinterpret_cast<uint32_t*>(p);
     void* ctl_mem = p + align_up((size_t) n * 8, 256);
     uint32_t* raw_counts = reinterpret_cast<uint32_t*>(p + align_up((size_t) n * 8, 256) + control_bytes(n));
-    const sort_variant& var = g_variants[g_variant];
+    const sort_variant& var = pick_variant(n);
     const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
     sort_control* ctl = static_cast<sort_control*>(ctl_mem);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
