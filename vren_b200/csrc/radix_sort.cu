@@ -382,6 +382,7 @@ enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 
                               start of the tile, consumed by the regroup stores); only the keys are staged */,
        REG_COUNTS = 131072 /* count-first kernel: the per-warp digit counts stay in registers between the publish and the
                               offset step instead of being read from shared memory twice */,
+       MATCH_SPLIT4 = 1048576 /* ballot match with four accumulators (shorter dependent chains) */,
        VALS_LATE = 524288 /* VALS_DIRECT: the value loads are issued after the counting step instead of before the wait for the keys */,
        KEYS_CHUNKED = 262144 /* count-first kernel: the key staging copy is split in four, every warp waits only for the
                                 quarter that holds its own keys */
@@ -394,7 +395,32 @@ template <int MATCH>
 __device__ __forceinline__ unsigned match_digit(uint32_t d)
 {
     unsigned mask = kFullMask;
-    if ((MATCH & MATCH_BALLOT_C) == 0)
+    if (MATCH & MATCH_SPLIT4)
+    {
+        // four accumulators (bits 0-3 and 4-7 apart): dependent chains of 4 instead of 8, one more instruction per key
+        unsigned ones_lo = kFullMask, zeros_lo = 0u, ones_hi = kFullMask, zeros_hi = 0u;
+#pragma unroll
+        for (int b = 0; b < kRadixBits / 2; b++)
+        {
+            asm("{\n"
+                ".reg .pred p, q;\n"
+                ".reg .b32 t, u, bal, bal2;\n"
+                "and.b32 t, %4, %5;\n"
+                "setp.ne.u32 p, t, 0;\n"
+                "and.b32 u, %4, %6;\n"
+                "setp.ne.u32 q, u, 0;\n"
+                "vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+                "vote.sync.ballot.b32 bal2, q, 0xffffffff;\n"
+                "@p and.b32 %0, %0, bal;\n"
+                "@!p or.b32 %1, %1, bal;\n"
+                "@q and.b32 %2, %2, bal2;\n"
+                "@!q or.b32 %3, %3, bal2;\n"
+                "}\n"
+                : "+r"(ones_lo), "+r"(zeros_lo), "+r"(ones_hi), "+r"(zeros_hi) : "r"(d), "r"(1u << b), "r"(16u << b));
+        }
+        mask = (ones_lo & ones_hi) & ~(zeros_lo | zeros_hi);
+    }
+    else if ((MATCH & MATCH_BALLOT_C) == 0)
     {
         // peers = AND of the ballots of my set bits, minus OR of the ballots of my clear bits: two independent
         // accumulators, each updated by ONE predicated LOP3 per bit (vote + 2 instructions per bit)
@@ -1609,6 +1635,8 @@ const sort_variant g_variants[] = {
     CVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2, 2),   // 45: without the leader atomic
     CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 46: the largest tile two CTAs fit
     CVARIANT(256, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | RANK_LEADER_ATOMIC, 3),   // 47: 4096-pair tiles for mid-size inputs
+    CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | MATCH_SPLIT4, 2),   // 48
+    CVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | MATCH_SPLIT4, 2),   // 49
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
