@@ -22,7 +22,9 @@ for n, off in ((1000, 0), (70001, 1), ((1 << 22) + 16384 * 3 + 5, 0), ((1 << 22)
 # sort: pairs, keys, every non-experimental variant at a ragged size
 n = 3 * 8192 + 1234
 k = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
-for var in range(lib.vrenb200_radix_sort_num_variants()):
+import os  # noqa: E402
+only = [int(a) for a in os.environ.get("VREN_SANITIZER_VARIANTS", "").split(",") if a]
+for var in only or range(lib.vrenb200_radix_sort_num_variants()):
     if b"FAKE" in lib.vrenb200_radix_sort_variant_name(var):
         continue
     vlib.check(lib.vrenb200_radix_sort_set_variant(var), "variant")
@@ -35,7 +37,23 @@ for var in range(lib.vrenb200_radix_sort_num_variants()):
     u = kk.to(torch.int64) & 0xFFFFFFFF
     assert bool((u[1:] >= u[:-1]).all()), ("keys", var)
 vlib.check(lib.vrenb200_radix_sort_set_variant(0), "variant")
-# bucket sort
+# variant 0 takes the small tile below 2^20 pairs: exercise the default 256x46 tile too (ragged last tile)
+n = (1 << 20) + 12345
+k = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+kk, vv = k.clone(), torch.arange(n, dtype=torch.int32, device=dev)
+vlib.radix_sort_pairs(kk, vv)
+u = kk.to(torch.int64) & 0xFFFFFFFF
+assert bool((u[1:] >= u[:-1]).all()) and torch.equal(k[vv.long()], kk), "pairs, default tile"
+kk = k.clone()
+vlib.radix_sort_keys(kk)
+u = kk.to(torch.int64) & 0xFFFFFFFF
+assert bool((u[1:] >= u[:-1]).all()), "keys, default tile"
+# bucket sort: END offsets by search in the sorted output (the path of inputs >= 2^20 pairs), then by counting
+vlib.check(lib.vrenb200_bucket_sort_set_search_min(0), "search_min")
+pairs = torch.randint(0, 1 << 16, (50001, 2), dtype=torch.int32, device=dev, generator=g)
+_, sorted_pairs, counters = vlib.bucket_sort(pairs)
+assert int(counters[-1]) == 50001
+vlib.check(lib.vrenb200_bucket_sort_set_search_min(1 << 20), "search_min")
 pairs = torch.randint(0, 1 << 16, (50001, 2), dtype=torch.int32, device=dev, generator=g)
 _, sorted_pairs, counters = vlib.bucket_sort(pairs)
 keys16 = sorted_pairs[:, 0] & 0xFFFF
