@@ -1637,6 +1637,12 @@ const sort_variant g_variants[] = {
     CVARIANT(256, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | RANK_LEADER_ATOMIC, 3),   // 47: 4096-pair tiles for mid-size inputs
     CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | MATCH_SPLIT4, 2),   // 48
     CVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | MATCH_SPLIT4, 2),   // 49
+    CVARIANT(256, 72, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 50: keys-only tiles (4 B/key of shared memory)
+    CVARIANT(256, 80, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 51
+    CVARIANT(256, 88, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 52
+    CVARIANT(384, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 53: keys only, 24 warps/SM
+    CVARIANT(256, 56, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 54
+    CVARIANT(256, 64, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 55
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
@@ -1649,9 +1655,15 @@ constexpr int kSmallTileVariant = 47;
 constexpr uint32_t kSmallTileBelow = 1u << 20;
 static_assert(kNumVariants > kSmallTileVariant, "variant table changed");
 
-const sort_variant& pick_variant(uint32_t n)
+// Keys-only sorts stage 4 B per key, so 64 rows per thread fit the same shared memory and registers (16 384-key tiles):
+// 76.2 vs 73.2 Gkeys/s at 2^28 keys (profiles/r1x_sort_keys_sweep.log)
+constexpr int kKeysOnlyVariant = 55;
+static_assert(kNumVariants > kKeysOnlyVariant, "variant table changed");
+
+const sort_variant& pick_variant(uint32_t n, int layout)
 {
     if (g_variant == 0 && n < kSmallTileBelow) return g_variants[kSmallTileVariant];
+    if (g_variant == 0 && layout == LAYOUT_KEYS) return g_variants[kKeysOnlyVariant];
     return g_variants[g_variant];
 }
 uint32_t g_bucket_search_min = 1u << 20;   // bucket sort: from this many pairs on, END offsets come from a search in the sorted output
@@ -1708,7 +1720,7 @@ int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, 
          reinterpret_cast<uintptr_t>(ctl_mem)) & 15)
         return VRENB200_EALIGN;
     const int layout = vals != nullptr ? LAYOUT_SOA : LAYOUT_KEYS;
-    const sort_variant& var = pick_variant(n);
+    const sort_variant& var = pick_variant(n, layout);
     const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
     sort_control* ctl = static_cast<sort_control*>(ctl_mem);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
@@ -2012,7 +2024,7 @@ extern "C" int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pai
     uint32_t* tmp = reinterpret_cast<uint32_t*>(p);
     void* ctl_mem = p + align_up((size_t) n * 8, 256);
     uint32_t* raw_counts = reinterpret_cast<uint32_t*>(p + align_up((size_t) n * 8, 256) + control_bytes(n));
-    const sort_variant& var = pick_variant(n);
+    const sort_variant& var = pick_variant(n, LAYOUT_AOS);
     const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
     sort_control* ctl = static_cast<sort_control*>(ctl_mem);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
