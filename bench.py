@@ -469,7 +469,8 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         pass_avg_ms = sum(pass_ms) / len(pass_ms)
-        variant_name = lib.vrenb200_radix_sort_variant_name(args.variant or 0).decode()
+        variant_name = (lib.vrenb200_radix_sort_variant_name(args.variant) if args.variant else
+                        lib.vrenb200_radix_sort_selected_variant_name(n, 1)).decode()
         pass_kernel = "onesweep_count_first_kernel" if "count-first" in variant_name else "onesweep_pass_kernel"
         achieved = BYTES_PER_PAIR_PASS * n / (pass_avg_ms * 1e-3) / 1e9
         cpu = None
@@ -483,7 +484,8 @@ def run_ours(args):
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"radix sort of 2^{args.log2n} uint32 key-value pairs per GPU (uniform keys, value=index)",
                        "l2": "inputs larger than L2 (2 GiB restored between steps)",
-                       "variant": lib.vrenb200_radix_sort_variant_name(args.variant or 0).decode(),
+                       "variant": variant_name,
+                       "ranking_probe": "ascending lane order" if lib.vrenb200_radix_sort_ranking_probe() else "not ascending: ballot match",
                        "parallelism": "1 GPU" if world == 1 else
                        f"one global sort of {world}x2^{args.log2n} pairs: top-digit split + " +
                        ("partition kernel storing into peer receive buffers over NVLink" if (world > 1 and exchange is not None)

@@ -132,6 +132,14 @@ int vrenb200_radix_partition_scatter(vrenb200_stream_t stream, const uint32_t* k
 
 /* tuning / measurement hooks (not part of the reference surface) */
 int vrenb200_radix_sort_set_variant(int variant);
+/* Ranking step of the default pass kernels. 0 (default): automatic — the first sort on a device runs a one-time probe
+ * (~0.2 ms, own stream; skipped while the caller's stream is being captured) of how the device orders the lanes of one
+ * shared-memory atomic that hit the same address, and uses the match-free "atomic order" kernels only if the order is
+ * ascending by lane (it is on B200); 1: always the ballot-match kernels (order by construction); 2: always atomic order.
+ * Environment: VRENB200_SORT_RANKING=auto|match|atomic. Results are identical in every mode the probe accepts. */
+int vrenb200_radix_sort_set_ranking(int mode);
+int vrenb200_radix_sort_ranking_probe(void);   /* 1: ascending lane order on the current device, 0: not */
+const char* vrenb200_radix_sort_selected_variant_name(uint32_t n, int with_values);
 int vrenb200_radix_sort_set_dephase(uint32_t ns, uint32_t rule);   /* DEPHASE variants: start delay of the second CTA of every SM (first wave only) */
 int vrenb200_radix_sort_set_prefetch_tiles(uint32_t tiles);   /* PREFETCH_L2 variants: distance of the L2 prefetch, in tiles */
 int vrenb200_radix_partition_set_shape(int shape);   /* exchange pass tile: 0: 256x32, 1: 256x16, 2: 512x16 */

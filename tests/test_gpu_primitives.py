@@ -217,6 +217,46 @@ def test_radix_pairs_stable(vren, n):
     assert np.array_equal(host_u32(gk), wk) and np.array_equal(host_u32(gv), wv)
 
 
+def test_radix_ranking_probe_passes_on_this_device(vren):
+    """the match-free ranking is only used where same-address lanes of a shared atomic are served in ascending lane
+    order; the one-time probe must say so on B200 (else the library falls back to the ballot match and this test tells)"""
+    lib = vren.load()
+    assert lib.vrenb200_radix_sort_ranking_probe() == 1
+    assert b"RANK_ATOMIC_ORDER" in lib.vrenb200_radix_sort_selected_variant_name(1 << 24, 1)
+    assert b"RANK_ATOMIC_ORDER" in lib.vrenb200_radix_sort_selected_variant_name(1 << 24, 0)
+    assert b"RANK_ATOMIC_ORDER" in lib.vrenb200_radix_sort_selected_variant_name(1000, 1)
+
+
+@pytest.mark.parametrize("mode", [1, 2])   # 1: ballot match, 2: atomic order
+@pytest.mark.parametrize("pattern", ["equal", "two_values", "mod100", "low_byte_only", "uniform"])
+@pytest.mark.parametrize("n", [33, 4097, 100003, (1 << 20) + 77, (1 << 22) + 12345])
+def test_radix_pairs_both_rankings_collision_heavy(vren, mode, pattern, n):
+    """every lane-collision pattern of the ranking step (32 lanes on one counter ... all different), both ranking
+    modes, keys and values bit-exact against the stable oracle"""
+    lib = vren.load()
+    if pattern == "equal":
+        k = np.full(n, 0x12345678, np.uint32)
+    elif pattern == "two_values":
+        k = np.where(rand_u32(51, n) & np.uint32(1), np.uint32(0x01010101), np.uint32(0x02020202)).astype(np.uint32)
+    elif pattern == "mod100":
+        k = (rand_u32(52, n) % np.uint32(100)).astype(np.uint32)
+    elif pattern == "low_byte_only":
+        k = (rand_u32(53, n) & np.uint32(0x7)).astype(np.uint32) * np.uint32(0x01010101)
+    else:
+        k = rand_u32(54, n)
+    v = np.arange(n, dtype=np.uint32)
+    wk, wv = oracle.sort_pairs(k, v)
+    assert lib.vrenb200_radix_sort_set_ranking(mode) == 0
+    try:
+        want_name = b"RANK_ATOMIC_ORDER" if mode == 2 else b"RANK_LEADER_ATOMIC"
+        assert want_name in lib.vrenb200_radix_sort_selected_variant_name(n, 1)
+        gk, gv = vren.radix_sort_pairs(dev_u32(k), dev_u32(v))
+        assert np.array_equal(host_u32(gk), wk) and np.array_equal(host_u32(gv), wv)
+        assert np.array_equal(host_u32(vren.radix_sort_keys(dev_u32(k))), wk)
+    finally:
+        lib.vrenb200_radix_sort_set_ranking(0)
+
+
 def test_radix_all_variants_agree(vren):
     lib = vren.load()
     n = (1 << 18) + 333

@@ -18,6 +18,9 @@
 // deterministic and stable (the canonical tie-break), bucket END offsets from a fused 65536-bin count.
 // Stability: warp-striped order (warp, item, lane) == element order, so equal keys keep input order.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -382,6 +385,9 @@ enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 
                               start of the tile, consumed by the regroup stores); only the keys are staged */,
        REG_COUNTS = 131072 /* count-first kernel: the per-warp digit counts stay in registers between the publish and the
                               offset step instead of being read from shared memory twice */,
+       RANK_ATOMIC_ORDER = 2097152 /* EXPERIMENT: rank = returning shared atomic per lane, no match (relies on unspecified
+                                      ordering of same-address lanes; see the kernel) */,
+       LB_STEP16 = 4194304 /* look-back step every 16 ranking rows */,
        MATCH_SPLIT4 = 1048576 /* ballot match with four accumulators (shorter dependent chains) */,
        VALS_LATE = 524288 /* VALS_DIRECT: the value loads are issued after the counting step instead of before the wait for the keys */,
        KEYS_CHUNKED = 262144 /* count-first kernel: the key staging copy is split in four, every warp waits only for the
@@ -1133,7 +1139,15 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
     for (int j = 0; j < ITEMS; j++)
     {
         uint32_t r;
-        if (MATCH & RANK_LEADER_ATOMIC)
+        if (MATCH & RANK_ATOMIC_ORDER)
+        {
+            // EXPERIMENT (not selectable as a default): no match at all, every lane takes its slot with a returning shared
+            // atomic.  Stable only if the hardware serialises the lanes of ONE instruction that hit the same address in
+            // ascending lane order, which PTX leaves unspecified; the sweep tool's stability check tells.
+            r = atomicAdd(&my_hist[digit_of(key[j], prmt_sel)], 1u);
+            __syncwarp();   // row j's adds are performed before row j+1's (different lanes may hit the same counter)
+        }
+        else if (MATCH & RANK_LEADER_ATOMIC)
         {
             const unsigned mask = mask_nxt;
             const uint32_t old = old_nxt;
@@ -1161,7 +1175,7 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
             reinterpret_cast<uint2*>(sm.kv)[r] = make_uint2(key[j], val[j]);
         else
             sm.kv[r] = key[j];
-        constexpr int LB_EVERY = (MATCH & LB_STEP2) ? 2 : ((MATCH & LB_STEP8) ? 8 : 4);
+        constexpr int LB_EVERY = (MATCH & LB_STEP2) ? 2 : ((MATCH & LB_STEP8) ? 8 : ((MATCH & LB_STEP16) ? 16 : 4));
         if (INTERLEAVED && (j % LB_EVERY) == LB_EVERY - 1 && j + 1 < ITEMS) lb_try();
     }
 
@@ -1643,28 +1657,128 @@ const sort_variant g_variants[] = {
     CVARIANT(384, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 53: keys only, 24 warps/SM
     CVARIANT(256, 56, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 54
     CVARIANT(256, 64, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 55
+    CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 56: EXPERIMENT, see RANK_ATOMIC_ORDER
+    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 57
+    CVARIANT(256, 50, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 58
+    CVARIANT(384, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 59
+    CVARIANT(384, 30, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 60
+    CVARIANT(384, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 61
+    CVARIANT(512, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 62
+    CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 63
+    CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP16 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 64
+    CVARIANT(256, 46, TILE_BY_BLOCKIDX | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 65: look-back after the ranking
+    CVARIANT(384, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 66
+    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 67
+    CVARIANT(256, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | RANK_ATOMIC_ORDER, 3),   // 68: 4096-pair tiles
+    CVARIANT(256, 64, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 69: keys-only tiles
+    CVARIANT(256, 80, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 70
+    CVARIANT(256, 96, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 71
+    CVARIANT(384, 56, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 72: keys only, 24 warps
+    CVARIANT(256, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | RANK_ATOMIC_ORDER, 4),   // 73
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
 constexpr uint32_t kMinTile = 256 * 16;
 
 int g_variant = 0;
-// Variant 0 means "automatic": inputs below 2^20 pairs take the 4096-pair tile (more CTAs than SMs from 2^19 on, and the
-// per-tile steps are shorter: 44 vs 63 us at 2^16 pairs, equal at 2^20, profiles/r1x_sort_size_variants.log)
-constexpr int kSmallTileVariant = 47;
+// Variant 0 means "automatic" (pick_variant below):
+//  * inputs below 2^20 pairs take the 4096-pair tile (more CTAs than SMs from 2^19 on, shorter per-tile steps: 44 vs 63 us
+//    at 2^16 pairs, equal at 2^20, profiles/r1x_sort_size_variants.log);
+//  * keys-only sorts stage 4 B per key, so 64 rows per thread fit the same shared memory and registers (16 384-key tiles);
+//  * the ranking step is RANK_ATOMIC_ORDER where the device passes the probe below, else the ballot match.
 constexpr uint32_t kSmallTileBelow = 1u << 20;
-static_assert(kNumVariants > kSmallTileVariant, "variant table changed");
+constexpr int kMatchSmall = 47, kMatchKeys = 55, kMatchPairs = 0;          // ballot-match ranking (order by construction)
+constexpr int kAtomicSmall = 68, kAtomicKeys = 69, kAtomicPairs = 67;      // RANK_ATOMIC_ORDER ranking
+static_assert(kNumVariants > 69, "variant table changed");
 
-// Keys-only sorts stage 4 B per key, so 64 rows per thread fit the same shared memory and registers (16 384-key tiles):
-// 76.2 vs 73.2 Gkeys/s at 2^28 keys (profiles/r1x_sort_keys_sweep.log)
-constexpr int kKeysOnlyVariant = 55;
-static_assert(kNumVariants > kKeysOnlyVariant, "variant table changed");
+// ---- ranking mode --------------------------------------------------------------------------------------------------
+// RANK_ATOMIC_ORDER kernels take every pair's slot with ONE returning shared atomic per lane and no match at all
+// (3.72 vs 4.34 ms per 2^28-pair sort).  The sort stays stable only if the lanes of one warp instruction that hit the
+// SAME shared address are served in ascending lane order.  PTX leaves that order unspecified; the B200 does it that
+// way, and the library does not take it on trust: the first sort on a device runs ranking_order_probe_kernel (every SM,
+// 16 warps per SM, ~4.7 M warp instructions over collision patterns from "all 32 lanes on one counter" to "256 random
+// counters", checked against the ballot match) and falls back to the ballot-match kernels if a single lane disagrees.
+// vrenb200_radix_sort_set_ranking / VRENB200_SORT_RANKING=match|atomic|auto override the choice.
+enum { RANKING_AUTO = 0, RANKING_MATCH = 1, RANKING_ATOMIC_ORDER = 2 };
+int g_ranking_mode = -1;                    // -1: not read from the environment yet
+constexpr int kMaxDevices = 64;
+int g_probe_state[kMaxDevices] = {};        // 0 unknown, 1 passed, 2 failed
+std::mutex g_probe_mutex;
+__device__ uint32_t g_probe_failures;
 
-const sort_variant& pick_variant(uint32_t n, int layout)
+__global__ void __launch_bounds__(256) ranking_order_probe_kernel(uint32_t rounds)
 {
-    if (g_variant == 0 && n < kSmallTileBelow) return g_variants[kSmallTileVariant];
-    if (g_variant == 0 && layout == LAYOUT_KEYS) return g_variants[kKeysOnlyVariant];
-    return g_variants[g_variant];
+    __shared__ uint32_t cnt[8][kRadix];
+    const unsigned tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 8 * kRadix; i += 256) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned lt = lanemask_lt();
+    uint32_t bad = 0;
+    uint32_t h = (blockIdx.x * 256u + tid) * 2654435761u + 12345u;
+    for (uint32_t r = 0; r < rounds; r++)
+    {
+        h ^= h << 13; h ^= h >> 17; h ^= h << 5;                       // xorshift32 per lane
+        const uint32_t distinct = 1u << ((r % 6u) * 2u > 8u ? 8u : (r % 6u) * 2u);   // 1, 4, 16, 64, 256, 256 counters in play
+        uint32_t d = (h >> 7) & (distinct - 1u);
+        if (r & 8u) d = (d * 32u + (d >> 3)) & 255u;                    // same-bank / different-address collisions as well
+        const uint32_t prior = cnt[warp][d];
+        __syncwarp();
+        const uint32_t old = atomicAdd(&cnt[warp][d], 1u);
+        __syncwarp();
+        const unsigned mask = __match_any_sync(kFullMask, d);
+        bad += old != prior + (uint32_t) __popc(mask & lt);
+    }
+    if (bad) atomicAdd(&g_probe_failures, bad);
+}
+
+// runs the probe once per device, on its own stream; never while the caller's stream is being captured
+bool atomic_order_ranking_ok(cudaStream_t user_stream)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+    std::lock_guard<std::mutex> lock(g_probe_mutex);
+    if (g_probe_state[dev]) return g_probe_state[dev] == 1;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(user_stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+    {
+        cudaGetLastError();
+        return false;   // not cached: the next call outside a capture probes
+    }
+    cudaStream_t s = nullptr;
+    uint32_t failures = 0xFFFFFFFFu, zero = 0;
+    bool ran = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+    ran = ran && cudaMemcpyToSymbolAsync(g_probe_failures, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    if (ran)
+    {
+        ranking_order_probe_kernel<<<kNumSMs * 2, 256, 0, s>>>(2000);
+        ran = cudaGetLastError() == cudaSuccess;
+    }
+    ran = ran && cudaMemcpyFromSymbolAsync(&failures, g_probe_failures, sizeof(failures), 0, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+    ran = ran && cudaStreamSynchronize(s) == cudaSuccess;
+    if (s) cudaStreamDestroy(s);
+    if (!ran) cudaGetLastError();
+    g_probe_state[dev] = (ran && failures == 0) ? 1 : 2;
+    return g_probe_state[dev] == 1;
+}
+
+int ranking_mode()
+{
+    if (g_ranking_mode < 0)
+    {
+        const char* e = std::getenv("VRENB200_SORT_RANKING");
+        g_ranking_mode = (e && std::strcmp(e, "match") == 0) ? RANKING_MATCH : ((e && std::strcmp(e, "atomic") == 0) ? RANKING_ATOMIC_ORDER : RANKING_AUTO);
+    }
+    return g_ranking_mode;
+}
+
+const sort_variant& pick_variant(uint32_t n, int layout, cudaStream_t s)
+{
+    if (g_variant != 0) return g_variants[g_variant];
+    const int mode = ranking_mode();
+    const bool atomic = mode == RANKING_ATOMIC_ORDER || (mode == RANKING_AUTO && atomic_order_ranking_ok(s));
+    if (n < kSmallTileBelow) return g_variants[atomic ? kAtomicSmall : kMatchSmall];
+    if (layout == LAYOUT_KEYS) return g_variants[atomic ? kAtomicKeys : kMatchKeys];
+    return g_variants[atomic ? kAtomicPairs : kMatchPairs];
 }
 uint32_t g_bucket_search_min = 1u << 20;   // bucket sort: from this many pairs on, END offsets come from a search in the sorted output
 int g_partition_shape = 0;   // 0: 256x32 (2 CTAs/SM), 1: 256x16 (4 CTAs/SM), 2: 512x16 (2 CTAs/SM)
@@ -1720,7 +1834,7 @@ int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, 
          reinterpret_cast<uintptr_t>(ctl_mem)) & 15)
         return VRENB200_EALIGN;
     const int layout = vals != nullptr ? LAYOUT_SOA : LAYOUT_KEYS;
-    const sort_variant& var = pick_variant(n, layout);
+    const sort_variant& var = pick_variant(n, layout, s);
     const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
     sort_control* ctl = static_cast<sort_control*>(ctl_mem);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
@@ -1756,6 +1870,20 @@ extern "C" int vrenb200_radix_sort_set_variant(int v)
     if (v < 0 || v >= kNumVariants) return VRENB200_EINVAL_ARG;
     g_variant = v;
     return VRENB200_OK;
+}
+// ranking step of the default kernels: 0 = automatic (probe the device once), 1 = ballot match, 2 = atomic order
+extern "C" int vrenb200_radix_sort_set_ranking(int mode)
+{
+    if (mode < RANKING_AUTO || mode > RANKING_ATOMIC_ORDER) return VRENB200_EINVAL_ARG;
+    g_ranking_mode = mode;
+    return VRENB200_OK;
+}
+// 1 if the current device serves same-address lanes of a shared atomic in ascending lane order (runs the probe if needed)
+extern "C" int vrenb200_radix_sort_ranking_probe(void) { return atomic_order_ranking_ok(nullptr) ? 1 : 0; }
+// name of the pass configuration a sort of n elements would use now (reporting)
+extern "C" const char* vrenb200_radix_sort_selected_variant_name(uint32_t n, int with_values)
+{
+    return pick_variant(n, with_values ? LAYOUT_SOA : LAYOUT_KEYS, nullptr).name;
 }
 extern "C" int vrenb200_radix_sort_set_dephase(uint32_t ns, uint32_t rule)
 {
@@ -2024,7 +2152,7 @@ extern "C" int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pai
     uint32_t* tmp = reinterpret_cast<uint32_t*>(p);
     void* ctl_mem = p + align_up((size_t) n * 8, 256);
     uint32_t* raw_counts = reinterpret_cast<uint32_t*>(p + align_up((size_t) n * 8, 256) + control_bytes(n));
-    const sort_variant& var = pick_variant(n, LAYOUT_AOS);
+    const sort_variant& var = pick_variant(n, LAYOUT_AOS, s);
     const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
     sort_control* ctl = static_cast<sort_control*>(ctl_mem);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);

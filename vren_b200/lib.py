@@ -85,6 +85,9 @@ def load() -> C.CDLL:
     sig("vrenb200_radix_sort_set_variant", i32, i32)
     sig("vrenb200_radix_sort_set_prefetch_tiles", i32, u32)
     sig("vrenb200_radix_sort_set_dephase", i32, u32, u32)
+    sig("vrenb200_radix_sort_set_ranking", i32, i32)
+    sig("vrenb200_radix_sort_ranking_probe", i32)
+    sig("vrenb200_radix_sort_selected_variant_name", C.c_char_p, u32, i32)
     sig("vrenb200_radix_sort_num_variants", i32)
     sig("vrenb200_radix_sort_variant_name", C.c_char_p, i32)
     sig("vrenb200_sort_profile_create", vp)
