@@ -1675,6 +1675,14 @@ const sort_variant g_variants[] = {
     CVARIANT(256, 96, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 71
     CVARIANT(384, 56, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 72: keys only, 24 warps
     CVARIANT(256, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | RANK_ATOMIC_ORDER, 4),   // 73
+    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS, 2),   // 74
+    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 2),   // 75
+    CVARIANT(256, 50, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 76
+    CVARIANT(384, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 77
+    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | VALS_DIRECT | VALS_LATE, 2),   // 78
+    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS | KEYS_CHUNKED, 2),   // 79
+    CVARIANT(256, 64, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS | KEYS_CHUNKED, 2),   // 80: keys only
+    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP16 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS | KEYS_CHUNKED, 2),   // 81
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
@@ -1688,8 +1696,8 @@ int g_variant = 0;
 //  * the ranking step is RANK_ATOMIC_ORDER where the device passes the probe below, else the ballot match.
 constexpr uint32_t kSmallTileBelow = 1u << 20;
 constexpr int kMatchSmall = 47, kMatchKeys = 55, kMatchPairs = 0;          // ballot-match ranking (order by construction)
-constexpr int kAtomicSmall = 68, kAtomicKeys = 69, kAtomicPairs = 67;      // RANK_ATOMIC_ORDER ranking
-static_assert(kNumVariants > 69, "variant table changed");
+constexpr int kAtomicSmall = 68, kAtomicKeys = 80, kAtomicPairs = 79;      // RANK_ATOMIC_ORDER ranking
+static_assert(kNumVariants > 80, "variant table changed");
 
 // ---- ranking mode --------------------------------------------------------------------------------------------------
 // RANK_ATOMIC_ORDER kernels take every pair's slot with ONE returning shared atomic per lane and no match at all
