@@ -4,8 +4,10 @@
  * Every entry point is what a binding from the reference (loryruta/vren, C++/Vulkan) would call in
  * place of recording Vulkan dispatches.  All `*_run`-style calls are:
  *   - asynchronous on the given CUDA stream (the analogue of "record into a VkCommandBuffer"),
- *   - allocation-free and host-sync-free (caller owns inputs, outputs and scratch),
- *   - re-entrant: no global mutable state.
+ *   - allocation-free and host-sync-free (caller owns inputs, outputs and scratch); the one exception is the 0.6 ms
+ *     device probe the first radix / bucket sort on a device runs on a private stream (see
+ *     vrenb200_radix_sort_set_ranking; never during a stream capture),
+ *   - re-entrant: no global mutable state apart from the tuning hooks (`*_set_*`) and the cached probe result.
  * Pointers are raw device pointers unless the name ends in `_host`.  Lengths are ELEMENTS,
  * sizes are BYTES.  Return value: 0 on success, one of VRENB200_E* otherwise.
  *
