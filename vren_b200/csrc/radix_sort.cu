@@ -1683,6 +1683,10 @@ const sort_variant g_variants[] = {
     CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS | KEYS_CHUNKED, 2),   // 79
     CVARIANT(256, 64, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS | KEYS_CHUNKED, 2),   // 80: keys only
     CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP16 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS | KEYS_CHUNKED, 2),   // 81
+    CVARIANT(320, 36, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 2),   // 82
+    CVARIANT(320, 38, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 2),   // 83
+    CVARIANT(256, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 3),   // 84
+    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 3),   // 85
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
