@@ -18,7 +18,8 @@ g = torch.Generator(device=dev)
 g.manual_seed(11)
 
 nvar = lib.vrenb200_radix_sort_num_variants()
-variants = [int(a) for a in sys.argv[1:]] or [0] + list(range(17, nvar))   # 0 = default, 25 = the default before r1w
+variants = [int(a) for a in sys.argv[1:]] or [v for v in [0] + list(range(17, nvar))
+                                             if b"[retired]" not in lib.vrenb200_radix_sort_variant_name(v)]   # 0 = ballot-match default
 
 
 def check_sorted(k0, k, v):

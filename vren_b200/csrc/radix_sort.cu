@@ -1597,96 +1597,100 @@ int launch_count_first(cudaStream_t s, const uint32_t* kin, uint32_t* kout, cons
 #define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B> }
 #define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
 #define CVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B, (T) * (I), launch_count_first<T, I, M, B> }
+// retired entries: measured once (name and number appear in profiles/), no longer compiled; not selectable
+#define RVARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B " [retired]", (T) * (I), nullptr }
+#define RPVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B " [retired]", (T) * (I), nullptr }
+#define RCVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B " [retired]", (T) * (I), nullptr }
 const sort_variant g_variants[] = {
     // 0: default (best of the sweeps in profiles/): 11776-pair tiles (256 threads x 46 rows, 2 CTAs = 16 warps per SM, 128
     // registers per thread: the per-tile steps are amortised over more pairs), staging copies issued first, L2 prefetch for
     // the successor CTA, leader-atomic ranking, interleaved look-back
     CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),
-    VARIANT(256, 32, TILE_BY_BLOCKIDX | SPLIT_KV, 2),
+    RVARIANT(256, 32, TILE_BY_BLOCKIDX | SPLIT_KV, 2),
     PVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // persistent CTAs + key prefetch, static tile striding
     PVARIANT(256, 32, MATCH_BALLOT, 2),      // persistent, tickets
-    VARIANT(512, 16, TILE_BY_BLOCKIDX | SPLIT_KV, 2),   // 32 warps/SM instead of 16: slower (profiles/r1k_*)
+    RVARIANT(512, 16, TILE_BY_BLOCKIDX | SPLIT_KV, 2),   // 32 warps/SM instead of 16: slower (profiles/r1k_*)
     VARIANT(256, 32, MATCH_BALLOT, 2),       // ticket instead of block index
-    VARIANT(256, 32, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 2),
-    VARIANT(256, 32, TILE_BY_BLOCKIDX | LEADER_ATOMIC, 2),
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // 8
+    RVARIANT(256, 32, MATCH_BALLOT_C | TILE_BY_BLOCKIDX, 2),
+    RVARIANT(256, 32, TILE_BY_BLOCKIDX | LEADER_ATOMIC, 2),
+    RCVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // 8
     VARIANT(256, 32, TILE_BY_BLOCKIDX, 2),   // 9: rank-then-count order, the default until r1m
     VARIANT(256, 32, TILE_BY_BLOCKIDX | FAKE_LOOKBACK, 2),  // 10: ceiling without the look-back chain (wrong results)
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX | DIRECT_LOAD, 2),   // 11
-    CVARIANT(256, 24, TILE_BY_BLOCKIDX | DIRECT_LOAD, 3),   // 12
-    CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED, 3),   // 13
+    RCVARIANT(256, 32, TILE_BY_BLOCKIDX | DIRECT_LOAD, 2),   // 11
+    RCVARIANT(256, 24, TILE_BY_BLOCKIDX | DIRECT_LOAD, 3),   // 12
+    RCVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED, 3),   // 13
     CVARIANT(256, 24, TILE_BY_BLOCKIDX, 3),   // 14: default of r1m
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP2, 2),   // 15
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8, 2),   // 16
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | PREFETCH_L2, 2),   // 17
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | RANK_LEADER_ATOMIC, 2),   // 18
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | PREFETCH_L2 | EARLY_TMA, 2),   // 19
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA, 2),   // 20
-    CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2, 3),   // 21
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 22
-    CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 3),   // 23
-    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2, 2),   // 24
+    RCVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP2, 2),   // 15
+    RCVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8, 2),   // 16
+    RCVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | PREFETCH_L2, 2),   // 17
+    RCVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | RANK_LEADER_ATOMIC, 2),   // 18
+    RCVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | PREFETCH_L2 | EARLY_TMA, 2),   // 19
+    RCVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA, 2),   // 20
+    RCVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2, 3),   // 21
+    RCVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 22
+    RCVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 3),   // 23
+    RCVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2, 2),   // 24
     CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED, 2),   // 25: default until r1w
-    CVARIANT(512, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 26
-    CVARIANT(320, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 27
+    RCVARIANT(512, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 26
+    RCVARIANT(320, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 27
     CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT, 2),   // 28
-    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | REG_COUNTS, 2),   // 29
+    RCVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | REG_COUNTS, 2),   // 29
     CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | KEYS_CHUNKED, 2),   // 30
-    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT | KEYS_CHUNKED, 2),   // 31
-    CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT | KEYS_CHUNKED | REG_COUNTS, 2),   // 32
-    CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT | KEYS_CHUNKED, 3),   // 33
+    RCVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT | KEYS_CHUNKED, 2),   // 31
+    RCVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT | KEYS_CHUNKED | REG_COUNTS, 2),   // 32
+    RCVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | VALS_DIRECT | KEYS_CHUNKED, 3),   // 33
     CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | DEPHASE, 2),   // 34
-    CVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | DEPHASE, 3),   // 35
-    CVARIANT(256, 36, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 36: 16 warps/SM, more rows per thread
-    CVARIANT(256, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 37
+    RCVARIANT(256, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | DEPHASE, 3),   // 35
+    RCVARIANT(256, 36, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 36: 16 warps/SM, more rows per thread
+    RCVARIANT(256, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 37
     CVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 38
-    CVARIANT(320, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 39
-    CVARIANT(512, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 1),   // 40: one CTA per SM, 20480-pair tiles
-    CVARIANT(512, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 1),   // 41
+    RCVARIANT(320, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 39
+    RCVARIANT(512, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 1),   // 40: one CTA per SM, 20480-pair tiles
+    RCVARIANT(512, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 1),   // 41
     CVARIANT(384, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 42: default of r1w
-    CVARIANT(288, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 43
-    CVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | LB_STEP8, 2),   // 44
-    CVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2, 2),   // 45: without the leader atomic
-    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 46: the largest tile two CTAs fit
+    RCVARIANT(288, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 43
+    RCVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | LB_STEP8, 2),   // 44
+    RCVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2, 2),   // 45: without the leader atomic
+    RCVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 46: the largest tile two CTAs fit
     CVARIANT(256, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | RANK_LEADER_ATOMIC, 3),   // 47: 4096-pair tiles for mid-size inputs
     CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | MATCH_SPLIT4, 2),   // 48
-    CVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | MATCH_SPLIT4, 2),   // 49
-    CVARIANT(256, 72, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 50: keys-only tiles (4 B/key of shared memory)
-    CVARIANT(256, 80, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 51
-    CVARIANT(256, 88, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 52
-    CVARIANT(384, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 53: keys only, 24 warps/SM
-    CVARIANT(256, 56, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 54
+    RCVARIANT(256, 44, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC | MATCH_SPLIT4, 2),   // 49
+    RCVARIANT(256, 72, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 50: keys-only tiles (4 B/key of shared memory)
+    RCVARIANT(256, 80, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 51
+    RCVARIANT(256, 88, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 52
+    RCVARIANT(384, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 53: keys only, 24 warps/SM
+    RCVARIANT(256, 56, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 54
     CVARIANT(256, 64, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 55
     CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 56: EXPERIMENT, see RANK_ATOMIC_ORDER
-    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 57
-    CVARIANT(256, 50, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 58
-    CVARIANT(384, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 59
-    CVARIANT(384, 30, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 60
-    CVARIANT(384, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 61
-    CVARIANT(512, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 62
+    RCVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 57
+    RCVARIANT(256, 50, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 58
+    RCVARIANT(384, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 59
+    RCVARIANT(384, 30, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 60
+    RCVARIANT(384, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 61
+    RCVARIANT(512, 24, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 62
     CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 63
-    CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP16 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 64
+    RCVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP16 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 64
     CVARIANT(256, 46, TILE_BY_BLOCKIDX | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 65: look-back after the ranking
-    CVARIANT(384, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 66
+    RCVARIANT(384, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 66
     CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 67
     CVARIANT(256, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | RANK_ATOMIC_ORDER, 3),   // 68: 4096-pair tiles
     CVARIANT(256, 64, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 69: keys-only tiles
-    CVARIANT(256, 80, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 70
-    CVARIANT(256, 96, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 71
-    CVARIANT(384, 56, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 72: keys only, 24 warps
-    CVARIANT(256, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | RANK_ATOMIC_ORDER, 4),   // 73
-    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS, 2),   // 74
-    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 2),   // 75
-    CVARIANT(256, 50, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 76
-    CVARIANT(384, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 77
-    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | VALS_DIRECT | VALS_LATE, 2),   // 78
+    RCVARIANT(256, 80, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 70
+    RCVARIANT(256, 96, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 71
+    RCVARIANT(384, 56, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 72: keys only, 24 warps
+    RCVARIANT(256, 16, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | RANK_ATOMIC_ORDER, 4),   // 73
+    RCVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS, 2),   // 74
+    RCVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 2),   // 75
+    RCVARIANT(256, 50, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 76
+    RCVARIANT(384, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 77
+    RCVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | VALS_DIRECT | VALS_LATE, 2),   // 78
     CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS | KEYS_CHUNKED, 2),   // 79
     CVARIANT(256, 64, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS | KEYS_CHUNKED, 2),   // 80: keys only
-    CVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP16 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS | KEYS_CHUNKED, 2),   // 81
-    CVARIANT(320, 36, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 2),   // 82
-    CVARIANT(320, 38, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 2),   // 83
-    CVARIANT(256, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 3),   // 84
-    CVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 3),   // 85
+    RCVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP16 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | REG_COUNTS | KEYS_CHUNKED, 2),   // 81
+    RCVARIANT(320, 36, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 2),   // 82
+    RCVARIANT(320, 38, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 2),   // 83
+    RCVARIANT(256, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 3),   // 84
+    RCVARIANT(256, 32, TILE_BY_BLOCKIDX | LB_INTERLEAVED | LB_STEP8 | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER | KEYS_CHUNKED, 3),   // 85
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 // the scratch layout must not depend on the variant: size the look-back for the smallest tile
@@ -1879,7 +1883,7 @@ using namespace vrenb200;
 // tuning hook (not part of the reference surface): select the kernel configuration used by subsequent calls
 extern "C" int vrenb200_radix_sort_set_variant(int v)
 {
-    if (v < 0 || v >= kNumVariants) return VRENB200_EINVAL_ARG;
+    if (v < 0 || v >= kNumVariants || g_variants[v].launch == nullptr) return VRENB200_EINVAL_ARG;
     g_variant = v;
     return VRENB200_OK;
 }
