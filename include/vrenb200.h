@@ -143,6 +143,7 @@ int vrenb200_radix_sort_set_ranking(int mode);
 int vrenb200_radix_sort_ranking_probe(void);   /* 1: ascending lane order on the current device, 0: not */
 const char* vrenb200_radix_sort_selected_variant_name(uint32_t n, int with_values);
 int vrenb200_radix_sort_set_dephase(uint32_t ns, uint32_t rule);   /* DEPHASE variants: start delay of the second CTA of every SM (first wave only) */
+int vrenb200_radix_sort_set_hist_loads(uint32_t loads);   /* histogram kernel: 128-bit loads in flight per thread (2 or 4) */
 int vrenb200_radix_sort_set_prefetch_tiles(uint32_t tiles);   /* PREFETCH_L2 variants: distance of the L2 prefetch, in tiles */
 int vrenb200_radix_partition_set_shape(int shape);   /* exchange pass tile: 0: 256x32, 1: 256x16, 2: 512x16 */
 int vrenb200_scan_set_variant(int variant);

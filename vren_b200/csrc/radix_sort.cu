@@ -145,6 +145,7 @@ radix_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, sort_contr
 // different banks: one wavefront per instruction instead of ~3.4 for 32 random digits.  The shared-atomic pipe was the
 // limiter of the plain version (0.40 ms at 2^28 keys).
 constexpr int kHist2Threads = 1024;
+__device__ uint32_t g_hist_loads_in_flight = 4;   // tuning hook (vrenb200_radix_sort_set_hist_loads): 2 or 4 (0.217 vs 0.207 ms at 2^28 keys)
 constexpr size_t kHist2Smem = (size_t) kPasses * kRadix * 32 * sizeof(uint32_t);
 
 __global__ void __launch_bounds__(kHist2Threads, 1)
@@ -165,6 +166,22 @@ radix_histogram_columns_kernel(const uint32_t* __restrict__ keys, uint32_t n, so
     const uint4* keys4 = reinterpret_cast<const uint4*>(keys);
     const uint32_t stride = gridDim.x * kHist2Threads;
     uint32_t i = blockIdx.x * kHist2Threads + threadIdx.x;
+    if (g_hist_loads_in_flight >= 4)
+    {
+        // four 128-bit loads in flight per thread (64 KB per SM): one CTA of 1024 threads per SM needs that much to cover
+        // the HBM latency at full bandwidth
+        for (; (uint64_t) i + 3ull * stride < n4; i += 4 * stride)
+        {
+            const uint4 a = ldg_stream_u4(keys4 + i);
+            const uint4 b = ldg_stream_u4(keys4 + i + stride);
+            const uint4 c = ldg_stream_u4(keys4 + i + 2 * stride);
+            const uint4 d = ldg_stream_u4(keys4 + i + 3 * stride);
+            count(a.x); count(a.y); count(a.z); count(a.w);
+            count(b.x); count(b.y); count(b.z); count(b.w);
+            count(c.x); count(c.y); count(c.z); count(c.w);
+            count(d.x); count(d.y); count(d.z); count(d.w);
+        }
+    }
     for (; (uint64_t) i + stride < n4; i += 2 * stride)
     {
         const uint4 a = ldg_stream_u4(keys4 + i);
@@ -1905,6 +1922,11 @@ extern "C" int vrenb200_radix_sort_set_dephase(uint32_t ns, uint32_t rule)
 {
     VRENB200_TRY(check_cuda(cudaMemcpyToSymbol(g_dephase_ns, &ns, sizeof(ns))));
     return check_cuda(cudaMemcpyToSymbol(g_dephase_rule, &rule, sizeof(rule)));
+}
+
+extern "C" int vrenb200_radix_sort_set_hist_loads(uint32_t loads)
+{
+    return check_cuda(cudaMemcpyToSymbol(g_hist_loads_in_flight, &loads, sizeof(loads)));
 }
 
 extern "C" int vrenb200_radix_sort_set_prefetch_tiles(uint32_t tiles)

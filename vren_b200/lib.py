@@ -84,6 +84,7 @@ def load() -> C.CDLL:
     sig("vrenb200_radix_sort_pairs_host", i32, vp, vp, vp, u32, vp, sz)
     sig("vrenb200_radix_sort_set_variant", i32, i32)
     sig("vrenb200_radix_sort_set_prefetch_tiles", i32, u32)
+    sig("vrenb200_radix_sort_set_hist_loads", i32, u32)
     sig("vrenb200_radix_sort_set_dephase", i32, u32, u32)
     sig("vrenb200_radix_sort_set_ranking", i32, i32)
     sig("vrenb200_radix_sort_ranking_probe", i32)
