@@ -261,6 +261,20 @@ def test_radix_pairs_both_rankings_collision_heavy(vren, mode, pattern, n):
         lib.vrenb200_radix_sort_set_ranking(0)
 
 
+@pytest.mark.parametrize("delta", [-1, 0, 1])
+@pytest.mark.parametrize("tile", [12288, 11776, 16384])
+def test_radix_sizes_around_the_default_tiles(vren, tile, delta):
+    """whole number of default tiles (12288 pairs atomic order, 11776 ballot match, 16384 keys only) and one element either
+    side, above the 2^20 switch to the large tiles"""
+    n = tile * 90 + delta
+    k = rand_u32(61, n)
+    v = np.arange(n, dtype=np.uint32)
+    wk, wv = oracle.sort_pairs(k, v)
+    gk, gv = vren.radix_sort_pairs(dev_u32(k), dev_u32(v))
+    assert np.array_equal(host_u32(gk), wk) and np.array_equal(host_u32(gv), wv)
+    assert np.array_equal(host_u32(vren.radix_sort_keys(dev_u32(k))), wk)
+
+
 def test_radix_all_variants_agree(vren):
     lib = vren.load()
     n = (1 << 18) + 333
