@@ -365,6 +365,7 @@ radix_scan_histograms_kernel(sort_control* ctl)
 
 // ---- 3. the fused onesweep pass ------------------------------------------------------------------------------
 enum { LAYOUT_KEYS = 0, LAYOUT_SOA = 1, LAYOUT_AOS = 2 };
+constexpr int kClearNextPassRow = 0x100;   // flag in the `pass` argument of the count-first kernel
 
 template <int THREADS, int ITEMS, int LAYOUT, bool P2P = false>
 struct onesweep_smem
@@ -868,8 +869,13 @@ template <int THREADS, int ITEMS, int LAYOUT, int MATCH, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
                             const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
-                            uint32_t n, int pass, sort_control* ctl, uint32_t* lookback, uint32_t num_tiles)
+                            uint32_t n, int pass_arg, sort_control* ctl, uint32_t* lookback, uint32_t num_tiles)
 {
+    // bit 8 of the pass argument: this tile also clears its look-back row of the NEXT pass (the host then clears only the
+    // first pass's rows: 22 MB instead of 89 MB of memset per 2^28-pair sort)
+    const int pass = pass_arg & 0xFF;
+    if ((pass_arg & kClearNextPassRow) && threadIdx.x < kRadix)
+        lookback[((size_t) (pass + 1) * num_tiles + blockIdx.x) * kRadix + threadIdx.x] = 0u;
     using smem_t = onesweep_smem<THREADS, ITEMS, LAYOUT, false>;
     constexpr int WARPS = smem_t::WARPS;
     constexpr int TILE = smem_t::TILE;
@@ -1529,6 +1535,7 @@ struct sort_variant
     const char* name;
     uint32_t tile;
     launch_fn launch;
+    bool clears_next_pass;   // count-first kernels: a pass clears the look-back rows of its successor (kClearNextPassRow)
 };
 
 template <int THREADS, int ITEMS, int LAYOUT, int MATCH, int MIN_BLOCKS>
@@ -1611,13 +1618,13 @@ int launch_count_first(cudaStream_t s, const uint32_t* kin, uint32_t* kout, cons
     }
 }
 
-#define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B> }
-#define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B> }
-#define CVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B, (T) * (I), launch_count_first<T, I, M, B> }
+#define VARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B, (T) * (I), launch_onesweep<T, I, M, B>, false }
+#define PVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B, (T) * (I), launch_persistent<T, I, M, B>, false }
+#define CVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B, (T) * (I), launch_count_first<T, I, M, B>, true }
 // retired entries: measured once (name and number appear in profiles/), no longer compiled; not selectable
-#define RVARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B " [retired]", (T) * (I), nullptr }
-#define RPVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B " [retired]", (T) * (I), nullptr }
-#define RCVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B " [retired]", (T) * (I), nullptr }
+#define RVARIANT(T, I, M, B) { #T "x" #I "/" #M "/occ" #B " [retired]", (T) * (I), nullptr, false }
+#define RPVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B " [retired]", (T) * (I), nullptr, false }
+#define RCVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B " [retired]", (T) * (I), nullptr, false }
 const sort_variant g_variants[] = {
     // 0: default (best of the sweeps in profiles/): 11776-pair tiles (256 threads x 46 rows, 2 CTAs = 16 warps per SM, 128
     // registers per thread: the per-tile steps are amortised over more pairs), staging copies issued first, L2 prefetch for
@@ -1871,9 +1878,17 @@ int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, 
     const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
     sort_control* ctl = static_cast<sort_control*>(ctl_mem);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
-    // only the part of the look-back this variant touches needs clearing
-    const size_t clear = sizeof(sort_control) + (size_t) kPasses * tiles * kRadix * sizeof(uint32_t);
-    VRENB200_TRY(check_cuda(cudaMemsetAsync(ctl_mem, 0, clear, s)));
+    // only the part of the look-back this variant touches needs clearing; count-first passes clear their successor's rows
+    if (var.clears_next_pass)
+    {
+        VRENB200_TRY(check_cuda(cudaMemsetAsync(ctl_mem, 0, sizeof(sort_control), s)));
+        VRENB200_TRY(check_cuda(cudaMemsetAsync(lookback + (size_t) first_pass * tiles * kRadix, 0, (size_t) tiles * kRadix * sizeof(uint32_t), s)));
+    }
+    else
+    {
+        const size_t clear = sizeof(sort_control) + (size_t) kPasses * tiles * kRadix * sizeof(uint32_t);
+        VRENB200_TRY(check_cuda(cudaMemsetAsync(ctl_mem, 0, clear, s)));
+    }
     if (prof) cudaEventRecord(prof->ev[0], s);
     VRENB200_TRY(launch_histogram(s, keys, n, ctl));
     if (prof) cudaEventRecord(prof->ev[1], s);
@@ -1885,8 +1900,9 @@ int radix_sort_impl(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, 
     {
         const int pass = first_pass + i;
         const bool even = (i & 1) == 0;
+        const int pass_arg = pass | ((var.clears_next_pass && i + 1 < num_passes) ? kClearNextPassRow : 0);
         VRENB200_TRY(var.launch(s, even ? keys : alt_keys, even ? alt_keys : keys, even ? vals : alt_vals,
-                                even ? alt_vals : vals, n, pass, ctl, lookback, tiles, layout));
+                                even ? alt_vals : vals, n, pass_arg, ctl, lookback, tiles, layout));
         if (prof && num_passes == kPasses) cudaEventRecord(prof->ev[3 + pass], s);
     }
     return VRENB200_OK;
@@ -2194,7 +2210,7 @@ extern "C" int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pai
     const uint32_t tiles = (uint32_t) (((size_t) n + var.tile - 1) / var.tile);
     sort_control* ctl = static_cast<sort_control*>(ctl_mem);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(ctl + 1);
-    const size_t clear = sizeof(sort_control) + (size_t) 2 * tiles * kRadix * sizeof(uint32_t);
+    const size_t clear = sizeof(sort_control) + (size_t) (var.clears_next_pass ? 1 : 2) * tiles * kRadix * sizeof(uint32_t);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(ctl_mem, 0, clear, s)));
     // small inputs (the light Morton sort of the clustered chain): bucket counts by global atomics in the histogram read,
     // prefix by bucket_end_offsets_kernel; large inputs: no global atomics, END offsets by search in the sorted output
@@ -2208,7 +2224,8 @@ extern "C" int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pai
     VRENB200_TRY(check_launch());
     radix_scan_histograms_kernel<<<2, kRadix, 0, s>>>(ctl);
     VRENB200_TRY(check_launch());
-    VRENB200_TRY(var.launch(s, static_cast<const uint32_t*>(in_pairs), tmp, nullptr, nullptr, n, 0, ctl, lookback, tiles, LAYOUT_AOS));
+    VRENB200_TRY(var.launch(s, static_cast<const uint32_t*>(in_pairs), tmp, nullptr, nullptr, n, var.clears_next_pass ? kClearNextPassRow : 0,
+                            ctl, lookback, tiles, LAYOUT_AOS));
     VRENB200_TRY(var.launch(s, tmp, static_cast<uint32_t*>(out), nullptr, nullptr, n, 1, ctl, lookback, tiles, LAYOUT_AOS));
     if (by_search)
         bucket_end_offsets_search_kernel<<<kBucketKeys / 256, 256, 0, s>>>(static_cast<const uint2*>(out), n, counters);
