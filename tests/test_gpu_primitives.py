@@ -265,8 +265,8 @@ def test_radix_pairs_both_rankings_collision_heavy(vren, mode, pattern, n):
 @pytest.mark.parametrize("tile", [12288, 11776, 16384])
 def test_radix_sizes_around_the_default_tiles(vren, tile, delta):
     """whole number of default tiles (12288 pairs atomic order, 11776 ballot match, 16384 keys only) and one element either
-    side, above the 2^20 switch to the large tiles"""
-    n = tile * 90 + delta
+    side, above the 2^21 switch to the large tiles"""
+    n = tile * 180 + delta
     k = rand_u32(61, n)
     v = np.arange(n, dtype=np.uint32)
     wk, wv = oracle.sort_pairs(k, v)

@@ -37,8 +37,8 @@ for var in only or range(lib.vrenb200_radix_sort_num_variants()):
     u = kk.to(torch.int64) & 0xFFFFFFFF
     assert bool((u[1:] >= u[:-1]).all()), ("keys", var)
 vlib.check(lib.vrenb200_radix_sort_set_variant(0), "variant")
-# variant 0 takes the small tile below 2^20 pairs: exercise the default 256x46 tile too (ragged last tile)
-n = (1 << 20) + 12345
+# variant 0 takes the small tile below 2^21 pairs: exercise the default large tiles too (ragged last tile)
+n = (1 << 21) + 12345
 k = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
 kk, vv = k.clone(), torch.arange(n, dtype=torch.int32, device=dev)
 vlib.radix_sort_pairs(kk, vv)

@@ -1722,11 +1722,11 @@ constexpr uint32_t kMinTile = 256 * 16;
 
 int g_variant = 0;
 // Variant 0 means "automatic" (pick_variant below):
-//  * inputs below 2^20 pairs take the 4096-pair tile (more CTAs than SMs from 2^19 on, shorter per-tile steps: 44 vs 63 us
-//    at 2^16 pairs, equal at 2^20, profiles/r1x_sort_size_variants.log);
+//  * inputs below 2^21 pairs take the 4096-pair tile (more CTAs than SMs from 2^19 on, shorter per-tile steps: 44 vs 63 us
+//    at 2^16 pairs, 64.5 vs 71.6 us at 2^20, equal at 2^21-2^22, profiles/r1x_sort_size_variants.log, r1z_*);
 //  * keys-only sorts stage 4 B per key, so 64 rows per thread fit the same shared memory and registers (16 384-key tiles);
 //  * the ranking step is RANK_ATOMIC_ORDER where the device passes the probe below, else the ballot match.
-constexpr uint32_t kSmallTileBelow = 1u << 20;
+constexpr uint32_t kSmallTileBelow = 1u << 21;
 constexpr int kMatchSmall = 47, kMatchKeys = 55, kMatchPairs = 0;          // ballot-match ranking (order by construction)
 constexpr int kAtomicSmall = 68, kAtomicKeys = 80, kAtomicPairs = 79;      // RANK_ATOMIC_ORDER ranking
 static_assert(kNumVariants > 80, "variant table changed");
