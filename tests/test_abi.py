@@ -86,3 +86,33 @@ def test_facade_reference_style_tests(vren):
     sys.stdout.write(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ALL PASS" in r.stdout
+
+
+def test_sort_kernel_selection_and_ranking_guard(handle):
+    """host-side selection logic of the sort passes (no kernel is launched).  Without a device that passes the probe the
+    library must pick the ballot-match kernels by itself; the atomic-order kernels are chosen only when forced or probed."""
+    import torch
+
+    name = lambda n, kv: handle.vrenb200_radix_sort_selected_variant_name(n, kv).decode()
+    try:
+        if not torch.cuda.is_available():
+            assert handle.vrenb200_radix_sort_ranking_probe() == 0                 # no device: the guard says no
+            for n, kv in ((1000, 1), (1 << 24, 1), (1 << 24, 0)):
+                assert "RANK_LEADER_ATOMIC" in name(n, kv) and "RANK_ATOMIC_ORDER" not in name(n, kv)
+        assert handle.vrenb200_radix_sort_set_ranking(1) == 0                       # ballot match, whatever the device says
+        assert name(1 << 24, 1).startswith("256x46/") and "RANK_LEADER_ATOMIC" in name(1 << 24, 1)
+        assert name(1 << 24, 0).startswith("256x64/") and name(1000, 1).startswith("256x16/")
+        assert handle.vrenb200_radix_sort_set_ranking(2) == 0                       # atomic order forced
+        assert name(1 << 24, 1).startswith("256x48/") and "RANK_ATOMIC_ORDER" in name(1 << 24, 1)
+        assert name(1 << 24, 0).startswith("256x64/") and "RANK_ATOMIC_ORDER" in name(1 << 24, 0)
+        assert name((1 << 21) - 1, 1).startswith("256x16/") and name(1 << 21, 1).startswith("256x48/")   # small-tile switch
+        assert handle.vrenb200_radix_sort_set_ranking(3) == lib.EINVAL_ARG
+        # retired table entries keep their name and number but cannot be selected
+        retired = [v for v in range(handle.vrenb200_radix_sort_num_variants()) if b"[retired]" in handle.vrenb200_radix_sort_variant_name(v)]
+        assert retired and all(handle.vrenb200_radix_sort_set_variant(v) == lib.EINVAL_ARG for v in retired)
+        assert handle.vrenb200_radix_sort_set_variant(handle.vrenb200_radix_sort_num_variants()) == lib.EINVAL_ARG
+        # an explicit variant wins over the ranking mode
+        assert handle.vrenb200_radix_sort_set_variant(42) == 0 and name(1 << 24, 1).startswith("384x24/")
+    finally:
+        handle.vrenb200_radix_sort_set_variant(0)
+        handle.vrenb200_radix_sort_set_ranking(0)
