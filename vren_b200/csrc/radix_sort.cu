@@ -403,8 +403,8 @@ enum { MATCH_BALLOT = 0, MATCH_BALLOT_C = 1, TILE_BY_BLOCKIDX = 2, EARLY_HIST = 
                               start of the tile, consumed by the regroup stores); only the keys are staged */,
        REG_COUNTS = 131072 /* count-first kernel: the per-warp digit counts stay in registers between the publish and the
                               offset step instead of being read from shared memory twice */,
-       RANK_ATOMIC_ORDER = 2097152 /* EXPERIMENT: rank = returning shared atomic per lane, no match (relies on unspecified
-                                      ordering of same-address lanes; see the kernel) */,
+       RANK_ATOMIC_ORDER = 2097152 /* rank = returning shared atomic per lane, no match (relies on the lane order of
+                                      same-address shared atomics: guarded by the device probe, see pick_variant) */,
        LB_STEP16 = 4194304 /* look-back step every 16 ranking rows */,
        MATCH_SPLIT4 = 1048576 /* ballot match with four accumulators (shorter dependent chains) */,
        VALS_LATE = 524288 /* VALS_DIRECT: the value loads are issued after the counting step instead of before the wait for the keys */,
@@ -1164,9 +1164,9 @@ onesweep_count_first_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __re
         uint32_t r;
         if (MATCH & RANK_ATOMIC_ORDER)
         {
-            // EXPERIMENT (not selectable as a default): no match at all, every lane takes its slot with a returning shared
-            // atomic.  Stable only if the hardware serialises the lanes of ONE instruction that hit the same address in
-            // ascending lane order, which PTX leaves unspecified; the sweep tool's stability check tells.
+            // no match at all: every lane takes its slot with a returning shared atomic.  Stable only if the hardware serves
+            // the lanes of ONE instruction that hit the same address in ascending lane order, which PTX leaves unspecified:
+            // selected by pick_variant only after ranking_order_probe_kernel has verified it on the device.
             r = atomicAdd(&my_hist[digit_of(key[j], prmt_sel)], 1u);
             __syncwarp();   // row j's adds are performed before row j+1's (different lanes may hit the same counter)
         }
@@ -1626,9 +1626,10 @@ int launch_count_first(cudaStream_t s, const uint32_t* kin, uint32_t* kout, cons
 #define RPVARIANT(T, I, M, B) { #T "x" #I "/persistent/occ" #B " [retired]", (T) * (I), nullptr, false }
 #define RCVARIANT(T, I, M, B) { #T "x" #I "/count-first/" #M "/occ" #B " [retired]", (T) * (I), nullptr, false }
 const sort_variant g_variants[] = {
-    // 0: default (best of the sweeps in profiles/): 11776-pair tiles (256 threads x 46 rows, 2 CTAs = 16 warps per SM, 128
-    // registers per thread: the per-tile steps are amortised over more pairs), staging copies issued first, L2 prefetch for
-    // the successor CTA, leader-atomic ranking, interleaved look-back
+    // 0: "automatic" (pick_variant); as a table entry, the ballot-match default for pairs: 11776-pair tiles (256 threads x
+    // 46 rows, 2 CTAs = 16 warps per SM, 128 registers per thread: the per-tile steps are amortised over more pairs),
+    // staging copies issued first, L2 prefetch for the successor CTA, leader-atomic ranking, interleaved look-back.
+    // The atomic-order defaults are 79 (pairs), 80 (keys only) and 68 (below 2^21 elements).
     CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),
     RVARIANT(256, 32, TILE_BY_BLOCKIDX | SPLIT_KV, 2),
     PVARIANT(256, 32, TILE_BY_BLOCKIDX, 2),  // persistent CTAs + key prefetch, static tile striding
@@ -1685,7 +1686,7 @@ const sort_variant g_variants[] = {
     RCVARIANT(384, 40, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 53: keys only, 24 warps/SM
     RCVARIANT(256, 56, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 54
     CVARIANT(256, 64, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_LEADER_ATOMIC, 2),   // 55
-    CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 56: EXPERIMENT, see RANK_ATOMIC_ORDER
+    CVARIANT(256, 46, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 56: first atomic-order measurement
     RCVARIANT(256, 48, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 57
     RCVARIANT(256, 50, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 58
     RCVARIANT(384, 28, TILE_BY_BLOCKIDX | LB_INTERLEAVED | EARLY_TMA | PREFETCH_L2 | RANK_ATOMIC_ORDER, 2),   // 59
