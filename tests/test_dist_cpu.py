@@ -146,3 +146,48 @@ def test_plan_p2p_offsets_tile_the_receive_buffers():
                 pos += int(hists[src, bounds[dst]:bounds[dst + 1]].sum())
                 assert int(per_dest[src, dst]) == int(hists[src, bounds[dst]:bounds[dst + 1]].sum())
             assert pos == plans[0][2][dst]
+
+
+def test_plan_digit_exchange_then_segment_sorts_give_the_global_stable_order():
+    """numpy simulation of the planned full-top-digit exchange: every source writes its pairs of top digit d at
+    my_digit_offset[d] of the owner's buffer (stable inside (source, digit)), every destination then sorts each
+    top-digit segment by the low 24 bits (three LSD passes); the concatenation must be the stable sort of the input"""
+    rng = np.random.Generator(np.random.PCG64(12))
+    for world, sizes in ((1, [1000]), (2, [5000, 3000]), (4, [4096, 0, 777, 9000]), (8, [2000] * 8)):
+        keys = [rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32) for n in sizes]
+        keys[0][: sizes[0] // 2] &= np.uint32(0x03FF00FF)                      # skew + many equal keys
+        vals, base = [], 0
+        for n in sizes:
+            vals.append(np.arange(base, base + n, dtype=np.uint32))
+            base += n
+        hists = torch.from_numpy(np.stack([np.bincount(k >> 24, minlength=256) for k in keys]).astype(np.int64))
+        bounds = vdist.plan_digit_ranges(hists.sum(0), world)
+        plans = [vdist.plan_digit_exchange(hists, bounds, r) for r in range(world)]
+        recv_counts = plans[0][3]
+        bufs_k = [np.zeros(c, np.uint32) for c in recv_counts]
+        bufs_v = [np.zeros(c, np.uint32) for c in recv_counts]
+        filled = [np.zeros(c, bool) for c in recv_counts]
+        for src in range(world):
+            rank_of, my_off, seg_start, _ = plans[src]
+            seen = np.zeros(256, np.int64)
+            for k, v in zip(keys[src], vals[src]):                               # the exchange pass: stable in (source, digit)
+                d = int(k >> 24)
+                dst = int(rank_of[d])
+                pos = int(my_off[d]) + seen[d]
+                seen[d] += 1
+                assert not filled[dst][pos]
+                filled[dst][pos] = True
+                bufs_k[dst][pos], bufs_v[dst][pos] = k, v
+        out_k, out_v = [], []
+        for dst in range(world):
+            assert filled[dst].all()
+            seg_start = plans[dst][2][dst]
+            for d in range(256):                                                 # the three low passes, per segment
+                lo, hi = int(seg_start[d]), int(seg_start[d + 1])
+                k, v = bufs_k[dst][lo:hi], bufs_v[dst][lo:hi]
+                assert k.size == 0 or ((k >> 24) == d).all()
+                order = np.argsort(k & np.uint32(0x00FFFFFF), kind="stable")
+                out_k.append(k[order]); out_v.append(v[order])
+        all_k, all_v = np.concatenate(keys), np.concatenate(vals)
+        want = np.argsort(all_k, kind="stable")
+        assert np.array_equal(np.concatenate(out_k), all_k[want]) and np.array_equal(np.concatenate(out_v), all_v[want])

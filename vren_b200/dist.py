@@ -154,6 +154,26 @@ def plan_p2p_offsets(hists: torch.Tensor, bounds: list, rank: int):
     return rank_of, my_offset, [int(v) for v in per_dest.sum(0)], per_dest
 
 
+def plan_digit_exchange(hists: torch.Tensor, bounds: list, rank: int):
+    """Planning for an exchange pass that partitions by the FULL top digit (host side only, the device side
+    is not wired yet).  Destination r's receive buffer is laid out by top digit, and inside a digit by source rank, so it
+    arrives grouped into top-digit segments and the local sort needs only the three low passes per segment.
+    hists: int64 [G, 256] top-digit counts of every rank (CPU); bounds: plan_digit_ranges().
+    Returns (rank_of uint8[256], my_digit_offset int64[256] = where THIS rank's pairs of top digit d start inside the
+    owner's buffer, segment_start int64[G][257] = start of every digit segment in every destination's buffer
+    (segment_start[r][d] == segment_start[r][d+1] outside r's range), recv_counts[G])."""
+    world = hists.shape[0]
+    b = torch.tensor(bounds, dtype=torch.int64)
+    rank_of = (torch.bucketize(torch.arange(256), b[1:-1], right=True)).to(torch.uint8) if world > 1 else torch.zeros(256, dtype=torch.uint8)
+    total = hists.sum(0)                                                   # [256]
+    owner = rank_of.to(torch.int64)
+    in_range = torch.nn.functional.one_hot(owner, world).T.to(torch.int64)  # [G, 256]: 1 where digit d belongs to rank r
+    seg_len = in_range * total                                             # [G, 256]
+    segment_start = torch.cat([torch.zeros(world, 1, dtype=torch.int64), torch.cumsum(seg_len, 1)], dim=1)   # [G, 257]
+    my_digit_offset = segment_start[owner, torch.arange(256)] + hists[:rank].sum(0)
+    return rank_of, my_digit_offset, segment_start, [int(v) for v in seg_len.sum(1)]
+
+
 class P2PExchange:
     """symmetric-memory receive buffers (keys, values) of one process group, created once and reused"""
 
