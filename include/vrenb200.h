@@ -233,6 +233,15 @@ int vrenb200_assign_lights(vrenb200_stream_t stream,
                            uint32_t* counts_out, uint32_t* offsets_out, uint32_t* status_out,
                            void* scratch, size_t scratch_bytes);
 
+/* Diagnostics of a8, one element per thread: the device functions the light-assignment walk is made of, for the parity tests
+ * pinned to the reference's own GLSL (tests/test_clustered_reference.py).  Per cluster key i: out_min3/out_max3[i] = the
+ * cluster corners of clustered_shading.glsl:72-110 (both NULL to skip); out_flags[i] bit 0 = test_aabb_aabb against
+ * node_boxes6[i] = {min.xyz, max.xyz}, bit 1 = test_sphere_aabb against spheres4[i] = {centre.xyz, radius}
+ * (assign_lights.comp:84-102); either input and out_flags may be NULL. */
+int vrenb200_cluster_tests(vrenb200_stream_t stream, uint32_t width, uint32_t height, const vrenb200_camera* camera,
+                           const uint32_t* cluster_keys, uint32_t count, float* out_min3, float* out_max3,
+                           const float* node_boxes6, const float* spheres4, uint8_t* out_flags);
+
 /* ---- n1: consumer side of the light lists (shade.comp:101-105, vren_demo show_clusters.comp:97-118) -------- */
 /* out_count_hash: uvec2[W*H] = {assigned_light_counts[cluster_reference(x,y)], XOR of that cluster's light indices} */
 size_t vrenb200_light_list_hash_scratch_bytes(uint32_t max_keys);

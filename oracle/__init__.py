@@ -84,7 +84,19 @@ class Camera(C.Structure):
     _fields_ = [("fov_y", C.c_float), ("aspect_ratio", C.c_float), ("near_plane", C.c_float), ("far_plane", C.c_float)]
 
 
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
 _LATE: list = [
+    ("oracle_projection", None, (C.c_void_p, f32p, f32p)),
+    ("oracle_discretize_normal", None, (f32p, C.c_uint32, u32p)),
+    ("oracle_cluster_key", None, (f32p, f32p, C.c_uint32, C.c_uint32, C.c_void_p, u32p, f32p)),
+    ("oracle_cluster_aabb", None, (u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, f32p, f32p)),
+    ("oracle_test_aabb_aabb", None, (f32p, C.c_uint32, u8p)),
+    ("oracle_test_sphere_aabb", None, (f32p, C.c_uint32, u8p)),
+    ("oracle_get_node_address", C.c_int32, (C.c_uint32, C.c_uint32, u32p)),
+    ("oracle_morton_code", None, (f32p, C.c_uint32, f32p, f32p, u32p)),
+    ("oracle_position_to_view_space", None, (f32p, f32p, C.c_uint32, f32p)),
+    ("oracle_light_leaf_box", None, (f32p, f32p, C.c_uint32, f32p, f32p)),
     ("oracle_light_list_hash", None, (C.c_uint32, C.c_uint32, u32p, u32p, u32p, u32p, u32p)),
     ("oracle_depth_pyramid", C.c_uint32, (f32p, C.c_uint32, C.c_uint32, f32p)),
     ("oracle_bounce_point_lights", None, (f32p, f32p, C.c_uint32, f32p, f32p, C.c_float, C.c_float)),
@@ -161,6 +173,46 @@ def load_ref():
         return None
     _ref = C.CDLL(str(REF_LIB_PATH))
     return _ref
+
+
+REF_GLSL_LIB_PATH = HERE / "_ref" / "libvrenref_glsl.so"
+_ref_glsl = None
+
+
+def load_ref_glsl():
+    """oracle/_ref/libvrenref_glsl.so — pure functions of the reference's compute shaders compiled by g++ through
+    oracle/glsl_shim.hpp from the GLSL where it lies (oracle/ref_extract.py).  None where /root/reference is absent."""
+    global _ref_glsl
+    if _ref_glsl is not None:
+        return _ref_glsl
+    if not REF_GLSL_LIB_PATH.exists():
+        return None
+    lib = C.CDLL(str(REF_GLSL_LIB_PATH))
+    u32, f32, i32 = C.c_uint32, C.c_float, C.c_int
+    u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+    def sig(name, res, *args):
+        f = getattr(lib, name)
+        f.restype = res
+        f.argtypes = list(args)
+
+    sig("refglsl_set_inverse_override", None, voidp)
+    sig("refglsl_inverse", None, f32p, f32p)
+    sig("refglsl_discretize_normal", None, f32p, u32, u32p)
+    sig("refglsl_decode_cluster_key", None, u32p, u32, u32p)
+    sig("refglsl_calc_cluster_aabb", None, u32p, u32, u32, u32, f32, f32, f32p, f32p, f32p)
+    sig("refglsl_test_aabb_aabb", None, f32p, u32, u8p)
+    sig("refglsl_test_sphere_aabb", None, f32p, u32, u8p)
+    sig("refglsl_get_node_address", C.c_int32, u32, u32, u32p)
+    sig("refglsl_morton_code", None, f32p, u32, f32p, f32p, u32p)
+    sig("refglsl_cluster_key", None, f32p, f32p, f32p, u32, u32, u32, u32, f32, f32, f32p, u32p, f32p)
+    sig("refglsl_position_to_view_space", None, f32p, f32p, u32, f32p)
+    sig("refglsl_light_leaf_box", None, f32p, f32p, u32, f32p, f32p)
+    sig("refglsl_depth_reduce", None, f32p, i32, i32, f32p, i32, i32)
+    sig("refglsl_bounce_point_lights", None, f32p, f32p, u32, f32p, f32p, f32, f32)
+    sig("refglsl_light_list_xor", None, u32p, u32p, u32p, u32, u32, u32p)
+    _ref_glsl = lib
+    return lib
 
 
 # ---- numpy convenience wrappers ---------------------------------------------------------------------------------

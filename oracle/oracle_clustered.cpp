@@ -8,7 +8,8 @@
 // file is compiled with -ffp-contract=off); mat4*vec4 = ((m0*x + m1*y) + (m2*z + m3*w)); normalize(v) = v / sqrt(dot);
 // dot(v,v) = (x*x + y*y) + z*z.  Transcendentals (tan, pow, log) are evaluated once on the host:
 //   a        = 1.0f + (2.0f * tanf(fov_y / 2.0f)) / (float) Ty                (find_unique_clusters.comp:65)
-//   slice k  = floor(log(z / near) / log(a)) evaluated in DOUBLE from the fp32 z, near, a; negative -> 0
+//   slice k  = floor(logf(z / near) / logf(a)) in fp32, as the shader types it (r2: was evaluated in double, which disagrees
+//              with the fp32 form for 0.0005-0.003 % of all depths, always by one slice at a boundary); negative -> 0
 //   near_k   = near * powf(a, (float) k)                                       (clustered_shading.glsl:97-98)
 //   inverse(projection) in closed form: i00 = 1/m00, i11 = 1/m11, row3 = (0, 0, 1/m32, -m22/m32), row2 = (0,0,0,1)
 #include <algorithm>
@@ -58,6 +59,13 @@ proj_t make_projection(const camera_t& c)
     return p;
 }
 
+// find_unique_clusters.comp:52-57: frag_pos = inverse(P) * (., ., d, 1); frag_pos /= frag_pos.w  ->  z = 1 / w'
+float view_z(float d, const proj_t& pr)
+{
+    const float w = d * pr.iB + 1.0f * pr.nAB;
+    return 1.0f / w;
+}
+
 float slice_base(const proj_t& p, uint32_t tiles_y)
 {
     return 1.0f + (2.0f * p.tan_half) / (float) tiles_y;
@@ -65,9 +73,10 @@ float slice_base(const proj_t& p, uint32_t tiles_y)
 
 uint32_t slice_of(float z, float near_plane, float a)
 {
-    const double k = std::floor(std::log((double) z / (double) near_plane) / std::log((double) a));
-    if (!(k >= 0.0)) return 0u;                 // CANONICAL: uint(negative or NaN) -> 0
-    if (k > 4294967295.0) return 0xFFFFFFFFu;
+    // find_unique_clusters.comp:65 as GLSL types it: every operand and operation is fp32 (libm logf; division rounded once)
+    const float k = std::floor(logf(z / near_plane) / logf(a));
+    if (!(k >= 0.0f)) return 0u;                // CANONICAL: uint(negative or NaN) -> 0
+    if (k > 4294967040.0f) return 0xFFFFFFFFu;
     return (uint32_t) k;
 }
 
@@ -118,6 +127,78 @@ uint32_t discretize_normal(float nx, float ny, float nz)
     return (face_idx * 9u + dx * 3u + dy) & 0x3Fu;
 }
 
+// point_light_position_to_view_space.comp:30 — mat4 * vec4(p.xyz, 1) as ((m0*x + m1*y) + (m2*z + m3*1))
+void to_view_space(const float* view, const float* p, float* out)
+{
+    for (int c = 0; c < 4; c++)
+    {
+        const float a = view[0 + c] * p[0] + view[4 + c] * p[1];
+        const float b = view[8 + c] * p[2] + view[12 + c] * 1.0f;
+        out[c] = a + b;
+    }
+}
+
+// discretize_point_light_positions.comp:31-39
+uint32_t morton_code(const float* vp, const float* mn, const float* mx)
+{
+    uint32_t q[3];
+    for (int c = 0; c < 3; c++)
+    {
+        const float t = (vp[c] - mn[c]) / (mx[c] - mn[c]) * 32.0f;
+        const float f = std::floor(t);
+        q[c] = f >= 0.0f ? (uint32_t) f : 0u; // CANONICAL v: NaN (max == min) -> bin 0
+    }
+    uint32_t code = 0;
+    for (uint32_t b = 0; b < 5; b++)
+    {
+        code |= ((q[0] >> b) & 1u) << (b * 3);
+        code |= ((q[1] >> b) & 1u) << (b * 3 + 1);
+        code |= ((q[2] >> b) & 1u) << (b * 3 + 2);
+    }
+    return code;
+}
+
+// init_light_array_bvh.comp:52-53
+void light_leaf_box(const float* vp, float intensity, float* mn, float* mx)
+{
+    for (int c = 0; c < 3; c++) { mn[c] = vp[c] - intensity; mx[c] = vp[c] + intensity; }
+}
+
+// assign_lights.comp:84-94, (min_1, max_1) = cluster corners as written, (min_2, max_2) = node box
+bool test_aabb_aabb(const float* min1, const float* max1, const float* min2, const float* max2)
+{
+    return max1[0] >= min2[0] && min1[0] <= max2[0] && max1[1] >= min2[1] && min1[1] <= max2[1] && max1[2] >= min2[2] && min1[2] <= max2[2];
+}
+
+// assign_lights.comp:97-102
+bool test_sphere_aabb(const float* o, float r, const float* amin, const float* amax)
+{
+    float q[3];
+    for (int k = 0; k < 3; k++)
+    {
+        const float m = amax[k] < o[k] ? amax[k] : o[k];      // min(sphere_o, aabb_max)
+        q[k] = amin[k] < m ? m : amin[k];                     // max(aabb_min, .)
+        q[k] = q[k] - o[k];
+    }
+    const float d = std::sqrt((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]);
+    return d < r;
+}
+
+// get_node_address, assign_lights.comp:108-119 (exp2 of small integers is exact: integer powers of 32)
+int64_t node_address(uint32_t bvh_root_index, uint32_t level, const uint32_t* overlaps)
+{
+    int64_t sum = 0, p32 = 1;
+    for (uint32_t e = 0; e <= level + 1; e++) { sum += p32; p32 *= 32; }
+    int64_t addr = (int64_t) bvh_root_index - (sum - 1);
+    for (uint32_t i = 0; i < level; i++)
+    {
+        int64_t w = 1;
+        for (uint32_t e = 0; e < level - i; e++) w *= 32;
+        addr += w * (int64_t) __builtin_ctz(overlaps[i]);
+    }
+    return addr;
+}
+
 } // namespace
 
 extern "C" {
@@ -129,16 +210,7 @@ void oracle_construct_point_light_bvh(const float* positions, const float* light
                                       float* view_pos, bvh_node* nodes, uint32_t* sorted_pairs)
 {
     // K9: point_light_position_to_view_space.comp:30
-    for (uint32_t i = 0; i < L; i++)
-    {
-        const float x = positions[4 * i], y = positions[4 * i + 1], z = positions[4 * i + 2];
-        for (int c = 0; c < 4; c++)
-        {
-            const float a = view[0 + c] * x + view[4 + c] * y;
-            const float b = view[8 + c] * z + view[12 + c] * 1.0f;
-            view_pos[4 * i + c] = a + b;
-        }
-    }
+    for (uint32_t i = 0; i < L; i++) to_view_space(view, positions + 4 * (size_t) i, view_pos + 4 * (size_t) i);
     // clustered_shading.cpp:141-178: reduce<vec4,max>, reduce<vec4,min> over next_pow2(L) slots, result = last slot
     const uint32_t P = oracle_round_to_next_power_of_2(L);
     std::vector<float> tree((size_t) P * 4);
@@ -151,21 +223,7 @@ void oracle_construct_point_light_bvh(const float* positions, const float* light
     std::vector<uint32_t> pairs((size_t) L * 2);
     for (uint32_t i = 0; i < L; i++)
     {
-        uint32_t q[3];
-        for (int c = 0; c < 3; c++)
-        {
-            const float t = (view_pos[4 * i + c] - mn[c]) / (mx[c] - mn[c]) * 32.0f;
-            const float f = std::floor(t);
-            q[c] = f >= 0.0f ? (uint32_t) f : 0u; // CANONICAL v: NaN (max == min) -> bin 0
-        }
-        uint32_t code = 0;
-        for (uint32_t b = 0; b < 5; b++)
-        {
-            code |= ((q[0] >> b) & 1u) << (b * 3);
-            code |= ((q[1] >> b) & 1u) << (b * 3 + 1);
-            code |= ((q[2] >> b) & 1u) << (b * 3 + 2);
-        }
-        pairs[2 * (size_t) i] = code;
+        pairs[2 * (size_t) i] = morton_code(view_pos + 4 * (size_t) i, mn, mx);
         pairs[2 * (size_t) i + 1] = i;
     }
     // bucket sort (CANONICAL i: ties keep input order)
@@ -180,12 +238,7 @@ void oracle_construct_point_light_bvh(const float* positions, const float* light
         if (i < L)
         {
             const uint32_t l = sorted_pairs[2 * (size_t) i + 1];
-            const float r = lights[4 * (size_t) l + 3];
-            for (int c = 0; c < 3; c++)
-            {
-                nd.mn[c] = view_pos[4 * (size_t) l + c] - r;
-                nd.mx[c] = view_pos[4 * (size_t) l + c] + r;
-            }
+            light_leaf_box(view_pos + 4 * (size_t) l, lights[4 * (size_t) l + 3], nd.mn, nd.mx);
             nd.next = LEAF;
         }
         else
@@ -218,10 +271,7 @@ uint32_t oracle_find_unique_clusters(const float* depth, const uint16_t* normals
             {
                 const uint32_t x = ((i << 5) + (t & 31)) % W, y = ((j << 5) + (t >> 5)) % H;
                 const float d = depth[(size_t) y * W + x];
-                // frag_pos = inverse(P) * (., ., d, 1); frag_pos /= frag_pos.w -> z = 1 / w'
-                const float w = d * pr.iB + 1.0f * pr.nAB;
-                const float z = 1.0f / w;
-                const uint32_t k = slice_of(z, cam->near_plane, a);
+                const uint32_t k = slice_of(view_z(d, pr), cam->near_plane, a);
                 uint32_t nb = 0xFFFFFFFFu;
                 if (normals)
                 {
@@ -247,7 +297,8 @@ uint32_t oracle_find_unique_clusters(const float* depth, const uint16_t* normals
 
 // ---- a8 ------------------------------------------------------------------------------------------------------------
 // clustered_shading.glsl:72-110 — cluster "min/max" corners exactly as written (NOT component-wise ordered)
-static void cluster_aabb(uint32_t ci, uint32_t cj, uint32_t ck, uint32_t Tx, uint32_t Ty, const camera_t& cam,
+namespace {
+void cluster_aabb(uint32_t ci, uint32_t cj, uint32_t ck, uint32_t Tx, uint32_t Ty, const camera_t& cam,
                          const proj_t& pr, float a, float* cmin, float* cmax)
 {
     const float tx = (float) Tx, ty = (float) Ty;
@@ -270,6 +321,7 @@ static void cluster_aabb(uint32_t ci, uint32_t cj, uint32_t ck, uint32_t Tx, uin
     const float s0 = near_k / d0[2], s1 = far_k / d1[2];
     for (int c = 0; c < 3; c++) { cmin[c] = s0 * d0[c]; cmax[c] = s1 * d1[c]; }
 }
+} // namespace
 
 // assign_lights.comp:121-241 + clustered_shading.cpp:473-690.
 // counts/offsets: uint[max_keys] (offsets = exclusive scan of counts over all max_keys slots);
@@ -295,19 +347,6 @@ uint64_t oracle_assign_lights(uint32_t W, uint32_t H, const camera_t* cam, const
         cluster_aabb(key & 0xFFu, (key >> 8) & 0xFFu, (key >> 16) & 0x3FFu, Tx, Ty, *cam, pr, a, cmin, cmax);
         // the state machine of assign_lights.comp:133-239 is a depth-first walk, lowest set bit first
         uint32_t overlaps[8] = {0};
-        auto node_address = [&](uint32_t level) {
-            // get_node_address, assign_lights.comp:108-119
-            int64_t sum = 0, p32 = 1;
-            for (uint32_t e = 0; e <= level + 1; e++) { sum += p32; p32 *= 32; }
-            int64_t addr = (int64_t) bvh_root_index - (sum - 1);
-            for (uint32_t i = 0; i < level; i++)
-            {
-                int64_t w = 1;
-                for (uint32_t e = 0; e < level - i; e++) w *= 32;
-                addr += w * (int64_t) __builtin_ctz(overlaps[i]);
-            }
-            return (uint32_t) addr;
-        };
         uint32_t level = 0;
         int state = 2;
         std::vector<uint32_t>& out = lists[c];
@@ -326,7 +365,7 @@ uint64_t oracle_assign_lights(uint32_t W, uint32_t H, const camera_t* cam, const
             }
             else
             {
-                const uint32_t addr = node_address(level);
+                const uint32_t addr = (uint32_t) node_address(bvh_root_index, level, overlaps);
                 if (level < levels - 1)
                 {
                     uint32_t mask = 0;
@@ -334,9 +373,7 @@ uint64_t oracle_assign_lights(uint32_t W, uint32_t H, const camera_t* cam, const
                     {
                         const bvh_node& n = bvh[addr + t];
                         if (n.next == INVALID) continue;
-                        const bool ov = cmax[0] >= n.mn[0] && cmin[0] <= n.mx[0] && cmax[1] >= n.mn[1] && cmin[1] <= n.mx[1] &&
-                                        cmax[2] >= n.mn[2] && cmin[2] <= n.mx[2];
-                        if (ov) mask |= 1u << t;
+                        if (test_aabb_aabb(cmin, cmax, n.mn, n.mx)) mask |= 1u << t;
                     }
                     overlaps[level] = mask;
                     if (mask == 0) state = 1;
@@ -351,16 +388,7 @@ uint64_t oracle_assign_lights(uint32_t W, uint32_t H, const camera_t* cam, const
                         const bvh_node& n = bvh[addr + t];
                         const uint32_t l = sorted_pairs[2 * (size_t) (addr + t) + 1];
                         const float* o = view_pos + 4 * (size_t) l;
-                        const float r = (n.mx[0] - n.mn[0]) / 2.0f;
-                        float q[3];
-                        for (int k = 0; k < 3; k++)
-                        {
-                            const float m = cmax[k] < o[k] ? cmax[k] : o[k];      // min(o, cmax)
-                            q[k] = cmin[k] < m ? m : cmin[k];                     // max(cmin, .)
-                            q[k] = q[k] - o[k];
-                        }
-                        const float d = std::sqrt((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]);
-                        if (d < r) mask |= 1u << t;
+                        if (test_sphere_aabb(o, (n.mx[0] - n.mn[0]) / 2.0f, cmin, cmax)) mask |= 1u << t;
                     }
                     for (int t = 31; t >= 0; t--)
                         if (mask & (1u << t)) out.push_back(sorted_pairs[2 * (size_t) (addr + t) + 1]);
@@ -380,6 +408,64 @@ uint64_t oracle_assign_lights(uint32_t W, uint32_t H, const camera_t* cam, const
         total += lists[c].size();
     }
     return total;
+}
+
+// ---- the pure functions above, one call per array: what tests/test_clustered_reference.py compares with the reference's own
+// GLSL compiled through oracle/glsl_shim.hpp (oracle/_ref/libvrenref_glsl.so) and with tests/golden/clustered_reference_outputs.npz
+void oracle_projection(const camera_t* cam, float* proj16, float* inverse16)
+{
+    const proj_t p = make_projection(*cam);
+    for (int i = 0; i < 16; i++) proj16[i] = inverse16[i] = 0.0f;
+    proj16[0] = p.m00; proj16[5] = p.m11; proj16[10] = p.m22; proj16[11] = 1.0f; proj16[14] = p.m32;          // camera.cpp:40-50, m[col][row]
+    inverse16[0] = p.i00; inverse16[5] = p.i11; inverse16[11] = p.iB; inverse16[14] = 1.0f; inverse16[15] = p.nAB;   // closed form
+}
+void oracle_discretize_normal(const float* n3, uint32_t count, uint32_t* out)
+{
+    for (uint32_t i = 0; i < count; i++) out[i] = discretize_normal(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]);
+}
+// key of tile (0, 0): slice << 16 | normal bin << 26; normals3 may be NULL (bin 63)
+void oracle_cluster_key(const float* depth, const float* normals3, uint32_t count, uint32_t tiles_y, const camera_t* cam, uint32_t* out_key, float* out_view_z)
+{
+    const proj_t pr = make_projection(*cam);
+    const float a = slice_base(pr, tiles_y);
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float z = view_z(depth[i], pr);
+        const uint32_t nb = normals3 ? discretize_normal(normals3[3 * i], normals3[3 * i + 1], normals3[3 * i + 2]) : 0xFFFFFFFFu;
+        out_key[i] = ((slice_of(z, cam->near_plane, a) & 0x3FFu) << 16) | (nb << 26);
+        out_view_z[i] = z;
+    }
+}
+void oracle_cluster_aabb(const uint32_t* ijk3, uint32_t count, uint32_t tiles_x, uint32_t tiles_y, const camera_t* cam, float* out_min3, float* out_max3)
+{
+    const proj_t pr = make_projection(*cam);
+    const float a = 2.0f * pr.tan_half / (float) tiles_y + 1.0f;
+    for (uint32_t i = 0; i < count; i++)
+        cluster_aabb(ijk3[3 * i], ijk3[3 * i + 1], ijk3[3 * i + 2], tiles_x, tiles_y, *cam, pr, a, out_min3 + 3 * (size_t) i, out_max3 + 3 * (size_t) i);
+}
+void oracle_test_aabb_aabb(const float* b12, uint32_t count, uint8_t* out)
+{
+    for (uint32_t i = 0; i < count; i++) out[i] = test_aabb_aabb(b12 + 12 * (size_t) i, b12 + 12 * (size_t) i + 3, b12 + 12 * (size_t) i + 6, b12 + 12 * (size_t) i + 9);
+}
+void oracle_test_sphere_aabb(const float* s10, uint32_t count, uint8_t* out)
+{
+    for (uint32_t i = 0; i < count; i++) out[i] = test_sphere_aabb(s10 + 10 * (size_t) i, s10[10 * (size_t) i + 3], s10 + 10 * (size_t) i + 4, s10 + 10 * (size_t) i + 7);
+}
+int32_t oracle_get_node_address(uint32_t bvh_root_index, uint32_t level, const uint32_t* level_overlaps4)
+{
+    return (int32_t) node_address(bvh_root_index, level, level_overlaps4);
+}
+void oracle_morton_code(const float* pos3, uint32_t count, const float* mn, const float* mx, uint32_t* out)
+{
+    for (uint32_t i = 0; i < count; i++) out[i] = morton_code(pos3 + 3 * (size_t) i, mn, mx);
+}
+void oracle_position_to_view_space(const float* view16, const float* pos4, uint32_t count, float* out4)
+{
+    for (uint32_t i = 0; i < count; i++) to_view_space(view16, pos4 + 4 * (size_t) i, out4 + 4 * (size_t) i);
+}
+void oracle_light_leaf_box(const float* view_pos4, const float* intensity, uint32_t count, float* out_min3, float* out_max3)
+{
+    for (uint32_t i = 0; i < count; i++) light_leaf_box(view_pos4 + 4 * (size_t) i, intensity[i], out_min3 + 3 * (size_t) i, out_max3 + 3 * (size_t) i);
 }
 
 // ---- n2: depth-buffer pyramid -------------------------------------------------------------------------------------------

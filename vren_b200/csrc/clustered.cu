@@ -60,17 +60,19 @@ proj_consts make_proj(const vrenb200_camera& c)
     return p;
 }
 
-// slice index of a view-space depth: floor(log(z/near)/log(a)) in double (find_unique_clusters.comp:65)
+// slice index of a view-space depth: uint(floor(log(z / near) / log(a))) with every operation in fp32, as the shader types
+// it (find_unique_clusters.comp:65); log = the host's logf.  Monotone in z for every camera tried (all floats of
+// [near/2, 2 far] checked for 3..135 tile rows), which is what the threshold table below relies on.
 uint32_t slice_of(float z, float near_plane, float a)
 {
-    const double k = std::floor(std::log((double) z / (double) near_plane) / std::log((double) a));
-    if (!(k >= 0.0)) return 0u;
-    if (k > 4294967295.0) return 0xFFFFFFFFu;
+    const float k = std::floor(logf(z / near_plane) / logf(a));
+    if (!(k >= 0.0f)) return 0u;
+    if (k > 4294967040.0f) return 0xFFFFFFFFu;
     return (uint32_t) k;
 }
 
 // thresholds[k] = smallest positive float z whose slice is >= k (k >= 1); the device finds the slice by comparing
-// against this table, so it agrees with the double-precision formula for every float z by construction.
+// against this table, so it agrees with the host formula above for every float z by construction.
 constexpr uint32_t kMaxSlices = 16384;
 
 struct slice_table
@@ -131,13 +133,30 @@ const slice_table& get_slice_table(float near_plane, float a)
     tab.a = a;
     tab.thresholds.clear();
     tab.thresholds.push_back(0.0f);
-    const uint32_t kmax = std::min<uint32_t>(slice_of(3.4028234e38f, near_plane, a), kMaxSlices - 2);
+    // zfin = the largest z whose slice is a number: beyond it z / near overflows to +inf in fp32 and uint(floor(inf)) is taken
+    // as 0xFFFFFFFF (key bits 0x3FF).  Bisection over the float bit patterns (slice_of is monotone).
+    uint32_t lo = 0x00800000u, hi = 0x7F800000u;   // slice_of(bits lo) finite, slice_of(+inf) = 0xFFFFFFFF
+    auto as_float = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+    while (hi - lo > 1)
+    {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (slice_of(as_float(mid), near_plane, a) == 0xFFFFFFFFu) hi = mid; else lo = mid;
+    }
+    const float zfin = as_float(lo);
+    const uint32_t kfin = slice_of(zfin, near_plane, a);
+    const uint32_t kmax = std::min<uint32_t>(kfin, kMaxSlices - 2);
     for (uint32_t k = 1; k <= kmax; k++)
     {
-        float c = (float) ((double) near_plane * std::pow((double) a, (double) k));
+        float c = std::min((float) ((double) near_plane * std::pow((double) a, (double) k)), zfin);
         while (slice_of(c, near_plane, a) < k) c = std::nextafterf(c, INFINITY);
         while (slice_of(std::nextafterf(c, 0.0f), near_plane, a) >= k) c = std::nextafterf(c, 0.0f);
         tab.thresholds.push_back(c);
+    }
+    // the overflow region maps to the next index whose low 10 bits are all ones (what 0xFFFFFFFF & 0x3FF leaves in the key)
+    if (kfin == kmax && kmax + 1024 < kMaxSlices)
+    {
+        const float over = as_float(hi);
+        do tab.thresholds.push_back(over); while (((tab.thresholds.size() - 1) & 0x3FFu) != 0x3FFu);
     }
     return tab;
 }
@@ -273,8 +292,8 @@ find_unique_clusters_kernel(const __grid_constant__ CUtensorMap depth_map, const
         uint32_t k = 0;
         if (z > 0.0f)
         {
-            const float zc = fminf(z, 3.4028234e38f);
-            int g = (int) (__log2f(zc * prm.inv_near) * prm.inv_log2a);
+            const float zc = z;   // +inf included: it lands in the table's overflow run
+            int g = (int) fminf(__log2f(zc * prm.inv_near) * prm.inv_log2a, 65536.0f);
             g = max(0, min(g, (int) prm.table_len - 1));
             while (g > 0 && zc < __ldg(&thresholds[g])) g--;
             while (g + 1 < (int) prm.table_len && zc >= __ldg(&thresholds[g + 1])) g++;
@@ -441,6 +460,25 @@ __device__ __forceinline__ void cluster_aabb(uint32_t key, const assign_params& 
     }
 }
 
+// test_aabb_aabb(cluster_min, cluster_max, node._min, node._max), assign_lights.comp:84-94; INVALID nodes never overlap
+__device__ __forceinline__ bool node_overlaps(const float* cmin, const float* cmax, const float4& lo, const float4& hi)
+{
+    return __float_as_uint(lo.w) != kInvalid && cmax[0] >= lo.x && cmin[0] <= hi.x && cmax[1] >= lo.y && cmin[1] <= hi.y &&
+           cmax[2] >= lo.z && cmin[2] <= hi.z;
+}
+
+// test_sphere_aabb(light centre, radius, cluster_min, cluster_max), assign_lights.comp:97-102, on the leaf record
+// {centre.xyz, T}: T = sq_threshold(radius), so "length(p - o) < radius" == "dot(p - o, p - o) < T" bit for bit
+__device__ __forceinline__ bool leaf_hits(const float* cmin, const float* cmax, const float4& o)
+{
+    // min/max pick identical values as the GLSL ternaries (only the sign of a zero may differ, squared away)
+    const float q0 = __fsub_rn(fmaxf(cmin[0], fminf(o.x, cmax[0])), o.x);
+    const float q1 = __fsub_rn(fmaxf(cmin[1], fminf(o.y, cmax[1])), o.y);
+    const float q2 = __fsub_rn(fmaxf(cmin[2], fminf(o.z, cmax[2])), o.z);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), __fmul_rn(q2, q2));
+    return d2 < o.w;
+}
+
 constexpr int kAssignThreads = 256;
 constexpr int kAssignWarps = kAssignThreads / 32;
 constexpr int kHitCap = 96;    // leaf groups with hits remembered per cluster before falling back to a second walk
@@ -484,8 +522,7 @@ struct walker
         {
             // test_aabb_aabb(cluster_min, cluster_max, node.min, node.max), assign_lights.comp:84-94
             const float4 lo = c.bvh[2 * (size_t) addr], hi = c.bvh[2 * (size_t) addr + 1];
-            const bool overlap = __float_as_uint(lo.w) != kInvalid && c.cmax[0] >= lo.x && c.cmin[0] <= hi.x && c.cmax[1] >= lo.y &&
-                                 c.cmin[1] <= hi.y && c.cmax[2] >= lo.z && c.cmin[2] <= hi.z;
+            const bool overlap = node_overlaps(c.cmin, c.cmax, lo, hi);
             unsigned mask = __ballot_sync(kFullMask, overlap);
             c.stat_nodes += 32;
             while (mask != 0)
@@ -503,13 +540,7 @@ struct walker
             bool hit = false;
             if (addr < c.light_count)
             {
-                const float4 o = c.spheres[addr];
-                // min/max pick identical values as the GLSL ternaries (only the sign of a zero may differ, squared away)
-                const float q0 = __fsub_rn(fmaxf(c.cmin[0], fminf(o.x, c.cmax[0])), o.x);
-                const float q1 = __fsub_rn(fmaxf(c.cmin[1], fminf(o.y, c.cmax[1])), o.y);
-                const float q2 = __fsub_rn(fmaxf(c.cmin[2], fminf(o.z, c.cmax[2])), o.z);
-                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), __fmul_rn(q2, q2));
-                hit = d2 < o.w;
+                hit = leaf_hits(c.cmin, c.cmax, c.spheres[addr]);
             }
             const unsigned mask = __ballot_sync(kFullMask, hit);
             c.stat_leaves += 32;
@@ -703,6 +734,35 @@ int launch_assign(cudaStream_t s, const uint32_t* cluster_keys, const uint32_t* 
     return check_launch();
 }
 
+// Diagnostics: the device functions above evaluated one element per thread (vrenb200_cluster_tests)
+__global__ void __launch_bounds__(256)
+cluster_tests_kernel(const uint32_t* __restrict__ keys, uint32_t count, assign_params prm, const float* __restrict__ near_table,
+                     float* out_min3, float* out_max3, const float* __restrict__ node_boxes6, const float* __restrict__ spheres4,
+                     uint8_t* out_flags)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= count) return;
+    float3x cmin, cmax;
+    cluster_aabb(keys[i], prm, near_table, cmin, cmax);
+    if (out_min3 != nullptr)
+    {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { out_min3[3 * (size_t) i + k] = cmin.v[k]; out_max3[3 * (size_t) i + k] = cmax.v[k]; }
+    }
+    uint32_t flags = 0;
+    if (node_boxes6 != nullptr)
+    {
+        const float* b = node_boxes6 + 6 * (size_t) i;
+        if (node_overlaps(cmin.v, cmax.v, make_float4(b[0], b[1], b[2], __uint_as_float(0u)), make_float4(b[3], b[4], b[5], 0.0f))) flags |= 1u;
+    }
+    if (spheres4 != nullptr)
+    {
+        const float* sp = spheres4 + 4 * (size_t) i;
+        if (leaf_hits(cmin.v, cmax.v, make_float4(sp[0], sp[1], sp[2], sq_threshold(sp[3])))) flags |= 2u;
+    }
+    if (out_flags != nullptr) out_flags[i] = (uint8_t) flags;
+}
+
 // ---- tensor maps ----------------------------------------------------------------------------------------------------
 using encode_fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -735,10 +795,50 @@ bool make_tile_map(CUtensorMap* map, const void* base, uint32_t width, uint32_t 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+assign_params make_assign_params(uint32_t width, uint32_t height, const vrenb200_camera& camera)
+{
+    const proj_consts pc = make_proj(camera);
+    assign_params prm{};
+    prm.tiles_x = (width + 31) / 32; prm.tiles_y = (height + 31) / 32;
+    prm.i00 = pc.i00; prm.i11 = pc.i11; prm.nAB = pc.nAB;
+    prm.near_plane = camera.near_plane;
+    prm.a = 2.0f * pc.tan_half / (float) prm.tiles_y + 1.0f;            // clustered_shading.glsl:96
+    return prm;
+}
+
+// near_k = near * pow(a, k), k < 1024 (clustered_shading.glsl:97) evaluated on the host with powf; cached per device
+const float* get_near_table(const vrenb200_camera& camera, float a)
+{
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    const device_table* cached = find_device_table(1, camera.near_plane, a);
+    if (cached == nullptr)
+    {
+        float near_host[1024];
+        for (int k = 0; k < 1024; k++) near_host[k] = camera.near_plane * powf(a, (float) k);
+        cached = add_device_table(1, camera.near_plane, a, near_host, 1024);
+        if (cached == nullptr) return nullptr;
+    }
+    return cached->data;
+}
+
 } // namespace
 } // namespace vrenb200
 
 using namespace vrenb200;
+
+extern "C" int vrenb200_cluster_tests(vrenb200_stream_t stream, uint32_t width, uint32_t height, const vrenb200_camera* camera,
+                                      const uint32_t* cluster_keys, uint32_t count, float* out_min3, float* out_max3,
+                                      const float* node_boxes6, const float* spheres4, uint8_t* out_flags)
+{
+    if (!camera || (count > 0 && !cluster_keys) || ((out_min3 == nullptr) != (out_max3 == nullptr))) return VRENB200_EINVAL_ARG;
+    if (count == 0) return VRENB200_OK;
+    const assign_params prm = make_assign_params(width, height, *camera);
+    const float* near_table = get_near_table(*camera, prm.a);
+    if (near_table == nullptr) return VRENB200_ECUDA;
+    cluster_tests_kernel<<<(count + 255) / 256, 256, 0, as_stream(stream)>>>(cluster_keys, count, prm, near_table, out_min3, out_max3,
+                                                                               node_boxes6, spheres4, out_flags);
+    return check_launch();
+}
 
 extern "C" size_t vrenb200_find_unique_clusters_scratch_bytes(uint32_t width, uint32_t height)
 {
@@ -842,30 +942,11 @@ extern "C" int vrenb200_assign_lights(vrenb200_stream_t stream,
     const uint32_t levels = vrenb200_calc_bvh_level_count(light_count);
     if (levels > (uint32_t) kMaxBvhLevels) return VRENB200_ELIMIT;
 
-    const uint32_t tiles_x = (width + 31) / 32, tiles_y = (height + 31) / 32;
-    const proj_consts pc = make_proj(*camera);
-    assign_params prm{};
-    prm.tiles_x = tiles_x; prm.tiles_y = tiles_y;
-    prm.i00 = pc.i00; prm.i11 = pc.i11; prm.nAB = pc.nAB;
-    prm.near_plane = camera->near_plane;
-    prm.a = 2.0f * pc.tan_half / (float) tiles_y + 1.0f;            // clustered_shading.glsl:96
+    assign_params prm = make_assign_params(width, height, *camera);
     prm.bvh_root = bvh_root_index; prm.levels = levels; prm.light_count = light_count;
     prm.max_keys = max_keys; prm.max_assigned = max_assigned;
-
-    // near_k = near * pow(a, k), k < 1024 (clustered_shading.glsl:97) evaluated on the host with powf
-    const float* near_table = nullptr;
-    {
-        std::lock_guard<std::mutex> lock(g_table_mutex);
-        const device_table* cached = find_device_table(1, camera->near_plane, prm.a);
-        if (cached == nullptr)
-        {
-            float near_host[1024];
-            for (int k = 0; k < 1024; k++) near_host[k] = camera->near_plane * powf(prm.a, (float) k);
-            cached = add_device_table(1, camera->near_plane, prm.a, near_host, 1024);
-            if (cached == nullptr) return VRENB200_ECUDA;
-        }
-        near_table = cached->data;
-    }
+    const float* near_table = get_near_table(*camera, prm.a);
+    if (near_table == nullptr) return VRENB200_ECUDA;
     char* sp = static_cast<char*>(scratch);
     assign_state* state = reinterpret_cast<assign_state*>(sp + 1024 * sizeof(float));
     uint32_t* alloc = reinterpret_cast<uint32_t*>(sp + 1024 * sizeof(float) + 256);

@@ -129,6 +129,17 @@ __device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t* p)
     return v;
 }
 
+// smallest float s >= 0 with sqrt_rn(s) >= r.  sqrt_rn is monotone, so for every s >= 0:
+//   sqrt_rn(s) < r  <=>  s < sq_threshold(r)      (r <= 0 or NaN: never true -> 0)
+__device__ __forceinline__ float sq_threshold(float r)
+{
+    if (!(r > 0.0f)) return 0.0f;
+    uint32_t t = __float_as_uint(__fmul_rn(r, r));          // non-negative floats order like their bit patterns
+    while (t > 0 && __fsqrt_rn(__uint_as_float(t)) >= r) t--;
+    while (t < 0x7F800000u && __fsqrt_rn(__uint_as_float(t)) < r) t++;
+    return __uint_as_float(t);
+}
+
 #endif // __CUDACC__
 
 } // namespace vrenb200

@@ -104,6 +104,7 @@ def load() -> C.CDLL:
 
 _vp, _u32, _sz, _i32 = C.c_void_p, C.c_uint32, C.c_size_t, C.c_int
 _LATE_SIGS = [
+    ("vrenb200_cluster_tests", _i32, (_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp)),
     ("vrenb200_light_list_hash_scratch_bytes", _sz, (_u32,)),
     ("vrenb200_light_list_hash", _i32, (_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _sz)),
     ("vrenb200_depth_pyramid_level_count", _u32, (_u32, _u32)),
@@ -315,6 +316,21 @@ def assign_lights(width: int, height: int, camera: Camera, keys, disp, bvh, ligh
                                      light_count, _ptr(index_buffer), _ptr(view_pos), _ptr(indices), max_assigned,
                                      _ptr(counts), _ptr(offsets), _ptr(status), _ptr(scratch), sb), "vrenb200_assign_lights")
     return counts, offsets, indices, status
+
+
+def cluster_tests(width: int, height: int, camera: Camera, keys, node_boxes=None, spheres=None):
+    """diagnostics of a8 (vrenb200_cluster_tests): keys int32[n] -> (corner_min [n,3], corner_max [n,3], flags uint8[n]);
+    node_boxes float32 [n,6] / spheres float32 [n,4] device tensors or None"""
+    import torch
+
+    lib = load()
+    n = keys.numel()
+    cmin = torch.zeros(n, 3, dtype=torch.float32, device=keys.device)
+    cmax = torch.zeros(n, 3, dtype=torch.float32, device=keys.device)
+    flags = torch.zeros(n, dtype=torch.uint8, device=keys.device)
+    check(lib.vrenb200_cluster_tests(_stream(), width, height, C.byref(camera), _ptr(keys), n, _ptr(cmin), _ptr(cmax),
+                                     _ptr(node_boxes), _ptr(spheres), _ptr(flags)), "vrenb200_cluster_tests")
+    return cmin, cmax, flags
 
 
 def depth_pyramid(depth):
