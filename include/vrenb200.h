@@ -4,10 +4,8 @@
  * Every entry point is what a binding from the reference (loryruta/vren, C++/Vulkan) would call in
  * place of recording Vulkan dispatches.  All `*_run`-style calls are:
  *   - asynchronous on the given CUDA stream (the analogue of "record into a VkCommandBuffer"),
- *   - allocation-free and host-sync-free (caller owns inputs, outputs and scratch); the one exception is the 0.6 ms
- *     device probe the first radix / bucket sort on a device runs on a private stream (see
- *     vrenb200_radix_sort_set_ranking; never during a stream capture),
- *   - re-entrant: no global mutable state apart from the tuning hooks (`*_set_*`) and the cached probe result.
+ *   - allocation-free and host-sync-free (caller owns inputs, outputs and scratch),
+ *   - re-entrant: no global mutable state; how a call runs is an argument of the call (vrenb200_sort_config).
  * Pointers are raw device pointers unless the name ends in `_host`.  Lengths are ELEMENTS,
  * sizes are BYTES.  Return value: 0 on success, one of VRENB200_E* otherwise.
  *
@@ -88,6 +86,34 @@ int vrenb200_blelloch_downsweep_u32(vrenb200_stream_t stream, uint32_t* buf, uin
                                     int clear_last);
 
 /* ---- a3: radix sort ---------------------------------------------------------------------------- */
+/* How a sort call runs (all fields 0 = the library's defaults; pass NULL for the same).  Part of the call, not of the process:
+ * there is no global selection state.  The defaults can be overridden through the environment, read once:
+ * VRENB200_SORT_RANKING=match|verified|sampled|atomic, VRENB200_SORT_TILE_IDS=block|ticket. */
+enum {
+    VRENB200_RANKING_AUTO = 0,               /* = ATOMIC_VERIFIED */
+    VRENB200_RANKING_MATCH = 1,              /* warp-ballot digit match: order by construction */
+    VRENB200_RANKING_ATOMIC_VERIFIED = 2,    /* one returning shared atomic per pair; EVERY row is checked against the ballot match
+                                                off the critical path, and a pass that fails the check is repeated by the match
+                                                kernel before the next pass starts: correct whatever order the hardware serves
+                                                same-address lanes in (PTX does not specify it) */
+    VRENB200_RANKING_ATOMIC_SAMPLED = 3,     /* same, one row in eight checked */
+    VRENB200_RANKING_ATOMIC_UNVERIFIED = 4,  /* no check: relies on ascending lane order of same-address shared atomics */
+    VRENB200_RANKING_SELFTEST_REDO = 5       /* tests: the verified kernels report a failed check and write nothing, so the
+                                                result is what the repeat pass alone produces */
+};
+enum {
+    VRENB200_TILE_IDS_AUTO = 0,              /* = BLOCK_INDEX, or TICKET under MPS / compute-sanitizer / a debugger (environment) */
+    VRENB200_TILE_IDS_BLOCK_INDEX = 1,       /* tile = block index: assumes CTAs of a 1-D grid start in index order (as CUB's
+                                                decoupled-look-back scan does) */
+    VRENB200_TILE_IDS_TICKET = 2             /* tile = value of an atomic counter taken when the CTA starts: forward progress of
+                                                the look-back without any assumption about the dispatch order */
+};
+typedef struct vrenb200_sort_config {
+    int ranking;
+    int tile_ids;
+    int variant;     /* 0 = automatic; else 1-based index into the kernel table (vrenb200_radix_sort_variant_name) */
+} vrenb200_sort_config;
+
 /* one scratch blob holds the ping-pong buffers, digit histograms and look-back state. n < 2^30 */
 size_t vrenb200_radix_sort_scratch_bytes(uint32_t n, int with_values);
 /* ascending sort of uint32 keys, result in `keys` (radix_sort.cpp:149-337 semantics, any n>=0) */
@@ -96,6 +122,13 @@ int vrenb200_radix_sort_keys(vrenb200_stream_t stream, uint32_t* keys, uint32_t 
 /* key-value extension: stable ascending by key, result in keys/values */
 int vrenb200_radix_sort_pairs(vrenb200_stream_t stream, uint32_t* keys, uint32_t* values, uint32_t n,
                               void* scratch, size_t scratch_bytes);
+typedef struct vrenb200_sort_profile vrenb200_sort_profile;   /* CUDA events around every kernel of one sort */
+/* the general form: values may be NULL (keys only), cfg may be NULL (defaults), prof may be NULL */
+int vrenb200_radix_sort_ex(vrenb200_stream_t stream, uint32_t* keys, uint32_t* values, uint32_t n,
+                           void* scratch, size_t scratch_bytes, const vrenb200_sort_config* cfg, vrenb200_sort_profile* prof);
+/* device word inside `scratch`, != 0 after a sort in which the ranking check failed (and the repeat pass ran); read it after
+ * the stream has been synchronised */
+const uint32_t* vrenb200_radix_sort_violation_word(void* scratch, uint32_t n, int with_values);
 /* sizes of the two scratch buffers of the reference-shaped call (radix_sort.cpp:124-147 are SMALLER;
  * the facade's create_scratch_buffer_1/2 use these) */
 size_t vrenb200_radix_sort_scratch_buffer_1_bytes(uint32_t n);
@@ -115,7 +148,7 @@ int vrenb200_radix_sort_pairs_host_async(vrenb200_stream_t stream, const uint32_
                                          uint32_t* keys_out_host, uint32_t* values_out_host, uint32_t n,
                                          void* dev_work, size_t dev_work_bytes);
 
-/* building blocks of the multi-GPU sort: all four 256-bin digit histograms of the keys
+/* building blocks of the NCCL form of the multi-GPU sort: all four 256-bin digit histograms of the keys
  * (hist_out: device uint32[4][256]) and a stable sort restricted to the digits [first_pass, first_pass+num_passes) */
 int vrenb200_radix_digit_histograms(vrenb200_stream_t stream, const uint32_t* keys, uint32_t n, uint32_t* hist_out);
 size_t vrenb200_radix_sort_range_scratch_bytes(uint32_t n);
@@ -123,40 +156,51 @@ int vrenb200_radix_sort_pairs_range(vrenb200_stream_t stream, uint32_t* keys, ui
                                     uint32_t* alt_values, uint32_t n, int first_pass, int num_passes,
                                     void* scratch, size_t scratch_bytes, int* result_in_alt);
 
-/* histogram of the most significant byte only: hist_out device uint32[256] */
-int vrenb200_radix_top_digit_histogram(vrenb200_stream_t stream, const uint32_t* keys, uint32_t n, uint32_t* hist_out);
-/* fused partition + exchange of the multi-GPU sort: one onesweep pass that partitions the pairs by DESTINATION RANK
- * (rank_of[most significant byte]) and stores them, in input order, at kptr[rank] / vptr[rank] — plain stores on
- * (possibly peer-mapped) addresses.  dest_table: device struct { uint64 kptr[32]; uint64 vptr[32]; uint8 rank_of[256]; }.
- * scratch: vrenb200_radix_sort_range_scratch_bytes(n) */
-int vrenb200_radix_partition_scatter(vrenb200_stream_t stream, const uint32_t* keys, const uint32_t* values, uint32_t n,
-                                     const uint64_t* dest_table, void* scratch, size_t scratch_bytes);
-
-/* tuning / measurement hooks (not part of the reference surface) */
-int vrenb200_radix_sort_set_variant(int variant);
-/* Ranking step of the default pass kernels. 0 (default): automatic — the first sort on a device runs a one-time probe
- * (~0.2 ms, own stream; skipped while the caller's stream is being captured) of how the device orders the lanes of one
- * shared-memory atomic that hit the same address, and uses the match-free "atomic order" kernels only if the order is
- * ascending by lane (it is on B200); 1: always the ballot-match kernels (order by construction); 2: always atomic order.
- * Environment: VRENB200_SORT_RANKING=auto|match|atomic. Results are identical in every mode the probe accepts. */
-int vrenb200_radix_sort_set_ranking(int mode);
-int vrenb200_radix_sort_ranking_probe(void);   /* 1: ascending lane order on the current device, 0: not */
-const char* vrenb200_radix_sort_selected_variant_name(uint32_t n, int with_values);
-int vrenb200_radix_sort_set_dephase(uint32_t ns, uint32_t rule);   /* DEPHASE variants: start delay of the second CTA of every SM (first wave only) */
-int vrenb200_radix_sort_set_hist_loads(uint32_t loads);   /* histogram kernel: 128-bit loads in flight per thread (2 or 4) */
-int vrenb200_radix_sort_set_prefetch_tiles(uint32_t tiles);   /* PREFETCH_L2 variants: distance of the L2 prefetch, in tiles */
-int vrenb200_radix_partition_set_shape(int shape);   /* exchange pass tile: 0: 256x32, 1: 256x16, 2: 512x16 */
-int vrenb200_scan_set_variant(int variant);
-int vrenb200_scan_set_runahead(int finalize_lag_tiles, int scan_lag_tiles);   /* run-ahead scan kernel with explicit distances */   /* CTA size of the scan kernel: 0: 256, 1: 512, 2: 1024 threads */
+/* reporting: the kernel configuration a sort of n elements would use, and the table behind vrenb200_sort_config::variant */
+const char* vrenb200_radix_sort_selected_variant_name(uint32_t n, int with_values, const vrenb200_sort_config* cfg);
 int vrenb200_radix_sort_num_variants(void);
 const char* vrenb200_radix_sort_variant_name(int variant);
-typedef struct vrenb200_sort_profile vrenb200_sort_profile;   /* CUDA events around every kernel of one sort */
 vrenb200_sort_profile* vrenb200_sort_profile_create(void);
 void vrenb200_sort_profile_destroy(vrenb200_sort_profile* p);
-/* values may be NULL (keys only). ms_out[6] = {histogram, histogram-scan, pass0..pass3}, read after stream sync */
-int vrenb200_radix_sort_pairs_profiled(vrenb200_stream_t stream, uint32_t* keys, uint32_t* values, uint32_t n,
-                                       void* scratch, size_t scratch_bytes, vrenb200_sort_profile* prof);
+/* ms_out[6] = {histogram, histogram-scan, pass0..pass3}, read after stream sync */
 int vrenb200_sort_profile_read(vrenb200_sort_profile* p, float* ms_out);
+
+/* ---- e1: the multi-GPU form of the key-value radix sort (single-device in the reference: radix_sort.cpp:149-337) ----
+ * One context per rank.  Every rank owns a SYMMETRIC region (vrenb200_sharded_sort_symmetric_bytes) that all ranks can address:
+ * peer-mapped device memory (torch symmetric memory, cudaIpc handles, or cudaDeviceEnablePeerAccess inside one process).  The
+ * call is collective — every rank calls it once per sort with its shard — and, like every other entry point, only enqueues:
+ * no NCCL, no host synchronisation, no allocation.  Concatenating the ranks' outputs in rank order gives the stable sort by key
+ * of the concatenation of their inputs.  See vren_b200/csrc/sharded_sort.cu for the pipeline.
+ *   capacity    pairs a rank can receive (its share after the exchange, padded to whole tiles: about n_total / world * 1.25
+ *               + 256 tiles for balanced keys); a plan that does not fit sets status[0] and leaves the output untouched
+ *   rounds      1..8: how many pieces the exchange is cut into; the transfer of a piece overlaps the sorting of the one before
+ *   peer_regions[r]  base of rank r's symmetric region as addressable from THIS rank (256-byte aligned), r = 0..world-1
+ *   local       device scratch of this rank, vrenb200_sharded_sort_local_bytes(max_n, capacity) bytes, 256-byte aligned
+ * create() zeroes this rank's flag words with a synchronous memset: call it on every rank, then synchronise the ranks once
+ * (any barrier) before the first sort.  key_bits (32, 24, 16 or 8): how many low bits of the key take part (16 = the
+ * bucket-sort key of bucket_sort.hpp:15-16; the whole 32-bit word is carried).
+ * status (device uint32[8], valid once the stream has finished the call): {error, pairs in the output, first and one-past-last
+ * value of the partition digit this rank owns, index of the partition digit}; error bit 0: a rank's share exceeds the capacity,
+ * bit 1: a round exceeds its launch bound (retry with rounds = 1 or a larger capacity). */
+typedef struct vrenb200_sharded_sort vrenb200_sharded_sort;
+size_t vrenb200_sharded_sort_symmetric_bytes(uint32_t capacity);
+size_t vrenb200_sharded_sort_local_bytes(uint32_t max_n, uint32_t capacity);
+int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_t rank, uint32_t world, uint32_t max_n, uint32_t capacity,
+                                 uint32_t rounds, void* const* peer_regions, void* local, size_t local_bytes,
+                                 const vrenb200_sort_config* cfg);
+void vrenb200_sharded_sort_destroy(vrenb200_sharded_sort* ctx);
+int vrenb200_sharded_sort_pairs(vrenb200_sharded_sort* ctx, vrenb200_stream_t stream, const uint32_t* keys, const uint32_t* values,
+                                uint32_t n, int key_bits);
+const uint32_t* vrenb200_sharded_sort_out_keys(const vrenb200_sharded_sort* ctx);
+const uint32_t* vrenb200_sharded_sort_out_values(const vrenb200_sharded_sort* ctx);
+const uint32_t* vrenb200_sharded_sort_status(const vrenb200_sharded_sort* ctx);
+
+#ifdef VRENB200_TUNING
+/* tuning builds only (VRENB200_TUNING=1 python -m vren_b200.build): process-global selection of experimental scan kernels.
+ * The release library exports nothing that mutates process-wide state. */
+int vrenb200_scan_set_variant(int variant);
+int vrenb200_scan_set_runahead(int finalize_lag_tiles, int scan_lag_tiles);
+#endif
 
 /* ---- a4: bucket sort (16-bit key counting sort of uvec2) --------------------------------------- */
 /* bucket_sort::get_required_output_buffer_size (bucket_sort.cpp:67-70) */
@@ -166,9 +210,10 @@ size_t vrenb200_bucket_sort_scratch_bytes(uint32_t n);
  * (bucket_sort.cpp:86, bucket_sort_write.comp:32). Ties keep input order (canonical choice). */
 int vrenb200_bucket_sort(vrenb200_stream_t stream, const void* in_pairs, uint32_t n, void* out,
                          void* scratch, size_t scratch_bytes);
-/* tuning hook: from n_min pairs on, the END offsets are found by a search in the sorted output instead of per-key
- * global atomics (default 2^20; 0 = always search, 0xFFFFFFFF = never). Results are identical either way. */
-int vrenb200_bucket_sort_set_search_min(uint32_t n_min);
+/* general form.  end_offsets: -1 automatic (from 2^20 pairs on the END offsets are found by a search in the sorted output instead
+ * of per-key global atomics), 0 atomics, 1 search; results are identical either way.  cfg as for the radix sort (may be NULL). */
+int vrenb200_bucket_sort_ex(vrenb200_stream_t stream, const void* in_pairs, uint32_t n, void* out,
+                            void* scratch, size_t scratch_bytes, const vrenb200_sort_config* cfg, int end_offsets);
 
 /* ---- a5: 32-ary implicit BVH ------------------------------------------------------------------- */
 typedef struct vrenb200_bvh_node {   /* == vren::bvh_node (build_bvh.hpp:8-18), 32 bytes */

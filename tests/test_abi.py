@@ -1,6 +1,8 @@
 """CPU suite: the C-ABI library loads, exports every symbol include/vrenb200.h declares, and its pure-integer helpers
 agree with the oracle's restatement of the reference's double-precision formulas and with the reference KATs.
 No compute call is made here (no GPU needed)."""
+import ctypes as C
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -88,31 +90,32 @@ def test_facade_reference_style_tests(vren):
     assert "ALL PASS" in r.stdout
 
 
-def test_sort_kernel_selection_and_ranking_guard(handle):
-    """host-side selection logic of the sort passes (no kernel is launched).  Without a device that passes the probe the
-    library must pick the ballot-match kernels by itself; the atomic-order kernels are chosen only when forced or probed."""
-    import torch
+def test_sort_kernel_selection(handle):
+    """host-side selection logic of the sort passes (no kernel is launched): the configuration is an ARGUMENT of the call
+    (vrenb200_sort_config), the library keeps no selection state"""
+    def name(n, kv, **cfg):
+        c = lib.SortConfig(**cfg)
+        return handle.vrenb200_radix_sort_selected_variant_name(n, kv, C.addressof(c)).decode()
 
-    name = lambda n, kv: handle.vrenb200_radix_sort_selected_variant_name(n, kv).decode()
-    try:
-        if not torch.cuda.is_available():
-            assert handle.vrenb200_radix_sort_ranking_probe() == 0                 # no device: the guard says no
-            for n, kv in ((1000, 1), (1 << 24, 1), (1 << 24, 0)):
-                assert "RANK_LEADER_ATOMIC" in name(n, kv) and "RANK_ATOMIC_ORDER" not in name(n, kv)
-        assert handle.vrenb200_radix_sort_set_ranking(1) == 0                       # ballot match, whatever the device says
-        assert name(1 << 24, 1).startswith("256x46/") and "RANK_LEADER_ATOMIC" in name(1 << 24, 1)
-        assert name(1 << 24, 0).startswith("256x64/") and name(1000, 1).startswith("256x16/")
-        assert handle.vrenb200_radix_sort_set_ranking(2) == 0                       # atomic order forced
-        assert name(1 << 24, 1).startswith("256x48/") and "RANK_ATOMIC_ORDER" in name(1 << 24, 1)
-        assert name(1 << 24, 0).startswith("256x64/") and "RANK_ATOMIC_ORDER" in name(1 << 24, 0)
-        assert name((1 << 21) - 1, 1).startswith("256x16/") and name(1 << 21, 1).startswith("256x48/")   # small-tile switch
-        assert handle.vrenb200_radix_sort_set_ranking(3) == lib.EINVAL_ARG
-        # retired table entries keep their name and number but cannot be selected
-        retired = [v for v in range(handle.vrenb200_radix_sort_num_variants()) if b"[retired]" in handle.vrenb200_radix_sort_variant_name(v)]
-        assert retired and all(handle.vrenb200_radix_sort_set_variant(v) == lib.EINVAL_ARG for v in retired)
-        assert handle.vrenb200_radix_sort_set_variant(handle.vrenb200_radix_sort_num_variants()) == lib.EINVAL_ARG
-        # an explicit variant wins over the ranking mode
-        assert handle.vrenb200_radix_sort_set_variant(42) == 0 and name(1 << 24, 1).startswith("384x24/")
-    finally:
-        handle.vrenb200_radix_sort_set_variant(0)
-        handle.vrenb200_radix_sort_set_ranking(0)
+    # default: atomic ranking with every row verified and a by-construction redo pass
+    assert "F_RANK_ATOMIC" in name(1 << 24, 1) and "F_VERIFY_ALL" in name(1 << 24, 1)
+    assert handle.vrenb200_radix_sort_selected_variant_name(1 << 24, 1, None).decode() == name(1 << 24, 1)
+    m = dict(ranking=lib.RANKING_MATCH)
+    assert name(1 << 24, 1, **m).startswith("256x46/") and "F_RANK_LEADER" in name(1 << 24, 1, **m) and "ATOMIC" not in name(1 << 24, 1, **m)
+    assert name(1 << 24, 0, **m).startswith("256x64/") and name(1000, 1, **m).startswith("256x16/")
+    u = dict(ranking=lib.RANKING_ATOMIC_UNVERIFIED)
+    assert "F_RANK_ATOMIC" in name(1 << 24, 1, **u) and "VERIFY" not in name(1 << 24, 1, **u)
+    assert "F_VERIFY_SAMPLED" in name(1 << 24, 1, ranking=lib.RANKING_ATOMIC_SAMPLED)
+    assert name((1 << 21) - 1, 1).startswith("256x16/") and not name(1 << 21, 1).startswith("256x16/")   # small-tile switch
+    # an explicit table entry wins over the ranking mode; entries are 1-based, 0 = automatic
+    assert name(1 << 24, 1, variant=3) == handle.vrenb200_radix_sort_variant_name(3).decode()
+    assert handle.vrenb200_radix_sort_variant_name(0) == b"" and handle.vrenb200_radix_sort_variant_name(handle.vrenb200_radix_sort_num_variants() + 1) == b""
+
+
+def test_release_library_exports_no_process_global_hooks(handle):
+    """no global mutable state.  The tuning hooks exist only in VRENB200_TUNING builds."""
+    if os.environ.get("VRENB200_TUNING") == "1":
+        pytest.skip("tuning build")
+    for name in ("vrenb200_radix_sort_set_variant", "vrenb200_radix_sort_set_ranking", "vrenb200_scan_set_variant",
+                 "vrenb200_bucket_sort_set_search_min", "vrenb200_radix_partition_set_shape", "vrenb200_radix_sort_set_prefetch_tiles"):
+        assert not hasattr(handle, name), name

@@ -126,68 +126,85 @@ def test_plan_digit_ranges_properties():
     assert sum(int(h[b[r]:b[r + 1]].sum()) for r in range(8)) == 12345
 
 
-def test_plan_p2p_offsets_tile_the_receive_buffers():
-    """the fused exchange writes every source's block at plan_p2p_offsets: blocks must tile each receive buffer exactly, in
-    source-rank order, so that the final local stable sort yields the global stable order"""
-    rng = np.random.Generator(np.random.PCG64(7))
-    for world in (1, 2, 4, 8):
-        hists = torch.from_numpy(rng.integers(0, 50, size=(world, 256)).astype(np.int64))
-        bounds = vdist.plan_digit_ranges(hists.sum(0), world)
-        plans = [vdist.plan_p2p_offsets(hists, bounds, src) for src in range(world)]
-        rank_of = plans[0][0]
-        for d in range(256):
-            r = int(rank_of[d])
-            assert bounds[r] <= d < bounds[r + 1]
-        for dst in range(world):
-            pos = 0
-            for src in range(world):
-                _, my_offset, recv_counts, per_dest = plans[src]
-                assert int(my_offset[dst]) == pos
-                pos += int(hists[src, bounds[dst]:bounds[dst + 1]].sum())
-                assert int(per_dest[src, dst]) == int(hists[src, bounds[dst]:bounds[dst + 1]].sum())
-            assert pos == plans[0][2][dst]
+def _digit_hists(keys):
+    return np.stack([np.bincount((keys >> np.uint32(8 * p)) & np.uint32(0xFF), minlength=256) for p in range(4)]).astype(np.int64)
 
 
-def test_plan_digit_exchange_then_segment_sorts_give_the_global_stable_order():
-    """numpy simulation of the planned full-top-digit exchange: every source writes its pairs of top digit d at
-    my_digit_offset[d] of the owner's buffer (stable inside (source, digit)), every destination then sorts each
-    top-digit segment by the low 24 bits (three LSD passes); the concatenation must be the stable sort of the input"""
-    rng = np.random.Generator(np.random.PCG64(12))
-    for world, sizes in ((1, [1000]), (2, [5000, 3000]), (4, [4096, 0, 777, 9000]), (8, [2000] * 8)):
-        keys = [rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32) for n in sizes]
-        keys[0][: sizes[0] // 2] &= np.uint32(0x03FF00FF)                      # skew + many equal keys
-        vals, base = [], 0
-        for n in sizes:
-            vals.append(np.arange(base, base + n, dtype=np.uint32))
-            base += n
-        hists = torch.from_numpy(np.stack([np.bincount(k >> 24, minlength=256) for k in keys]).astype(np.int64))
-        bounds = vdist.plan_digit_ranges(hists.sum(0), world)
-        plans = [vdist.plan_digit_exchange(hists, bounds, r) for r in range(world)]
-        recv_counts = plans[0][3]
-        bufs_k = [np.zeros(c, np.uint32) for c in recv_counts]
-        bufs_v = [np.zeros(c, np.uint32) for c in recv_counts]
-        filled = [np.zeros(c, bool) for c in recv_counts]
-        for src in range(world):
-            rank_of, my_off, seg_start, _ = plans[src]
-            seen = np.zeros(256, np.int64)
-            for k, v in zip(keys[src], vals[src]):                               # the exchange pass: stable in (source, digit)
-                d = int(k >> 24)
-                dst = int(rank_of[d])
-                pos = int(my_off[d]) + seen[d]
-                seen[d] += 1
-                assert not filled[dst][pos]
-                filled[dst][pos] = True
-                bufs_k[dst][pos], bufs_v[dst][pos] = k, v
-        out_k, out_v = [], []
-        for dst in range(world):
-            assert filled[dst].all()
-            seg_start = plans[dst][2][dst]
-            for d in range(256):                                                 # the three low passes, per segment
-                lo, hi = int(seg_start[d]), int(seg_start[d + 1])
-                k, v = bufs_k[dst][lo:hi], bufs_v[dst][lo:hi]
-                assert k.size == 0 or ((k >> 24) == d).all()
-                order = np.argsort(k & np.uint32(0x00FFFFFF), kind="stable")
+@pytest.mark.parametrize("case", ["uniform", "skewed_half", "keys_below_2p24", "keys_below_2p13", "all_equal", "empty_ranks"])
+@pytest.mark.parametrize("world,rounds", [(1, 1), (2, 1), (2, 3), (4, 4), (8, 2)])
+def test_exchange_plan_then_segment_sorts_give_the_global_stable_order(case, world, rounds):
+    """numpy simulation of the multi-GPU sort as csrc/sharded_sort.cu runs it, driven by the host mirror of its device plan
+    (vdist.exchange_plan): the partition digit is the highest byte in which the keys differ; every source writes its pairs of
+    digit value d, in input order, at dst_off[source][d] of the owner's tile-aligned receive buffer; every owner sorts each
+    segment stably by the bytes below the partition digit, round by round, and emits the segments back to back.  The
+    concatenation over the ranks must be the stable sort of the concatenated input."""
+    rng = np.random.Generator(np.random.PCG64(12 + world))
+    tile = 64
+    sizes = [int(rng.integers(500, 3000)) for _ in range(world)]
+    if case == "empty_ranks" and world > 1:
+        sizes[0] = 0
+        sizes[-1] = 0 if world > 2 else sizes[-1]
+    keys = [rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32) for n in sizes]
+    if case == "skewed_half":
+        keys[-1][: sizes[-1] // 2] &= np.uint32(0x03FF00FF)
+    elif case == "keys_below_2p24":
+        keys = [k & np.uint32(0x00FFFFFF) for k in keys]
+    elif case == "keys_below_2p13":
+        keys = [k & np.uint32(0x1FFF) for k in keys]
+    elif case == "all_equal":
+        keys = [np.full_like(k, 0xABCD1234) for k in keys]
+    vals, base = [], 0
+    for n in sizes:
+        vals.append(np.arange(base, base + n, dtype=np.uint32))
+        base += n
+    hists = np.stack([_digit_hists(k) for k in keys])
+    total_tiles = sum(sizes) // tile + 257
+    plan = vdist.exchange_plan(hists, 4, tile, rounds, total_tiles, total_tiles)
+    assert plan["error"] == 0
+    p, owner, bounds = plan["pstar"], plan["owner"], plan["bounds"]
+    expect_p = {"keys_below_2p24": 2, "keys_below_2p13": 1, "all_equal": 0}.get(case, 3)
+    assert p == (expect_p if sum(sizes) > 1 else 0)
+    cap = total_tiles * tile
+    bufs_k = [np.zeros(cap, np.uint32) for _ in range(world)]
+    bufs_v = [np.zeros(cap, np.uint32) for _ in range(world)]
+    filled = [np.zeros(cap, bool) for _ in range(world)]
+    for src in range(world):
+        digit = (keys[src] >> np.uint32(8 * p)) & np.uint32(0xFF)
+        seen = np.zeros(256, np.int64)
+        for k, v, d in zip(keys[src], vals[src], digit):                       # local partition + transfer: stable in (source, digit)
+            dst = int(owner[d])
+            pos = int(plan["dst_off"][src][d]) + seen[d]
+            seen[d] += 1
+            assert not filled[dst][pos]
+            filled[dst][pos] = True
+            bufs_k[dst][pos], bufs_v[dst][pos] = k, v
+    out_k, out_v = [], []
+    low_mask = np.uint32((1 << (8 * p)) - 1)
+    for dst in range(world):
+        rd = plan["round_digit"][dst]
+        assert rd[0] == bounds[dst] and rd[-1] == bounds[dst + 1] and all(a <= b for a, b in zip(rd, rd[1:]))
+        got = 0
+        for k_round in range(rounds):
+            for d in range(int(rd[k_round]), int(rd[k_round + 1])):            # the segmented passes of one round
+                lo = int(plan["first_tile"][d]) * tile
+                n = int(plan["seg_len"][d])
+                assert filled[dst][lo:lo + n].all() and not filled[dst][lo + n:(lo + n + tile - 1) // tile * tile].any()
+                k, v = bufs_k[dst][lo:lo + n], bufs_v[dst][lo:lo + n]
+                assert n == 0 or (((k >> np.uint32(8 * p)) & np.uint32(0xFF)) == d).all()
+                order = np.argsort(k & low_mask, kind="stable")
                 out_k.append(k[order]); out_v.append(v[order])
-        all_k, all_v = np.concatenate(keys), np.concatenate(vals)
-        want = np.argsort(all_k, kind="stable")
-        assert np.array_equal(np.concatenate(out_k), all_k[want]) and np.array_equal(np.concatenate(out_v), all_v[want])
+                got += n
+        assert got == plan["out_count"][dst] == int(filled[dst].sum())
+    all_k, all_v = np.concatenate(keys), np.concatenate(vals)
+    want = np.argsort(all_k, kind="stable")
+    assert np.array_equal(np.concatenate(out_k), all_k[want]) and np.array_equal(np.concatenate(out_v), all_v[want])
+
+
+def test_exchange_plan_reports_what_does_not_fit():
+    """everything in one value of the partition digit: the owner needs room for all of it (error bit 0); a round that
+    outgrows its launch bound is error bit 1"""
+    k = np.concatenate([np.full(1000, 0x05000000, np.uint32), np.full(10, 0x06000000, np.uint32)])
+    hists = np.stack([_digit_hists(k), _digit_hists(k)])
+    assert vdist.exchange_plan(hists, 4, 64, 1, 40, 40)["error"] == 0
+    assert vdist.exchange_plan(hists, 4, 64, 1, 30, 30)["error"] & 1
+    assert vdist.exchange_plan(hists, 4, 64, 2, 40, 20)["error"] & 2

@@ -56,22 +56,17 @@ def test_bucket_sort_skewed_and_morton_like(vren):
     assert np.array_equal(counters.cpu().numpy().view(np.uint32), wc)
 
 
-@pytest.mark.parametrize("search_min", [0, 0xFFFFFFFF])
+@pytest.mark.parametrize("by_search", [1, 0])
 @pytest.mark.parametrize("n", [1, 3, 777, 70001, (1 << 20) + 5])
-def test_bucket_sort_end_offsets_both_paths(vren, n, search_min):
+def test_bucket_sort_end_offsets_both_paths(vren, n, by_search):
     """END offsets by search in the sorted output (large inputs) == by counting (small inputs), forced either way;
     sparse keys leave most buckets empty (an empty bucket repeats its predecessor's END)"""
-    handle = vren.load()
     keys = (rand_u32(41, n) % np.uint32(1000)) * np.uint32(61) + np.uint32(0xABCD0000)   # 1000 used buckets, high half noise
     pairs = np.stack([keys, np.arange(n, dtype=np.uint32)], axis=1)
     want, wc = oracle.bucket_sort(pairs)
-    vren.check(handle.vrenb200_bucket_sort_set_search_min(search_min), "set_search_min")
-    try:
-        _, got, counters = vren.bucket_sort(to_dev(pairs))
-        assert np.array_equal(got.cpu().numpy().view(np.uint32), want)
-        assert np.array_equal(counters.cpu().numpy().view(np.uint32), wc)
-    finally:
-        vren.check(handle.vrenb200_bucket_sort_set_search_min(1 << 20), "set_search_min")
+    _, got, counters = vren.bucket_sort(to_dev(pairs), end_offsets=by_search)
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), want)
+    assert np.array_equal(counters.cpu().numpy().view(np.uint32), wc)
 
 
 # ---- a5 -------------------------------------------------------------------------------------------------------------

@@ -136,9 +136,10 @@ def test_scan_kernels_agree(vren, n, offset):
     lib = vren.load()
     x = rand_u32(29, n + 8)
     want = oracle.exclusive_scan(x[offset:offset + n])
+    tuning = hasattr(lib, "vrenb200_scan_set_variant")     # VRENB200_TUNING builds expose the experimental kernels
     try:
-        for variant in (0, 1, 2, 3, 4, 8, 11, 12, 14, 15):
-            assert lib.vrenb200_scan_set_variant(variant) == 0
+        for variant in ((0, 1, 2, 3, 4, 8, 11, 12, 14, 15) if tuning else (0,)):
+            assert not tuning or lib.vrenb200_scan_set_variant(variant) == 0
             src = dev_u32(x)
             dst = torch.zeros_like(src)
             vren.exclusive_scan(src[offset:offset + n], out=dst[offset:offset + n])
@@ -150,7 +151,8 @@ def test_scan_kernels_agree(vren, n, offset):
                 vren.exclusive_scan(src[offset:offset + n])
                 assert np.array_equal(host_u32(src)[offset:offset + n], want), variant
     finally:
-        lib.vrenb200_scan_set_variant(0)
+        if tuning:
+            lib.vrenb200_scan_set_variant(0)
 
 
 def test_scan_full_size_c2(vren):
@@ -217,27 +219,24 @@ def test_radix_pairs_stable(vren, n):
     assert np.array_equal(host_u32(gk), wk) and np.array_equal(host_u32(gv), wv)
 
 
-def test_radix_ranking_probe_passes_on_this_device(vren):
-    """the match-free ranking is only used where same-address lanes of a shared atomic are served in ascending lane
-    order; the one-time probe must say so on B200 (else the library falls back to the ballot match and this test tells)"""
-    lib = vren.load()
-    if lib.vrenb200_radix_sort_ranking_probe() != 1:
-        assert b"RANK_LEADER_ATOMIC" in lib.vrenb200_radix_sort_selected_variant_name(1 << 24, 1)   # the guard did its job
-        pytest.skip("this device does not serve same-address lanes in lane order: ballot-match kernels in use")
-    assert b"RANK_ATOMIC_ORDER" in lib.vrenb200_radix_sort_selected_variant_name(1 << 24, 1)
-    assert b"RANK_ATOMIC_ORDER" in lib.vrenb200_radix_sort_selected_variant_name(1 << 24, 0)
-    assert b"RANK_ATOMIC_ORDER" in lib.vrenb200_radix_sort_selected_variant_name(1000, 1)
+RANKINGS = ["match", "verified", "sampled", "unverified", "selftest_redo"]
 
 
-@pytest.mark.parametrize("mode", [1, 2])   # 1: ballot match, 2: atomic order
+def _cfg(vren, ranking, tile_ids="auto", variant=0):
+    r = {"match": vren.RANKING_MATCH, "verified": vren.RANKING_ATOMIC_VERIFIED, "sampled": vren.RANKING_ATOMIC_SAMPLED,
+         "unverified": vren.RANKING_ATOMIC_UNVERIFIED, "selftest_redo": vren.RANKING_SELFTEST_REDO, "auto": vren.RANKING_AUTO}[ranking]
+    t = {"auto": vren.TILE_IDS_AUTO, "block": vren.TILE_IDS_BLOCK_INDEX, "ticket": vren.TILE_IDS_TICKET}[tile_ids]
+    return vren.SortConfig(r, t, variant)
+
+
+@pytest.mark.parametrize("ranking", RANKINGS)
 @pytest.mark.parametrize("pattern", ["equal", "two_values", "mod100", "low_byte_only", "uniform"])
 @pytest.mark.parametrize("n", [33, 4097, 100003, (1 << 20) + 77, (1 << 22) + 12345])
-def test_radix_pairs_both_rankings_collision_heavy(vren, mode, pattern, n):
-    """every lane-collision pattern of the ranking step (32 lanes on one counter ... all different), both ranking
-    modes, keys and values bit-exact against the stable oracle"""
-    lib = vren.load()
-    if mode == 2 and lib.vrenb200_radix_sort_ranking_probe() != 1:
-        pytest.skip("atomic-order ranking is not valid on this device (probe failed); the library does not select it")
+def test_radix_pairs_every_ranking_collision_heavy(vren, ranking, pattern, n):
+    """every lane-collision pattern of the ranking step (32 lanes on one counter ... all different) under every ranking
+    mode, keys and values bit-exact against the stable oracle.  The verified modes must never see their check fail on this
+    device (the hardware serves same-address lanes in lane order); "selftest_redo" makes the main passes write nothing and
+    report a failed check, so there the result is what the by-construction repeat passes produce."""
     if pattern == "equal":
         k = np.full(n, 0x12345678, np.uint32)
     elif pattern == "two_values":
@@ -250,15 +249,44 @@ def test_radix_pairs_both_rankings_collision_heavy(vren, mode, pattern, n):
         k = rand_u32(54, n)
     v = np.arange(n, dtype=np.uint32)
     wk, wv = oracle.sort_pairs(k, v)
-    assert lib.vrenb200_radix_sort_set_ranking(mode) == 0
-    try:
-        want_name = b"RANK_ATOMIC_ORDER" if mode == 2 else b"RANK_LEADER_ATOMIC"
-        assert want_name in lib.vrenb200_radix_sort_selected_variant_name(n, 1)
-        gk, gv = vren.radix_sort_pairs(dev_u32(k), dev_u32(v))
-        assert np.array_equal(host_u32(gk), wk) and np.array_equal(host_u32(gv), wv)
-        assert np.array_equal(host_u32(vren.radix_sort_keys(dev_u32(k))), wk)
-    finally:
-        lib.vrenb200_radix_sort_set_ranking(0)
+    cfg = _cfg(vren, ranking)
+    gk, gv = dev_u32(k), dev_u32(v)
+    violation = vren.radix_sort_ex(gk, gv, cfg)
+    assert np.array_equal(host_u32(gk), wk) and np.array_equal(host_u32(gv), wv)
+    assert violation == (0xF if ranking == "selftest_redo" else 0)
+    gk = dev_u32(k)
+    violation = vren.radix_sort_ex(gk, None, cfg)
+    assert np.array_equal(host_u32(gk), wk)
+    assert violation == (0xF if ranking == "selftest_redo" else 0)
+
+
+@pytest.mark.parametrize("ranking", ["match", "verified"])
+@pytest.mark.parametrize("n", [1, 4096, 4097, 3 * 12288 + 5, (1 << 21) + 999, (1 << 23) + 1])
+def test_radix_ticket_tile_ids(vren, ranking, n):
+    """tile ids taken from an atomic ticket (start order by construction) give the same result as the block index"""
+    k = rand_u32(55, n)
+    v = np.arange(n, dtype=np.uint32)
+    wk, wv = oracle.sort_pairs(k, v)
+    gk, gv = dev_u32(k), dev_u32(v)
+    assert vren.radix_sort_ex(gk, gv, _cfg(vren, ranking, "ticket")) == 0
+    assert np.array_equal(host_u32(gk), wk) and np.array_equal(host_u32(gv), wv)
+    gk = dev_u32(k)
+    vren.radix_sort_ex(gk, None, _cfg(vren, ranking, "ticket"))
+    assert np.array_equal(host_u32(gk), wk)
+
+
+def test_bucket_sort_redo_path(vren):
+    """the interleaved (uvec2) layout through the repeat passes"""
+    import torch
+
+    n = 300007
+    pairs = np.stack([rand_u32(56, n), np.arange(n, dtype=np.uint32)], axis=1)
+    want, wc = oracle.bucket_sort(pairs)
+    t = torch.from_numpy(pairs.view(np.int32)).cuda()
+    for ranking in ("selftest_redo", "match", "sampled"):
+        _, got, counters = vren.bucket_sort(t, config=_cfg(vren, ranking))
+        assert np.array_equal(got.cpu().numpy().view(np.uint32), want), ranking
+        assert np.array_equal(counters.cpu().numpy().view(np.uint32), wc), ranking
 
 
 @pytest.mark.parametrize("delta", [-1, 0, 1])
@@ -276,22 +304,21 @@ def test_radix_sizes_around_the_default_tiles(vren, tile, delta):
 
 
 def test_radix_all_variants_agree(vren):
+    """every entry of the kernel table (vrenb200_sort_config::variant), pairs and keys"""
     lib = vren.load()
     n = (1 << 18) + 333
     k = rand_u32(23, n)
     v = np.arange(n, dtype=np.uint32)
     wk, wv = oracle.sort_pairs(k, v)
-    try:
-        for var in range(lib.vrenb200_radix_sort_num_variants()):
-            if b"FAKE" in lib.vrenb200_radix_sort_variant_name(var) or b"[retired]" in lib.vrenb200_radix_sort_variant_name(var):
-                continue    # timing experiments that are wrong on purpose
-            assert lib.vrenb200_radix_sort_set_variant(var) == 0
-            gk, gv = vren.radix_sort_pairs(dev_u32(k), dev_u32(v))
-            assert np.array_equal(host_u32(gk), wk), lib.vrenb200_radix_sort_variant_name(var)
-            assert np.array_equal(host_u32(gv), wv), lib.vrenb200_radix_sort_variant_name(var)
-            assert np.array_equal(host_u32(vren.radix_sort_keys(dev_u32(k))), wk)
-    finally:
-        lib.vrenb200_radix_sort_set_variant(0)
+    for var in range(1, lib.vrenb200_radix_sort_num_variants() + 1):
+        name = lib.vrenb200_radix_sort_variant_name(var)
+        gk, gv = dev_u32(k), dev_u32(v)
+        if b"x64/" not in name:            # 64 rows per thread: keys-only tiles
+            vren.radix_sort_ex(gk, gv, _cfg(vren, "auto", variant=var))
+            assert np.array_equal(host_u32(gk), wk) and np.array_equal(host_u32(gv), wv), name
+        gk = dev_u32(k)
+        vren.radix_sort_ex(gk, None, _cfg(vren, "auto", variant=var))
+        assert np.array_equal(host_u32(gk), wk), name
 
 
 @pytest.mark.parametrize("n", [1, 1000, 8192 * 3 + 5, (1 << 20) + 3])

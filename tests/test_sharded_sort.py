@@ -1,0 +1,53 @@
+"""The multi-GPU sort (csrc/sharded_sort.cu through vren_b200.dist.ShardedSort) with all ranks emulated on ONE device: every
+code path of the pipeline — device plan, adaptive partition digit, tile-aligned receive layout, per-round transfers with
+the remote segment histograms, segmented onesweep passes, flags and epochs — against the oracle's stable sort of the
+concatenated input.  The real multi-GPU runs (NVLink peer stores between processes) are in tests/test_dist_gpu.py."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+SCRIPT = Path(__file__).with_name("run_sharded_emulated.py")
+
+
+def run(world, rounds, case, sizes, key_bits=32, ranking="auto"):
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")      # every stream on its own hardware queue
+    r = subprocess.run([sys.executable, str(SCRIPT), str(world), str(rounds), case, str(key_bits), ranking, ",".join(str(s) for s in sizes)],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("world,rounds,sizes", [
+    (1, 1, [100003]),
+    (2, 1, [1 << 20, 1 << 20]),
+    (2, 3, [300001, 77]),
+    (4, 2, [50000, 0, 123457, 1]),
+    (4, 4, [1 << 21, (1 << 21) + 5, 1 << 21, (1 << 21) - 9]),        # large tiles (12288 pairs), four rounds
+    (8, 2, [70001] * 8),
+])
+def test_sharded_sort_emulated_uniform(vren, world, rounds, sizes):
+    assert "pstar=3" in run(world, rounds, "uniform", sizes)
+
+
+@pytest.mark.parametrize("case,pstar", [("below_2p24", 2), ("below_2p13", 1), ("all_equal", 0), ("three_values", 3)])
+@pytest.mark.parametrize("world,rounds", [(2, 1), (4, 2)])
+def test_sharded_sort_emulated_key_ranges(vren, case, pstar, world, rounds):
+    """the partition digit follows the keys: Morton codes / indices / cluster keys below 2^24 no longer land on one rank
+    (ADVICE r1), all-equal keys need no local pass at all, a three-valued top digit is heavily skewed (capacity for everything)"""
+    assert f"pstar={pstar}" in run(world, rounds, case, [200000 + 17 * r for r in range(world)])
+
+
+def test_sharded_sort_emulated_bucket_key(vren):
+    """key_bits=16: stable by the low 16 bits, the high half is carried (vren::bucket_sort's key, bucket_sort.hpp:15-16)"""
+    assert "pstar=1" in run(4, 2, "high_noise_low16", [150000, 150001, 3, 99999], key_bits=16)
+
+
+@pytest.mark.parametrize("ranking", ["match", "selftest_redo", "auto+ticket"])
+def test_sharded_sort_emulated_ranking_modes(vren, ranking):
+    """ballot-match kernels, the repeat passes of the verified ranking (segmented form included) and ticket tile ids"""
+    run(2, 2, "uniform", [(1 << 21) + 3, 1 << 21], ranking=ranking)
+    run(3, 1, "below_2p24", [40000, 50000, 60000], ranking=ranking)

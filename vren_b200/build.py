@@ -24,6 +24,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "-shared",
 ]
+if os.environ.get("VRENB200_TUNING") == "1":     # experimental kernel table + process-global tuning hooks (never the shipped build)
+    NVCC_FLAGS.insert(0, "-DVRENB200_TUNING")
 
 
 def _nvcc() -> str:

@@ -633,15 +633,21 @@ inline int ilog2(uint32_t v) { int r = 0; while (v >>= 1) r++; return r; }
 using namespace vrenb200;
 
 namespace {
-int g_scan_variant = 0;
+#ifdef VRENB200_TUNING
+int g_scan_variant = 0;      // tuning builds only: selected through vrenb200_scan_set_variant
+int g_lag_finalize = 0, g_lag_scan = 0;
+#else
+constexpr int g_scan_variant = 0;   // release builds: no process-global selection state
+constexpr int g_lag_finalize = 0, g_lag_scan = 0;
+#endif
 constexpr int kScanAuto = 9999;
 constexpr int kScanVariantThreads[] = { kScanAuto, 256, 512, 1024, 0 /* staged 64 KB tile */, 1, 2, 3 /* staged, timing experiments (MODE) */,
                                         -64, -128, -256, -512 /* run-ahead, both lags = -value tiles */,
                                         -10064, -10128, -10256, -10512 /* same with L2 residency hints */ };
 }
 
+#ifdef VRENB200_TUNING
 // tuning hook: explicit run-ahead distances (tiles of 16384 elements); selects the run-ahead kernel
-int g_lag_finalize = 0, g_lag_scan = 0;
 extern "C" int vrenb200_scan_set_runahead(int finalize_lag, int scan_lag)
 {
     if (finalize_lag < 1 || scan_lag < 1 || finalize_lag > 4096 || scan_lag > 4096) return VRENB200_EINVAL_ARG;
@@ -660,6 +666,7 @@ extern "C" int vrenb200_scan_set_variant(int v)
     g_lag_finalize = g_lag_scan = 0;
     return VRENB200_OK;
 }
+#endif
 
 extern "C" size_t vrenb200_scan_scratch_bytes(uint32_t n)
 {
@@ -690,15 +697,11 @@ extern "C" int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const 
     if (threads == kScanAuto) threads = n >= (1u << 24) ? -10256 : (n >= (1u << 22) ? 1024 : 256);
     if (threads < 0)
     {
-        static bool configured = false;
-        if (!configured)
-        {
-            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_runahead_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int) (kStagedTile * 4))));
-            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_runahead_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int) (kStagedTile * 4))));
-            configured = true;
-        }
+        // per call: function attributes belong to the current device's context, and a process may use several devices
+        VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_runahead_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int) (kStagedTile * 4))));
+        VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_runahead_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int) (kStagedTile * 4))));
         const uint32_t staged_tiles = (uint32_t) (((size_t) n + kStagedTile - 1) / kStagedTile);
         const bool hints = -threads > 10000;
         const uint32_t lag = (uint32_t) (-threads % 10000);    // finalize lag = scan lag = lag
@@ -712,16 +715,11 @@ extern "C" int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const 
     }
     if (threads <= 3)
     {
-        static bool configured = false;
-        if (!configured)
-        {
-            const int bytes = (int) (kStagedTile * 4);
-            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
-            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
-            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
-            VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
-            configured = true;
-        }
+        const int bytes = (int) (kStagedTile * 4);
+        VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+        VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+        VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+        VRENB200_TRY(check_cuda(cudaFuncSetAttribute(exclusive_scan_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
         const uint32_t staged_tiles = (uint32_t) (((size_t) n + kStagedTile - 1) / kStagedTile);
         scan_state* st = static_cast<scan_state*>(scratch);
         const size_t smem = kStagedTile * 4;

@@ -1,20 +1,25 @@
-"""Multi-GPU (one process per GPU, torch.distributed) versions of the primitives that shard — SURVEY 8e.
+"""Multi-GPU (one process per GPU, torch.distributed) forms of the primitives that shard — SURVEY 8e.
 
 The reference is single-device; this is new work specified by the north-star:
-  * sharded_sort_pairs  : every rank holds n_r pairs.  Local top-digit histogram -> all_gather -> contiguous digit
-                          ranges per rank (balanced by count) -> stable local partition by the top digit (one
-                          onesweep pass) -> all-to-all-v of keys and values over NVLink (NCCL) -> local 4-pass
-                          onesweep of the received pairs.  Concatenating the ranks' outputs in rank order gives the
-                          stable sort of the concatenated input.
-  * sharded_exclusive_scan : local reduce -> all_gather of the partial sums -> local scan with base.
-  * views are independent: batched clustered shading needs no exchange (one view per rank, see bench.py).
+  * ShardedSort            : the product path.  Thin host wrapper of the C ABI's vrenb200_sharded_sort_* (csrc/sharded_sort.cu):
+                             histograms published into every peer, the plan computed on the device, local partition by the
+                             highest differing digit, per-round peer-store transfers over NVLink overlapped with segmented
+                             onesweep passes of what has arrived.  No NCCL on the data path, no host synchronisation inside a
+                             sort; torch only provides the symmetric (peer-mapped) memory and the process group for set-up.
+  * sharded_sort_pairs     : the NCCL form kept as the baseline — local top-digit partition, all_to_all_single of keys and
+                             values, local 4-pass sort of what was received.
+  * sharded_bucket_sort    : vren::bucket_sort sharded — ShardedSort on the 16-bit key, END offsets by all_reduce of the ranks'
+                             local END tables.
+  * sharded_exclusive_scan / sharded_reduce_add : local reduce -> all_gather / all_reduce of the partial sums -> local scan with base.
+  * views are independent: batched clustered shading needs no exchange (one view per rank, vren_b200/pipeline.py::ViewBatch).
 
-The collective plumbing is backend-agnostic (NCCL on GPUs, gloo in the CPU tests); the local compute steps come from
-a `LocalOps` object.  The product `CudaOps` calls the C ABI; tests may inject a numpy stand-in to exercise the
-exchange logic on CPU.  There is no CPU fallback in this module: without CUDA, `CudaOps()` raises.
+The collective plumbing of the NCCL forms is backend-agnostic (NCCL on GPUs, gloo in the CPU tests); the local compute steps
+come from a `LocalOps` object.  The product `CudaOps` calls the C ABI; tests may inject a numpy stand-in to exercise the exchange
+logic on CPU.  There is no CPU fallback in this module: without CUDA, `CudaOps()` raises.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 
 import torch
@@ -52,20 +57,6 @@ class CudaOps:
                                                                  n, 3, 1, scratch.data_ptr(), sb, None), "radix_sort_pairs_range")
         return ok, ov
 
-    def top_digit_histogram(self, keys: torch.Tensor) -> torch.Tensor:
-        hist = torch.empty(256, dtype=torch.int32, device=keys.device)
-        self.vlib.check(self.lib.vrenb200_radix_top_digit_histogram(self._stream(), keys.data_ptr(), keys.numel(), hist.data_ptr()),
-                        "radix_top_digit_histogram")
-        return hist
-
-    def partition_scatter(self, keys: torch.Tensor, vals: torch.Tensor, dest_table: torch.Tensor):
-        """fused partition + exchange: pairs are stored straight at dest_table[0/1][top digit] (peer-mapped or local)"""
-        n = keys.numel()
-        sb = self.lib.vrenb200_radix_sort_range_scratch_bytes(n)
-        scratch = torch.empty(max(sb, 256), dtype=torch.uint8, device=keys.device)
-        self.vlib.check(self.lib.vrenb200_radix_partition_scatter(self._stream(), keys.data_ptr(), vals.data_ptr(), n, dest_table.data_ptr(),
-                                                                  scratch.data_ptr(), sb), "radix_partition_scatter")
-
     def sort_pairs(self, keys: torch.Tensor, vals: torch.Tensor):
         self.vlib.radix_sort_pairs(keys, vals)
         return keys, vals
@@ -94,8 +85,9 @@ class SortPlan:
 
 
 def plan_digit_ranges(total_hist: torch.Tensor, world: int) -> list:
-    """split the 256 top digits into `world` contiguous ranges with (nearly) equal pair counts.
-    total_hist: int64[256] on CPU.  Returns world+1 boundaries, boundaries[0] = 0, boundaries[world] = 256."""
+    """split the 256 values of a digit into `world` contiguous ranges with (nearly) equal pair counts.
+    total_hist: int64[256] on CPU.  Returns world+1 boundaries, boundaries[0] = 0, boundaries[world] = 256.
+    (The device plan of csrc/sharded_sort.cu::plan_kernel applies the same rule.)"""
     cum = torch.cumsum(total_hist, 0)
     total = int(cum[-1])
     bounds = [0]
@@ -112,6 +104,14 @@ def plan_digit_ranges(total_hist: torch.Tensor, world: int) -> list:
     return bounds
 
 
+def plan_exchange_counts(hists: torch.Tensor, bounds: list):
+    """hists: int64 [G, 256] (CPU) -> per_dest [src, dst]: pairs every source sends to every destination"""
+    world = hists.shape[0]
+    b = torch.tensor(bounds, dtype=torch.int64)
+    csum = torch.cat([torch.zeros(world, 1, dtype=torch.int64), torch.cumsum(hists, 1)], dim=1)        # [G, 257]
+    return csum[:, b[1:]] - csum[:, b[:-1]]
+
+
 def make_sort_plan(local_top_hist: torch.Tensor, group=None) -> SortPlan:
     """local_top_hist: int64[256] on the rank's device (top-digit counts of the local keys)"""
     world = dist.get_world_size(group)
@@ -120,15 +120,15 @@ def make_sort_plan(local_top_hist: torch.Tensor, group=None) -> SortPlan:
     dist.all_gather(gathered, local_top_hist, group=group)
     hists = torch.stack(gathered).cpu()                      # [world, 256]
     bounds = plan_digit_ranges(hists.sum(0), world)
-    per_dest = plan_p2p_offsets(hists, bounds, rank)[3]                                               # [src, dst]
+    per_dest = plan_exchange_counts(hists, bounds)                                                     # [src, dst]
     return SortPlan(bounds, [int(v) for v in per_dest[rank]], [int(v) for v in per_dest[:, rank]])
 
 
 def sharded_sort_pairs(keys: torch.Tensor, vals: torch.Tensor, ops=None, group=None):
-    """globally stable sort by key of the pairs held by all ranks.  keys/vals: int32 storage of uint32 values.
-    Returns (keys_out, vals_out, plan): rank r holds the pairs whose top digit falls in its range, sorted."""
+    """NCCL baseline: globally stable sort by key of the pairs held by all ranks.  keys/vals: int32 storage of uint32
+    values.  Returns (keys_out, vals_out, plan): rank r holds the pairs whose top digit falls in its range, sorted."""
     ops = ops or CudaOps()
-    hist = ops.top_digit_histogram(keys) if hasattr(ops, "top_digit_histogram") else ops.digit_histograms(keys)[3]
+    hist = ops.digit_histograms(keys)[3]
     plan = make_sort_plan(hist.to(torch.int64), group)
     pk, pv = ops.partition_by_top_digit(keys, vals)
     n_recv = sum(plan.recv_counts)
@@ -140,107 +140,175 @@ def sharded_sort_pairs(keys: torch.Tensor, vals: torch.Tensor, ops=None, group=N
     return rk, rv, plan
 
 
-def plan_p2p_offsets(hists: torch.Tensor, bounds: list, rank: int):
-    """receive-buffer layout of the fused exchange: rank r's buffer holds one block per source rank, in source-rank order,
-    each block = that source's pairs whose top digit falls in r's range, in the source's original order.
-    hists: int64 [G, 256] (CPU).  Returns (rank_of[256] uint8, my_offset[G] = element offset of THIS rank's block inside
-    every destination's buffer, recv_counts[G])."""
-    world = hists.shape[0]
-    b = torch.tensor(bounds, dtype=torch.int64)
-    rank_of = (torch.bucketize(torch.arange(256), b[1:-1], right=True)).to(torch.uint8) if world > 1 else torch.zeros(256, dtype=torch.uint8)
-    csum = torch.cat([torch.zeros(world, 1, dtype=torch.int64), torch.cumsum(hists, 1)], dim=1)        # [G, 257]
-    per_dest = csum[:, b[1:]] - csum[:, b[:-1]]                                                        # [src, dst]
-    my_offset = per_dest[:rank].sum(0)
-    return rank_of, my_offset, [int(v) for v in per_dest.sum(0)], per_dest
+def exchange_plan(hists, key_digits: int, tile: int, rounds: int, cap_tiles: int, round_bound: int):
+    """Host mirror of csrc/sharded_sort.cu::plan_kernel (same arithmetic, numpy) — used by the CPU tests of the exchange
+    logic and for sizing the receive capacity ahead of a sort; the product computes its plan on the device.
+    hists: integer array [G, 4, 256], digit counts of every rank's shard.  Returns a dict:
+      pstar, error, bounds[G+1], owner[256], first_tile[256] (in the owner's buffer), seg_len[256], dst_off[G][256] (where
+      source s writes its block of digit d), round_digit[G][rounds+1], out_count[G]"""
+    import numpy as np
+
+    h = np.asarray(hists, dtype=np.int64)
+    world = h.shape[0]
+    pstar = 0
+    for p in range(key_digits - 1, -1, -1):
+        if int((h[:, p, :].sum(0) != 0).sum()) >= 2:
+            pstar = p
+            break
+    total = h[:, pstar, :].sum(0)
+    bounds = plan_digit_ranges(torch.from_numpy(total), world)
+    owner = np.zeros(256, np.int64)
+    for r in range(1, world):
+        owner += (np.arange(256) >= bounds[r])
+    tiles = (total + tile - 1) // tile
+    tiles_ex = np.concatenate([[0], np.cumsum(tiles)])
+    first_tile = tiles_ex[:-1] - tiles_ex[np.array(bounds)[owner]]
+    error = 0
+    round_digit = np.zeros((world, rounds + 1), np.int64)
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        if tiles_ex[hi] - tiles_ex[lo] > cap_tiles:
+            error |= 1
+        base, all_tiles = tiles_ex[lo], tiles_ex[hi] - tiles_ex[lo]
+        dd = lo
+        round_digit[r, 0] = lo
+        for k in range(1, rounds):
+            target = (all_tiles * k + rounds - 1) // rounds
+            while dd < hi and tiles_ex[dd] - base < target:
+                dd += 1
+            round_digit[r, k] = dd
+        round_digit[r, rounds] = hi
+        for k in range(rounds):
+            if tiles_ex[round_digit[r, k + 1]] - tiles_ex[round_digit[r, k]] > round_bound:
+                error |= 2
+    before = np.concatenate([np.zeros((1, 256), np.int64), np.cumsum(h[:, pstar, :], axis=0)[:-1]])     # [G, 256]: lower sources
+    dst_off = first_tile[None, :] * tile + before
+    out_count = [int(total[bounds[r]:bounds[r + 1]].sum()) for r in range(world)]
+    return {"pstar": pstar, "error": error, "bounds": bounds, "owner": owner, "first_tile": first_tile, "seg_len": total,
+            "dst_off": dst_off, "round_digit": round_digit, "out_count": out_count}
 
 
-def plan_digit_exchange(hists: torch.Tensor, bounds: list, rank: int):
-    """Planning for an exchange pass that partitions by the FULL top digit (host side only, the device side
-    is not wired yet).  Destination r's receive buffer is laid out by top digit, and inside a digit by source rank, so it
-    arrives grouped into top-digit segments and the local sort needs only the three low passes per segment.
-    hists: int64 [G, 256] top-digit counts of every rank (CPU); bounds: plan_digit_ranges().
-    Returns (rank_of uint8[256], my_digit_offset int64[256] = where THIS rank's pairs of top digit d start inside the
-    owner's buffer, segment_start int64[G][257] = start of every digit segment in every destination's buffer
-    (segment_start[r][d] == segment_start[r][d+1] outside r's range), recv_counts[G])."""
-    world = hists.shape[0]
-    b = torch.tensor(bounds, dtype=torch.int64)
-    rank_of = (torch.bucketize(torch.arange(256), b[1:-1], right=True)).to(torch.uint8) if world > 1 else torch.zeros(256, dtype=torch.uint8)
-    total = hists.sum(0)                                                   # [256]
-    owner = rank_of.to(torch.int64)
-    in_range = torch.nn.functional.one_hot(owner, world).T.to(torch.int64)  # [G, 256]: 1 where digit d belongs to rank r
-    seg_len = in_range * total                                             # [G, 256]
-    segment_start = torch.cat([torch.zeros(world, 1, dtype=torch.int64), torch.cumsum(seg_len, 1)], dim=1)   # [G, 257]
-    my_digit_offset = segment_start[owner, torch.arange(256)] + hists[:rank].sum(0)
-    return rank_of, my_digit_offset, segment_start, [int(v) for v in seg_len.sum(1)]
+def default_capacity(max_n: int, world: int, rounds: int = 1) -> int:
+    """receive capacity for balanced keys: the rank's share with 25 % slack plus a partial tile per segment (256 segments
+    of up to 12288 pairs in all) — see include/vrenb200.h"""
+    return int(max_n * 1.25) + 257 * 12288
 
 
-class P2PExchange:
-    """symmetric-memory receive buffers (keys, values) of one process group, created once and reused"""
+class ShardedSort:
+    """One rank's context of the multi-GPU sort (vrenb200_sharded_sort_*).
 
-    def __init__(self, capacity: int, device, group=None):
+    `regions`: the symmetric regions of ALL ranks as uint8 tensors addressable from this rank, in rank order.  Use
+    ShardedSort.for_process_group() (torch symmetric memory, one process per GPU) or ShardedSort.emulated() (several ranks on
+    one device inside one process: the peers are ordinary device tensors).  The output tensors are owned by the context and
+    overwritten by the next sort."""
+
+    def __init__(self, rank: int, world: int, max_n: int, capacity: int, regions, rounds: int = 1, config=None):
+        from . import lib as vlib
+
+        self.vlib, self.lib = vlib, vlib.load()
+        self.rank, self.world, self.max_n, self.capacity, self.rounds = rank, world, max_n, capacity, rounds
+        self.regions = regions
+        dev = regions[rank].device
+        self.local = torch.empty(self.lib.vrenb200_sharded_sort_local_bytes(max_n, capacity), dtype=torch.uint8, device=dev)
+        ptrs = (C.c_void_p * world)(*[int(r.data_ptr()) for r in regions])
+        handle = C.c_void_p()
+        self.config = config
+        vlib.check(self.lib.vrenb200_sharded_sort_create(C.byref(handle), rank, world, max_n, capacity, rounds, ptrs, self.local.data_ptr(),
+                                                         self.local.numel(), C.addressof(config) if config is not None else None),
+                   "vrenb200_sharded_sort_create")
+        self.handle = handle
+
+        def view(ptr, count):
+            off = ptr - self.local.data_ptr()
+            return self.local[off: off + 4 * count].view(torch.int32)
+
+        self.out_keys = view(self.lib.vrenb200_sharded_sort_out_keys(handle), capacity)
+        self.out_vals = view(self.lib.vrenb200_sharded_sort_out_values(handle), capacity)
+        self.status = view(self.lib.vrenb200_sharded_sort_status(handle), 8)
+
+    @staticmethod
+    def symmetric_bytes(capacity: int) -> int:
+        from . import lib as vlib
+
+        return int(vlib.load().vrenb200_sharded_sort_symmetric_bytes(capacity))
+
+    @classmethod
+    def for_process_group(cls, max_n: int, capacity: int | None = None, rounds: int = 1, group=None, config=None):
+        """one process per GPU: the symmetric regions come from torch symmetric memory (peer-mapped over NVLink)"""
         import torch.distributed._symmetric_memory as symm
 
-        self.group = group if group is not None else dist.group.WORLD
-        self.capacity = capacity
-        self.keys = symm.empty(capacity, dtype=torch.int32, device=device)
-        self.vals = symm.empty(capacity, dtype=torch.int32, device=device)
-        self.hk = symm.rendezvous(self.keys, self.group)
-        self.hv = symm.rendezvous(self.vals, self.group)
-        self.key_ptrs = [int(p) for p in self.hk.buffer_ptrs]
-        self.val_ptrs = [int(p) for p in self.hv.buffer_ptrs]
+        group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        capacity = capacity if capacity is not None else default_capacity(max_n, world, rounds)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nbytes = cls.symmetric_bytes(capacity)
+        region = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+        hdl = symm.rendezvous(region, group)
+        regions = [hdl.get_buffer(r, (nbytes,), torch.uint8) for r in range(world)]
+        self = cls(rank, world, max_n, capacity, regions, rounds, config)
+        self._symm = (region, hdl)
+        torch.cuda.synchronize()
+        dist.barrier(group)              # every rank has zeroed its flag words before anyone sorts
+        return self
 
-    def barrier(self):
-        self.hk.barrier()
+    @classmethod
+    def emulated(cls, world: int, max_n: int, capacity: int | None = None, rounds: int = 1, config=None, device="cuda"):
+        """all ranks in THIS process on one device (tests): returns the list of contexts"""
+        capacity = capacity if capacity is not None else default_capacity(max_n, world, rounds)
+        nbytes = cls.symmetric_bytes(capacity)
+        regions = [torch.zeros(nbytes, dtype=torch.uint8, device=device) for _ in range(world)]
+        ctxs = [cls(r, world, max_n, capacity, regions, rounds, config) for r in range(world)]
+        torch.cuda.synchronize()
+        return ctxs
+
+    def sort(self, keys: torch.Tensor, vals: torch.Tensor, key_bits: int = 32, stream=None):
+        """enqueue this rank's part of one collective sort (no synchronisation).  keys/vals: int32 storage, 16-byte aligned"""
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        self.vlib.check(self.lib.vrenb200_sharded_sort_pairs(self.handle, s, keys.data_ptr(), vals.data_ptr(), keys.numel(), key_bits),
+                        "vrenb200_sharded_sort_pairs")
+
+    def result(self):
+        """after the stream has finished the call: (keys, vals) views of this rank's sorted output; raises if the plan did
+        not fit (status word)"""
+        st = self.status.cpu().numpy().view("uint32")
+        if st[0] != 0:
+            raise RuntimeError(f"sharded sort: the exchange plan does not fit (status {int(st[0])}: "
+                               f"{'receive capacity exceeded' if st[0] & 1 else 'a round exceeds its launch bound'}); "
+                               f"capacity {self.capacity}, rounds {self.rounds} — retry with rounds=1 and/or a larger capacity")
+        n = int(st[1])
+        return self.out_keys[:n], self.out_vals[:n]
+
+    def owned_digits(self):
+        st = self.status.cpu().numpy().view("uint32")
+        return int(st[2]), int(st[3]), int(st[4])
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.vrenb200_sharded_sort_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
-def sharded_sort_pairs_p2p(keys: torch.Tensor, vals: torch.Tensor, exchange: P2PExchange, ops=None, group=None, phases: dict | None = None):
-    """same contract as sharded_sort_pairs, but the all-to-all is fused into the partition kernel: every rank's
-    onesweep pass on the top digit stores its pairs directly into the destination ranks' receive buffers through
-    NVLink peer pointers (no NCCL on the data path, no send-side staging copy).
-    `phases` (optional dict): filled with CUDA-event milliseconds of {plan, exchange, local_sort} for this call."""
-    ops = ops or CudaOps()
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if phases is not None else None
-    if ev:
-        ev[0].record()
-    # every rank has entered this call, i.e. is done with the previous contents of the receive buffers; issued first so
-    # that it completes under the planning below instead of in front of the exchange pass
-    exchange.barrier()
-    hist = ops.top_digit_histogram(keys).to(torch.int64)
-    gathered = [torch.empty_like(hist) for _ in range(world)]
-    dist.all_gather(gathered, hist, group=group)
-    hists = torch.stack(gathered).cpu()
-    bounds = plan_digit_ranges(hists.sum(0), world)
-    rank_of, my_offset, recv_counts, per_dest = plan_p2p_offsets(hists, bounds, rank)
-    if max(recv_counts) > exchange.capacity:
-        raise RuntimeError(f"P2P receive buffer too small: need {max(recv_counts)} pairs, capacity {exchange.capacity}")
-    if world > 32:
-        raise RuntimeError("fused exchange supports up to 32 ranks")
-    # device table {u64 kptr[32]; u64 vptr[32]; u8 rank_of[256]} (vrenb200_radix_partition_scatter)
-    kp = torch.zeros(32, dtype=torch.int64)
-    vp = torch.zeros(32, dtype=torch.int64)
-    kp[:world] = torch.tensor(exchange.key_ptrs, dtype=torch.int64) + 4 * my_offset
-    vp[:world] = torch.tensor(exchange.val_ptrs, dtype=torch.int64) + 4 * my_offset
-    table = torch.cat([kp.view(torch.uint8), vp.view(torch.uint8), rank_of]).to(keys.device, non_blocking=True)
-    if ev:
-        ev[1].record()
-    ops.partition_scatter(keys, vals, table)
-    exchange.barrier()                       # all remote stores into my buffers have completed
-    if ev:
-        ev[2].record()
-    n_recv = recv_counts[rank]
-    rk, rv = exchange.keys[:n_recv], exchange.vals[:n_recv]
-    ops.sort_pairs(rk, rv)
-    if ev:
-        ev[3].record()
-        ev[3].synchronize()
-        phases["plan_ms"] = ev[0].elapsed_time(ev[1])
-        phases["exchange_ms"] = ev[1].elapsed_time(ev[2])
-        phases["local_sort_ms"] = ev[2].elapsed_time(ev[3])
-        phases["received_pairs"] = int(n_recv)
-    plan = SortPlan(bounds, [int(v) for v in per_dest[rank]], [int(v) for v in per_dest[:, rank]])
-    return rk, rv, plan
+def sharded_bucket_sort(ctx: ShardedSort, pairs: torch.Tensor, group=None):
+    """vren::bucket_sort (bucket_sort.cpp:62-161) over the pairs of all ranks: stable by x & 0xFFFF.  pairs: int32 [n, 2]
+    (uvec2).  Returns (sorted pairs [m, 2] of this rank, END offsets int64[65536] of the GLOBAL sorted sequence — what the
+    reference's counter region holds after the call, bucket_sort_write.comp:32)."""
+    keys = pairs[:, 0].contiguous()
+    vals = pairs[:, 1].contiguous()
+    ctx.sort(keys, vals, key_bits=16)
+    torch.cuda.current_stream().synchronize()
+    k, v = ctx.result()
+    # local END table: number of local keys <= b; the global one is the sum over the ranks (shards are disjoint key ranges)
+    k16 = (k.to(torch.int64) & 0xFFFF)
+    ends = torch.searchsorted(k16, torch.arange(65536, dtype=torch.int64, device=k.device), right=True)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(ends, group=group)
+    return torch.stack([k, v], dim=1), ends
 
 
 def sharded_exclusive_scan(x: torch.Tensor, ops=None, group=None) -> torch.Tensor:

@@ -28,6 +28,15 @@ class VrenError(RuntimeError):
         super().__init__(f"{what}: status {status} ({STATUS_NAMES.get(status, '?')})")
 
 
+RANKING_AUTO, RANKING_MATCH, RANKING_ATOMIC_VERIFIED, RANKING_ATOMIC_SAMPLED, RANKING_ATOMIC_UNVERIFIED, RANKING_SELFTEST_REDO = range(6)
+TILE_IDS_AUTO, TILE_IDS_BLOCK_INDEX, TILE_IDS_TICKET = range(3)
+
+
+class SortConfig(C.Structure):
+    """vrenb200_sort_config: how one sort call runs (0 = library default)"""
+    _fields_ = [("ranking", C.c_int), ("tile_ids", C.c_int), ("variant", C.c_int)]
+
+
 class Camera(C.Structure):
     _fields_ = [("fov_y", C.c_float), ("aspect_ratio", C.c_float), ("near_plane", C.c_float), ("far_plane", C.c_float)]
 
@@ -36,6 +45,7 @@ def declared_symbols() -> list[str]:
     """every function name include/vrenb200.h declares (used by the CPU-side export test)"""
     text = HEADER.read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"#ifdef VRENB200_TUNING.*?#endif", "", text, flags=re.S)     # hooks of tuning builds only
     return sorted(set(re.findall(r"\b(vrenb200_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -82,19 +92,14 @@ def load() -> C.CDLL:
     sig("vrenb200_radix_sort_compat", i32, vp, vp, u32, vp, sz, vp, sz)
     sig("vrenb200_radix_sort_host_work_bytes", sz, u32, i32)
     sig("vrenb200_radix_sort_pairs_host", i32, vp, vp, vp, u32, vp, sz)
-    sig("vrenb200_radix_sort_set_variant", i32, i32)
-    sig("vrenb200_radix_sort_set_prefetch_tiles", i32, u32)
-    sig("vrenb200_radix_sort_set_hist_loads", i32, u32)
-    sig("vrenb200_radix_sort_set_dephase", i32, u32, u32)
-    sig("vrenb200_radix_sort_set_ranking", i32, i32)
-    sig("vrenb200_radix_sort_ranking_probe", i32)
-    sig("vrenb200_radix_sort_selected_variant_name", C.c_char_p, u32, i32)
+    sig("vrenb200_radix_sort_selected_variant_name", C.c_char_p, u32, i32, vp)
     sig("vrenb200_radix_sort_num_variants", i32)
     sig("vrenb200_radix_sort_variant_name", C.c_char_p, i32)
     sig("vrenb200_sort_profile_create", vp)
     sig("vrenb200_sort_profile_destroy", None, vp)
     sig("vrenb200_sort_profile_read", i32, vp, C.POINTER(C.c_float))
-    sig("vrenb200_radix_sort_pairs_profiled", i32, vp, vp, vp, u32, vp, sz, vp)
+    sig("vrenb200_radix_sort_ex", i32, vp, vp, vp, u32, vp, sz, vp, vp)
+    sig("vrenb200_radix_sort_violation_word", vp, vp, u32, i32)
     for name, res, args in _LATE_SIGS:
         if hasattr(lib, name):
             sig(name, res, *args)
@@ -104,6 +109,14 @@ def load() -> C.CDLL:
 
 _vp, _u32, _sz, _i32 = C.c_void_p, C.c_uint32, C.c_size_t, C.c_int
 _LATE_SIGS = [
+    ("vrenb200_sharded_sort_symmetric_bytes", _sz, (_u32,)),
+    ("vrenb200_sharded_sort_local_bytes", _sz, (_u32, _u32)),
+    ("vrenb200_sharded_sort_create", _i32, (_vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _sz, _vp)),
+    ("vrenb200_sharded_sort_destroy", None, (_vp,)),
+    ("vrenb200_sharded_sort_pairs", _i32, (_vp, _vp, _vp, _vp, _u32, _i32)),
+    ("vrenb200_sharded_sort_out_keys", _vp, (_vp,)),
+    ("vrenb200_sharded_sort_out_values", _vp, (_vp,)),
+    ("vrenb200_sharded_sort_status", _vp, (_vp,)),
     ("vrenb200_cluster_tests", _i32, (_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp)),
     ("vrenb200_light_list_hash_scratch_bytes", _sz, (_u32,)),
     ("vrenb200_light_list_hash", _i32, (_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _sz)),
@@ -125,14 +138,14 @@ _LATE_SIGS = [
     ("vrenb200_kd_tree_build", _sz, (_vp, _sz, _vp, _sz, _vp, _sz)),
     ("vrenb200_kd_tree_search", None, (_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp)),
     ("vrenb200_kd_tree_search_batch", _i32, (_vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp)),
-    ("vrenb200_scan_set_variant", _i32, (_i32,)),
-    ("vrenb200_scan_set_runahead", _i32, (_i32, _i32)),
+    ("vrenb200_scan_set_variant", _i32, (_i32,)),          # tuning builds only
+    ("vrenb200_scan_set_runahead", _i32, (_i32, _i32)),    # tuning builds only
     ("vrenb200_radix_sort_range_scratch_bytes", _sz, (_u32,)),
     ("vrenb200_radix_sort_pairs_range", _i32, (_vp, _vp, _vp, _vp, _vp, _u32, _i32, _i32, _vp, _sz, C.POINTER(C.c_int))),
     ("vrenb200_bucket_sort_output_bytes", _sz, (_u32,)),
     ("vrenb200_bucket_sort_scratch_bytes", _sz, (_u32,)),
     ("vrenb200_bucket_sort", _i32, (_vp, _vp, _u32, _vp, _vp, _sz)),
-    ("vrenb200_bucket_sort_set_search_min", _i32, (_u32,)),
+    ("vrenb200_bucket_sort_ex", _i32, (_vp, _vp, _u32, _vp, _vp, _sz, _vp, _i32)),
     ("vrenb200_calc_bvh_padded_leaf_count", _u32, (_u32,)),
     ("vrenb200_calc_bvh_buffer_length", _u32, (_u32,)),
     ("vrenb200_calc_bvh_buffer_size", _sz, (_u32,)),
@@ -220,17 +233,36 @@ def radix_sort_keys(keys, n: int | None = None):
     return keys
 
 
-def radix_sort_pairs(keys, vals, n: int | None = None, scratch=None):
+def radix_sort_pairs(keys, vals, n: int | None = None, scratch=None, config: SortConfig | None = None):
     lib = load()
     n = keys.numel() if n is None else n
     sb = lib.vrenb200_radix_sort_scratch_bytes(n, 1)
     if scratch is None:
         scratch = _scratch(sb)
-    check(lib.vrenb200_radix_sort_pairs(_stream(), _ptr(keys), _ptr(vals), n, _ptr(scratch), sb), "vrenb200_radix_sort_pairs")
+    if config is None:
+        check(lib.vrenb200_radix_sort_pairs(_stream(), _ptr(keys), _ptr(vals), n, _ptr(scratch), sb), "vrenb200_radix_sort_pairs")
+    else:
+        check(lib.vrenb200_radix_sort_ex(_stream(), _ptr(keys), _ptr(vals), n, _ptr(scratch), sb, C.addressof(config), None), "vrenb200_radix_sort_ex")
     return keys, vals
 
 
-def bucket_sort(pairs, n: int | None = None):
+def radix_sort_ex(keys, vals, config: SortConfig, n: int | None = None):
+    """general form (vals may be None); returns the violation flag of the ranking check (0 = the check never failed)"""
+    import torch
+
+    lib = load()
+    n = keys.numel() if n is None else n
+    kv = 0 if vals is None else 1
+    sb = lib.vrenb200_radix_sort_scratch_bytes(n, kv)
+    scratch = _scratch(sb)
+    check(lib.vrenb200_radix_sort_ex(_stream(), _ptr(keys), _ptr(vals), n, _ptr(scratch), sb, C.addressof(config), None), "vrenb200_radix_sort_ex")
+    torch.cuda.synchronize()
+    word = lib.vrenb200_radix_sort_violation_word(_ptr(scratch), n, kv)
+    off = word - _ptr(scratch)
+    return int(scratch[off: off + 4].view(torch.int32).item()) & 0xFFFFFFFF
+
+
+def bucket_sort(pairs, n: int | None = None, config: SortConfig | None = None, end_offsets: int = -1):
     """vren::bucket_sort over uvec2 pairs [n,2] (int32 storage). Returns (out_buffer_u8, sorted_view [n,2], counters_view [65536])"""
     import torch
 
@@ -240,7 +272,11 @@ def bucket_sort(pairs, n: int | None = None):
     out = torch.zeros(ob, dtype=torch.uint8, device=pairs.device)
     sb = lib.vrenb200_bucket_sort_scratch_bytes(n)
     scratch = _scratch(sb)
-    check(lib.vrenb200_bucket_sort(_stream(), _ptr(pairs), n, _ptr(out), _ptr(scratch), sb), "vrenb200_bucket_sort")
+    if config is None and end_offsets < 0:
+        check(lib.vrenb200_bucket_sort(_stream(), _ptr(pairs), n, _ptr(out), _ptr(scratch), sb), "vrenb200_bucket_sort")
+    else:
+        check(lib.vrenb200_bucket_sort_ex(_stream(), _ptr(pairs), n, _ptr(out), _ptr(scratch), sb, C.addressof(config) if config is not None else None,
+                                          end_offsets), "vrenb200_bucket_sort_ex")
     sorted_view = out[: n * 8].view(torch.int32).view(n, 2)
     coff = (n * 8 + 255) // 256 * 256
     counters = out[coff: coff + 65536 * 4].view(torch.int32)
