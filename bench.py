@@ -3,13 +3,17 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n 28]
 
-A "step" is one complete sort (histogram + 4 onesweep passes) of one batch of synthetic pairs.
+A "step" is one complete sort of one batch of synthetic pairs (uniform keys, value = global index).
   value        whole-job Gpairs/s, inputs resident in HBM, device-timed with CUDA events (max over ranks)
-  e2e          same metric through the host-buffer C-ABI call (H2D + sort + D2H inside the timed region)
+  e2e          same metric through the host-buffer path (H2D + sort + D2H inside the timed region); at N > 1 through the
+               SHARDED sort (host shards in, sorted shards out)
   roofline     dominant kernel = onesweep pass: algorithmic 16 B/pair/launch over its CUDA-event duration
-  cpu_baseline the oracle's restatement of the reference's CPU check (std::stable_sort by key) on a bounded sample
-N>1 (torchrun): ONE global sort of N x 2^log2n pairs, 2^log2n per rank (weak scaling): top-digit histogram ->
-all_gather -> stable local partition -> NCCL all-to-all-v over NVLink -> local 4-pass onesweep (vren_b200/dist.py).
+  cpu_baseline the oracle's restatement of the reference's CPU check (std::stable_sort by key), all host threads, same size
+N>1 (torchrun): ONE global sort of N x 2^log2n pairs, 2^log2n per rank (weak scaling) through the C ABI's multi-GPU sort
+(vren_b200/csrc/sharded_sort.cu): device plan, local partition, per-round NVLink peer-store transfers overlapped with
+segmented onesweep passes.  Before the timed steps a smaller global sort (2^22 per rank) is compared with the oracle on rank 0;
+the timed output is checked by an all-reduced (key, value) multiset checksum, per-shard sortedness with value order inside
+equal keys, and last-key(r) <= first-key(r+1) across ranks.
 """
 from __future__ import annotations
 
@@ -127,23 +131,26 @@ def cpu_sort_sample(log2_sample: int, threads: int, steps: int = 1, warmup: int 
     return n / sec / 1e9, sec
 
 
+def workload_string(log2n):
+    return f"radix sort of 2^{log2n} uint32 key-value pairs per GPU (uniform keys, value=index)"
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU check (std::stable_sort by key; oracle port) on all host threads"""
+    """--impl reference: the reference's CPU check (std::stable_sort by key; oracle port) on all host threads, on the SAME
+    size as the headline configuration (2^log2n pairs per step)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    log2_sample = min(args.log2n, 25)
-    value, sec = cpu_sort_sample(log2_sample, threads, steps=args.steps, warmup=args.warmup)
+    value, sec = cpu_sort_sample(args.log2n, threads, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"radix sort of 2^{args.log2n} uint32 key-value pairs per GPU (uniform keys, value=index)",
-                   "l2": "inputs larger than L2"},
+        "config": {"workload": workload_string(args.log2n), "l2": "inputs larger than L2"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"std::stable_sort by key (vren_test radix_sort.cpp:88 check, pairs extension) of 2^{log2_sample} "
-                                   f"pairs per step on {threads} threads (chunk sort + parallel merges)"},
+                         "sample": f"std::stable_sort by key (vren_test radix_sort.cpp:88 check, pairs extension) of 2^{args.log2n} "
+                                   f"pairs per step on {threads} threads (chunk sort + parallel merges); one shard's size at every N"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -294,6 +301,7 @@ def secondary_metrics(lib, vlib, dev):
 
 
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -308,60 +316,103 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = vlib.load()
-    if args.variant is not None:
-        vlib.check(lib.vrenb200_radix_sort_set_variant(args.variant), "set_variant")
-    if args.partition_shape is not None:
-        vlib.check(lib.vrenb200_radix_partition_set_shape(args.partition_shape), "set_partition_shape")
+    ranking = {"auto": vlib.RANKING_AUTO, "match": vlib.RANKING_MATCH, "verified": vlib.RANKING_ATOMIC_VERIFIED,
+               "sampled": vlib.RANKING_ATOMIC_SAMPLED, "unverified": vlib.RANKING_ATOMIC_UNVERIFIED}[args.ranking]
+    tile_ids = {"auto": vlib.TILE_IDS_AUTO, "block": vlib.TILE_IDS_BLOCK_INDEX, "ticket": vlib.TILE_IDS_TICKET}[args.tile_ids]
+    cfg = vlib.SortConfig(ranking, tile_ids, args.variant or 0)
+    cfg_ptr = C.addressof(cfg)
 
     n = 1 << args.log2n
     dev = torch.device("cuda", local_rank)
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
     keys0 = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
-    vals0 = torch.arange(n, dtype=torch.int32, device=dev)
-    keys, vals = torch.empty_like(keys0), torch.empty_like(vals0)
-    sbytes = lib.vrenb200_radix_sort_scratch_bytes(n, 1)
-    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    vals0 = torch.arange(rank * n, (rank + 1) * n, dtype=torch.int64, device=dev).to(torch.int32)      # global index: unique, rank-major
     stream = torch.cuda.current_stream().cuda_stream
     prof = lib.vrenb200_sort_profile_create()
     kern_ms = (C.c_float * 6)()
+    sign = torch.tensor(-(1 << 31), dtype=torch.int32, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    dops = None
-    exchange = None
-    if world > 1:
+    def checksum(k, v):
+        """order-independent 64-bit fingerprint of a multiset of pairs (sum of a mix of every pair, mod 2^63)"""
+        x = (k.to(torch.int64) & 0xFFFFFFFF) | ((v.to(torch.int64) & 0xFFFFFFFF) << 32)
+        x = (x ^ (x >> 31)) * 0x2545F4914F6CDD1D
+        x = x ^ (x >> 29)
+        return torch.stack([(x & 0x7FFFFFFF).sum(), ((x >> 31) & 0x7FFFFFFF).sum(), torch.tensor(k.numel(), dtype=torch.int64, device=k.device)])
+
+    def verify_sorted_shard(k, v, what):
+        """keys ascending (unsigned); inside equal keys the values (global indices) ascending = stable"""
+        if k.numel() < 2:
+            return
+        kk = (k ^ sign).to(torch.int64)
+        vv = v.to(torch.int64) & 0xFFFFFFFF
+        dk = kk[1:] - kk[:-1]
+        assert bool((dk >= 0).all()), f"bench: {what}: keys not sorted"
+        assert bool(((dk > 0) | (vv[1:] > vv[:-1])).all()), f"bench: {what}: equal keys out of input order (not stable)"
+
+    sorter = None
+    single = None
+    if world == 1:
+        keys, vals = torch.empty_like(keys0), torch.empty_like(vals0)
+        sbytes = lib.vrenb200_radix_sort_scratch_bytes(n, 1)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    else:
         from vren_b200 import dist as vdist
 
-        dops = vdist.CudaOps()
-        exchange = None
-        if not args.nccl_exchange:
-            try:
-                exchange = vdist.P2PExchange(int(n * 1.25) + 4096, dev)    # receive buffers in symmetric (peer-mapped) memory
-            except Exception as e:      # no P2P / symmetric memory: NCCL all-to-all-v path
-                if rank == 0:
-                    print(f"bench: symmetric memory unavailable ({e}); using the NCCL exchange", file=sys.stderr)
-    last = {}
+        # ---- parity of the multi-GPU path against the oracle before anything is timed (2^22 pairs per rank, rank 0 checks)
+        import oracle
+
+        nv = 1 << 22
+        small = vdist.ShardedSort.for_process_group(nv, None, 2, config=cfg)
+        for rep in range(2):
+            small.sort(keys0[:nv], vals0[:nv])
+        torch.cuda.synchronize()
+        sk, sv = small.result()
+        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([sk.numel()], dtype=torch.int64, device=dev))
+        sizes = [int(t.item()) for t in sizes]
+        pad = max(sizes)
+        gk = [torch.zeros(pad, dtype=torch.int32, device=dev) for _ in range(world)]
+        gv = [torch.zeros(pad, dtype=torch.int32, device=dev) for _ in range(world)]
+        ik = [torch.zeros(nv, dtype=torch.int32, device=dev) for _ in range(world)]
+        iv = [torch.zeros(nv, dtype=torch.int32, device=dev) for _ in range(world)]
+        dist.all_gather(gk, torch.nn.functional.pad(sk, (0, pad - sk.numel())))
+        dist.all_gather(gv, torch.nn.functional.pad(sv, (0, pad - sv.numel())))
+        dist.all_gather(ik, keys0[:nv].contiguous())
+        dist.all_gather(iv, vals0[:nv].contiguous())
+        if rank == 0:
+            got_k = np.concatenate([gk[r][:sizes[r]].cpu().numpy().view(np.uint32) for r in range(world)])
+            got_v = np.concatenate([gv[r][:sizes[r]].cpu().numpy().view(np.uint32) for r in range(world)])
+            wk, wv = oracle.sort_pairs(np.concatenate([t.cpu().numpy().view(np.uint32) for t in ik]),
+                                       np.concatenate([t.cpu().numpy().view(np.uint32) for t in iv]))
+            assert np.array_equal(got_k, wk) and np.array_equal(got_v, wv), "bench: sharded sort differs from the oracle"
+        del gk, gv, ik, iv
+        small.close()
+        del small
+        torch.cuda.empty_cache()
+        sorter = vdist.ShardedSort.for_process_group(n, None, args.rounds, config=cfg)
+    in_sum = checksum(keys0, vals0)
+    if world > 1:
+        dist.all_reduce(in_sum)
 
     def one_step(profile):
-        keys.copy_(keys0)      # restore the unsorted batch (untimed; 2 GiB of traffic also evicts L2)
-        vals.copy_(vals0)
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
         if world == 1:
-            vlib.check(lib.vrenb200_radix_sort_pairs_profiled(stream, keys.data_ptr(), vals.data_ptr(), n, scratch.data_ptr(),
-                                                              sbytes, prof if profile else None), "radix_sort_pairs")
+            keys.copy_(keys0)      # restore the unsorted batch (untimed; 2 GiB of traffic also evicts L2)
+            vals.copy_(vals0)
+            e0.record()
+            vlib.check(lib.vrenb200_radix_sort_ex(stream, keys.data_ptr(), vals.data_ptr(), n, scratch.data_ptr(), sbytes, cfg_ptr,
+                                                  prof if profile else None), "radix_sort_ex")
         else:
-            if exchange is not None:
-                last["phases"] = {}
-                last["k"], last["v"], last["plan"] = vdist.sharded_sort_pairs_p2p(keys, vals, exchange, ops=dops, phases=last["phases"])
-            else:
-                last["k"], last["v"], last["plan"] = vdist.sharded_sort_pairs(keys, vals, ops=dops)
+            e0.record()
+            sorter.sort(keys0, vals0)          # out of place: the input shard stays as it is; 2 GiB >> L2 between steps
         e1.record()
         return e0, e1
 
@@ -379,33 +430,47 @@ def run_ours(args):
                 hist_ms.append(kern_ms[0])
                 pass_ms.extend(kern_ms[2:6])
         barrier()
-    # correctness of the last step (cheap device-side property check; full parity lives in tests/)
-    sign = torch.tensor(-(1 << 31), dtype=torch.int32, device=dev)
+    # ---- correctness of the last timed step
+    violation = 0
     if world == 1:
-        flipped = keys ^ sign
-        if os.environ.get("VRENB200_BENCH_NOVERIFY") != "1":   # timing experiments with deliberately wrong kernels
-            assert bool((flipped[1:] >= flipped[:-1]).all()), "bench: output not sorted"
-            assert torch.equal(keys0[vals.long()], keys), "bench: pairs broken"
+        verify_sorted_shard(keys, vals, "output")
+        assert torch.equal(keys0[(vals.to(torch.int64) & 0xFFFFFFFF)], keys), "bench: pairs broken"
+        word = lib.vrenb200_radix_sort_violation_word(scratch.data_ptr(), n, 1) - scratch.data_ptr()
+        violation = int(scratch[word: word + 4].view(torch.int32).item())
+        out_sum = checksum(keys, vals)
     else:
-        ok = last["k"] ^ sign
-        assert bool((ok[1:] >= ok[:-1]).all()), "bench: shard not sorted"
-        lo, hi = last["plan"].digit_lo[rank], last["plan"].digit_lo[rank + 1]
-        top = (last["k"].to(torch.int64) & 0xFFFFFFFF) >> 24
-        assert ok.numel() == 0 or (int(top.min()) >= lo and int(top.max()) < hi), "bench: shard outside its digit range"
-        cnt = torch.tensor([ok.numel()], dtype=torch.int64, device=dev)
-        dist.all_reduce(cnt)
-        assert int(cnt.item()) == world * n, "bench: pairs lost in the exchange"
-        # one profiled local sort for the roofline object (kernel timing does not depend on the exchange)
+        ok, ov = sorter.result()
+        verify_sorted_shard(ok, ov, f"shard of rank {rank}")
+        out_sum = checksum(ok, ov)
+        dist.all_reduce(out_sum)
+        # last key of every rank <= first key of the next non-empty rank (unsigned), ties in rank-major value order
+        edge = torch.full((4,), -1, dtype=torch.int64, device=dev)
+        if ok.numel():
+            edge = torch.stack([(ok[0] ^ sign).to(torch.int64), ov[0].to(torch.int64) & 0xFFFFFFFF,
+                                (ok[-1] ^ sign).to(torch.int64), ov[-1].to(torch.int64) & 0xFFFFFFFF])
+        edges = [torch.zeros_like(edge) for _ in range(world)]
+        dist.all_gather(edges, edge)
+        nonempty = [e.tolist() for e in edges if int(e[1]) >= 0]
+        for a, b in zip(nonempty, nonempty[1:]):
+            assert (a[2], a[3]) < (b[0], b[1]), "bench: shards overlap / out of order across ranks"
+    assert torch.equal(in_sum, out_sum), "bench: the output is not a permutation of the input pairs"
+
+    if world == 1:
+        # one profiled run per kernel family for the roofline object happened above; nothing more to do
+        pass
+    else:
+        # the dominant kernel of the multi-GPU sort is the same pass kernel: profile one local sort for the roofline object
+        keys, vals = keys0.clone(), vals0.clone()
+        sbytes = lib.vrenb200_radix_sort_scratch_bytes(n, 1)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
         for _ in range(3):
             keys.copy_(keys0); vals.copy_(vals0)
-            vlib.check(lib.vrenb200_radix_sort_pairs_profiled(stream, keys.data_ptr(), vals.data_ptr(), n, scratch.data_ptr(), sbytes, prof),
-                       "radix_sort_pairs")
+            vlib.check(lib.vrenb200_radix_sort_ex(stream, keys.data_ptr(), vals.data_ptr(), n, scratch.data_ptr(), sbytes, cfg_ptr, prof), "radix_sort_ex")
             torch.cuda.synchronize()
             vlib.check(lib.vrenb200_sort_profile_read(prof, kern_ms), "profile_read")
             hist_ms.append(kern_ms[0])
             pass_ms.extend(kern_ms[2:6])
-        phases_last = last.get("phases")
-        last.clear()
+        del keys, vals, scratch
 
     ms = sum(step_ms) / len(step_ms)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -414,108 +479,223 @@ def run_ours(args):
     ms_max = float(t.item())
     value = world * n / (ms_max * 1e-3) / 1e9
 
-    # ---- e2e: host buffers through the C ABI (pinned), H2D + sort + D2H timed, max over ranks -----------------
-    # Every step uploads its 2 x 4n input bytes and downloads its 2 x 4n result bytes.  A single call is upload ->
-    # sort -> download, one PCIe direction at a time; consecutive steps are issued on two streams (two device work
-    # buffers, vrenb200_radix_sort_pairs_host_async), so step i+1 uploads while step i downloads.
+    # ---- e2e: HOST buffers in, HOST buffers out, H2D + sort + D2H timed (wall clock around a drained pipeline), max over ranks
     e2e_steps = max(2, min(args.steps, 12))
-    del keys, vals, scratch
     hk_in = torch.empty(n, dtype=torch.int32, pin_memory=True)
     hv_in = torch.empty(n, dtype=torch.int32, pin_memory=True)
     hk_in.copy_(keys0)
     hv_in.copy_(vals0)
-    wbytes = lib.vrenb200_radix_sort_host_work_bytes(n, 1)
-    lanes = [{"stream": torch.cuda.Stream(device=dev), "hk": torch.empty(n, dtype=torch.int32, pin_memory=True),
-              "hv": torch.empty(n, dtype=torch.int32, pin_memory=True), "work": torch.empty(wbytes, dtype=torch.uint8, device=dev)}
-             for _ in range(2)]
-    torch.cuda.synchronize()
+    if world == 1:
+        # consecutive steps are issued on two streams (two device work buffers, vrenb200_radix_sort_pairs_host_async), so step
+        # i+1 uploads while step i downloads; a single call is upload -> sort -> download, one PCIe direction at a time
+        del keys, vals, scratch
+        wbytes = lib.vrenb200_radix_sort_host_work_bytes(n, 1)
+        lanes = [{"stream": torch.cuda.Stream(device=dev), "hk": torch.empty(n, dtype=torch.int32, pin_memory=True),
+                  "hv": torch.empty(n, dtype=torch.int32, pin_memory=True), "work": torch.empty(wbytes, dtype=torch.uint8, device=dev)}
+                 for _ in range(2)]
+        torch.cuda.synchronize()
 
-    def issue(i):
-        lane = lanes[i % 2]
-        vlib.check(lib.vrenb200_radix_sort_pairs_host_async(lane["stream"].cuda_stream, hk_in.data_ptr(), hv_in.data_ptr(), lane["hk"].data_ptr(),
-                                                            lane["hv"].data_ptr(), n, lane["work"].data_ptr(), wbytes), "radix_sort_pairs_host_async")
+        def issue(i):
+            lane = lanes[i % 2]
+            vlib.check(lib.vrenb200_radix_sort_pairs_host_async(lane["stream"].cuda_stream, hk_in.data_ptr(), hv_in.data_ptr(), lane["hk"].data_ptr(),
+                                                                lane["hv"].data_ptr(), n, lane["work"].data_ptr(), wbytes), "radix_sort_pairs_host_async")
 
-    def drain():
+        def drain():
+            for lane in lanes:
+                lane["stream"].synchronize()
+
+        issue(0); issue(1); drain()                      # warm-up
+        t0 = time.perf_counter()
+        issue(0); drain()
+        single_ms = (time.perf_counter() - t0) * 1e3     # one call alone: upload, sort, download back to back
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            issue(i)
+        drain()
+        e2e_step_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
         for lane in lanes:
-            lane["stream"].synchronize()
+            hkn = lane["hk"].numpy().view("uint32")
+            assert bool((hkn[1:] >= hkn[:-1]).all()), "bench e2e: output not sorted"
+        assert bool(torch.equal(hk_in[(lanes[0]["hv"].to(torch.int64) & 0xFFFFFFFF) - rank * n], lanes[0]["hk"])), "bench e2e: pairs broken"
+        d2h_bytes = 8 * n
+        e2e_note = "consecutive steps alternate between two streams / device work buffers (upload of step i+1 overlaps download of step i)"
+        del lanes
+    else:
+        # the sharded sort with host shards: every step uploads the rank's 2 x 4n input bytes, runs the collective sort and
+        # downloads the rank's sorted shard (its share of the global result)
+        dk, dv = torch.empty_like(keys0), torch.empty_like(vals0)
+        hk_out = torch.empty(sorter.capacity, dtype=torch.int32, pin_memory=True)
+        hv_out = torch.empty(sorter.capacity, dtype=torch.int32, pin_memory=True)
+        ok, _ = sorter.result()
+        m = ok.numel()                                    # same keys every step: the shard size does not change
 
-    issue(0); issue(1); drain()                      # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    issue(0); drain()
-    single_ms = (time.perf_counter() - t0) * 1e3     # one call alone: upload, sort, download back to back
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        issue(i)
-    drain()
-    e2e_step_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    for lane in lanes:
-        hkn = lane["hk"].numpy().view("uint32")
-        assert os.environ.get("VRENB200_BENCH_NOVERIFY") == "1" or bool((hkn[1:] >= hkn[:-1]).all()), "bench e2e: output not sorted"
-    assert os.environ.get("VRENB200_BENCH_NOVERIFY") == "1" or bool(torch.equal(hk_in[lanes[0]["hv"].long()], lanes[0]["hk"])), "bench e2e: pairs broken"
-    te = torch.tensor([e2e_step_ms, single_ms], dtype=torch.float64, device=dev)
+        def e2e_step():
+            dk.copy_(hk_in, non_blocking=True)
+            dv.copy_(hv_in, non_blocking=True)
+            sorter.sort(dk, dv)
+            hk_out[:m].copy_(sorter.out_keys[:m], non_blocking=True)
+            hv_out[:m].copy_(sorter.out_vals[:m], non_blocking=True)
+
+        e2e_step(); barrier()
+        t0 = time.perf_counter()
+        e2e_step(); torch.cuda.synchronize()
+        single_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_step_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        hkn = hk_out[:m].numpy().view("uint32")
+        assert bool((hkn[1:] >= hkn[:-1]).all()), "bench e2e: shard not sorted"
+        d2h_bytes = 8 * m
+        e2e_note = "sharded sort with host shards: H2D of the rank's shard, collective sort, D2H of the rank's sorted shard"
+    te = torch.tensor([e2e_step_ms, single_ms, float(d2h_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n / (float(te[0].item()) * 1e-3) / 1e9
-    del lanes[1]["work"]
-    work = lanes[0].pop("work")
 
     secondary = None
-    if rank == 0 and world == 1 and not args.no_secondary:
-        del work
+    if not args.no_secondary:
         torch.cuda.empty_cache()
-        secondary = secondary_metrics(lib, vlib, dev)
+        if world == 1:
+            secondary = secondary_metrics(lib, vlib, dev)
+        else:
+            secondary = secondary_metrics_multi(lib, vlib, dev, sorter, rank, world)
     if rank == 0:
         peak, peak_src = measured_peaks()
         pass_avg_ms = sum(pass_ms) / len(pass_ms)
-        variant_name = (lib.vrenb200_radix_sort_variant_name(args.variant) if args.variant else
-                        lib.vrenb200_radix_sort_selected_variant_name(n, 1)).decode()
-        pass_kernel = "onesweep_count_first_kernel" if "count-first" in variant_name else "onesweep_pass_kernel"
+        variant_name = lib.vrenb200_radix_sort_selected_variant_name(n, 1, cfg_ptr).decode()
+        pass_kernel = "onesweep_pass_kernel"
         achieved = BYTES_PER_PAIR_PASS * n / (pass_avg_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, sec = cpu_sort_sample(min(args.log2n, 26), 1)
-            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"std::stable_sort by key of 2^{min(args.log2n, 26)} pairs, 1 thread, {sec:.1f} s"}
+            threads = os.cpu_count() or 1
+            v, sec = cpu_sort_sample(args.log2n, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"std::stable_sort by key of 2^{args.log2n} pairs (the whole step), {threads} threads, {sec:.1f} s"}
+        traffic = ncu_traffic(pass_kernel, args.log2n)
+        passes = 4
+        launches_single = 2 + 2 * passes                                   # histogram, offsets, 4 passes + their (idle) redo kernels
+        launches_multi = 4 + 2 + 1 + args.rounds * (1 + 2 + 6) + 2         # hist, publish, offsets, plan, partition + redo, wait, per round: transfer + wait + scan + 3 passes + 3 redos, compact, done
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"radix sort of 2^{args.log2n} uint32 key-value pairs per GPU (uniform keys, value=index)",
-                       "l2": "inputs larger than L2 (2 GiB restored between steps)",
+            "config": {"workload": workload_string(args.log2n),
+                       "l2": "inputs larger than L2 (2 GiB per GPU, restored or left untouched between steps)",
                        "variant": variant_name,
-                       "ranking_probe": "ascending lane order" if lib.vrenb200_radix_sort_ranking_probe() else "not ascending: ballot match",
+                       "ranking_check_failures": violation,
                        "parallelism": "1 GPU" if world == 1 else
-                       f"one global sort of {world}x2^{args.log2n} pairs: top-digit split + " +
-                       ("partition kernel storing into peer receive buffers over NVLink" if (world > 1 and exchange is not None)
-                        else "NCCL all-to-all-v") + " + local onesweep"},
+                       f"one global sort of {world}x2^{args.log2n} pairs: device plan, local partition by the top digit, {args.rounds} rounds of "
+                       "NVLink peer-store transfers overlapped with segmented 3-pass onesweep of what has arrived (no NCCL on the data path)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(pass_kernel, args.log2n), "kernel": pass_kernel,
-                         "peak_source": peak_src,
+                         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                         "traffic_source": traffic, "kernel": pass_kernel, "peak_source": peak_src,
                          "kernel_ms": pass_avg_ms, "histogram_ms": sum(hist_ms) / len(hist_ms),
                          "whole_sort_frac": BYTES_PER_PAIR_SORT * n / (ms_max * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-                    "ms_per_step": float(te[0].item()), "steps": e2e_steps,
-                    "issue": "consecutive steps alternate between two streams / device work buffers (upload of step i+1 overlaps download of step i)",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": int(te[2].item()),
+                    "ms_per_step": float(te[0].item()), "steps": e2e_steps, "issue": e2e_note,
                     "single_call_ms": float(te[1].item()), "single_call_value": world * n / (float(te[1].item()) * 1e-3) / 1e9},
-            "gpu_launches": (6 if world == 1 else (2 + 6 if exchange is not None else 1 + 1 + 2 + 6)) * args.steps,
+            "gpu_launches": (launches_single if world == 1 else launches_multi) * args.steps,
+            "verification": "sortedness + stability + pair integrity" if world == 1 else
+                            "2^22/rank global sort == oracle.sort_pairs; timed output: all-reduced pair-multiset checksum, per-shard sortedness and stability, cross-rank boundary order",
             "secondary": secondary,
-            "phases_rank0_last_step": phases_last if world > 1 else None,
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
     lib.vrenb200_sort_profile_destroy(prof)
     if world > 1:
+        sorter.close()
         dist.destroy_process_group()
 
 
+def secondary_metrics_multi(lib, vlib, dev, sorter, rank, world):
+    """N > 1: the other sharded paths of SURVEY 8e, device-timed (max over ranks): sharded exclusive scan and reduce over
+    2^28 u32 per GPU, sharded bucket sort (16-bit key) of 2^26 pairs per GPU, clustered shading of 8 views at 4K over the ranks"""
+    import math
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from vren_b200 import dist as vdist
+    from vren_b200 import synthetic
+    from vren_b200.pipeline import ViewBatch
+
+    peak, _ = measured_peaks()
+    out = {}
+
+    def timed(fn, iters=5):
+        ts = []
+        for i in range(iters + 2):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            if i >= 2:
+                ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([float(np.median(ts))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = 1 << 28
+    ops = vdist.CudaOps()
+    x = torch.ones(n, dtype=torch.int32, device=dev)
+    ms = timed(lambda: vdist.sharded_exclusive_scan(x, ops=ops))
+    out["sharded_scan_u32_2p28_per_gpu"] = {"ms": ms, "GB/s_per_gpu": 12 * n / ms / 1e6, "frac_hbm": 12 * n / ms / 1e6 / peak, "bytes_per_elt": 12,
+                                            "note": "local reduce (4 B) + all_gather of the partial sums + local scan with base (8 B); host reads the partials"}
+    ms = timed(lambda: vdist.sharded_reduce_add(x, ops=ops))
+    out["sharded_reduce_u32_2p28_per_gpu"] = {"ms": ms, "GB/s_per_gpu": 4 * n / ms / 1e6, "frac_hbm": 4 * n / ms / 1e6 / peak, "bytes_per_elt": 4}
+    del x
+    nb = 1 << 26
+    g = torch.Generator(device=dev)
+    g.manual_seed(77 + rank)
+    bk = torch.randint(0, 1 << 16, (nb,), dtype=torch.int32, device=dev, generator=g)
+    bv = torch.arange(nb, dtype=torch.int32, device=dev)
+    ms = timed(lambda: sorter.sort(bk, bv, key_bits=16))
+    out["sharded_bucket_sort_2p26_per_gpu"] = {"ms": ms, "Gpairs/s": world * nb / ms / 1e6,
+                                               "note": "16-bit key: partition digit = byte 1, one segmented pass; END offsets (all_reduce of 65536 counters) not timed"}
+    del bk, bv
+    # C5 batched: 8 views (yaw += 45 degrees) of a 3840x2160 frame, 65 536 lights broadcast once, one view per rank
+    w, h, L, views = 3840, 2160, 65536, 8
+    vb = ViewBatch(w, h, L)
+    pos = torch.zeros(L, 4, dtype=torch.float32, device=dev)
+    lights = torch.zeros(L, 4, dtype=torch.float32, device=dev)
+    if rank == 0:
+        p0, l0 = synthetic.point_lights(L, seed=2025, aspect=w / h, intensity=(1.0, 1.0))
+        pos, lights = torch.from_numpy(p0).to(dev), torch.from_numpy(l0).to(dev)
+    cam = vlib.Camera(np.float32(math.radians(45.0)), np.float32(w / h), np.float32(0.01), np.float32(1000.0))
+    frames = {v: (cam, synthetic.view_matrix(math.radians(45.0) * v, 0.0, (0, 0, 0)).tolist(),
+                  torch.from_numpy(synthetic.depth_buffer(w, h, seed=2024 + v)).to(dev), None) for v in vb.my_views(views)}
+    res = {}
+
+    def frame():
+        vb.set_lights(pos, lights, L)
+        res.update(vb(frames))
+
+    ms = timed(frame)
+    mine = {v: [int(t) for t in r.tolist()] for v, r in res.items()}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    per_view = {}
+    for d in gathered:
+        per_view.update(d)
+    out["light_assign_4k_65536_lights_8_views"] = {"ms_per_frame": ms, "ms_per_view": ms / views, "views": views,
+                                                   "views_per_rank": len(frames), "target_ms_per_view": 0.5,
+                                                   "clusters_per_view": [per_view[v][0] for v in sorted(per_view)],
+                                                   "assigned_lights_per_view": [per_view[v][4] for v in sorted(per_view)],
+                                                   "note": "lights broadcast once per frame (NCCL, inside the timed region), view v on rank v % world"}
+    return out
+
+
 def ncu_traffic(kernel, log2n):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+    (profiles/ncu_traffic.json records the commit the capture was taken at)."""
     try:
         rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))[kernel]
-        return rec["dram_bytes_per_launch"] if rec["log2n"] == log2n else None
+        return rec if rec["log2n"] == log2n else None
     except (OSError, KeyError, ValueError):
         return None
 
@@ -527,11 +707,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=28)
-    ap.add_argument("--variant", type=int, default=None)
-    ap.add_argument("--partition-shape", type=int, default=None, help="N>1: tile shape of the exchange pass (tuning)")
+    ap.add_argument("--variant", type=int, default=None, help="1-based entry of the kernel table (vrenb200_sort_config::variant)")
+    ap.add_argument("--ranking", default="auto", choices=["auto", "match", "verified", "sampled", "unverified"])
+    ap.add_argument("--tile-ids", default="auto", choices=["auto", "block", "ticket"])
+    ap.add_argument("--rounds", type=int, default=4, help="N>1: pieces the exchange is cut into (transfer of one overlaps the sorting of the previous)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use the NCCL all-to-all-v exchange instead of the fused P2P one")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

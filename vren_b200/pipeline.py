@@ -65,3 +65,50 @@ class ClusterAndShade:
                 self(width, height, camera, view16, depth, normals, positions, lights, light_count)
         torch.cuda.current_stream().wait_stream(side)
         return graph
+
+
+class ViewBatch:
+    """Batched multi-view clustered shading, one view per GPU (the reference runs one view per frame:
+    cluster_and_shade::operator(), clustered_shading.cpp:924-1172).
+
+    Views are independent — each has its own depth buffer, normals, camera and view matrix — so view v runs on rank
+    v % world with no exchange during the pass; the point lights of the frame are broadcast once (NCCL) from the rank that
+    holds them.  Every rank owns one ClusterAndShade (buffers allocated once) and runs its views back to back on its
+    stream.  With world == 1 (or no process group) all views run on this GPU."""
+
+    def __init__(self, width, height, max_point_lights, group=None, **limits):
+        import torch.distributed as dist
+
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.width, self.height = width, height
+        self.cs = ClusterAndShade(width, height, max_point_lights=max_point_lights, **limits)
+        self.positions = self.lights = None
+        self.light_count = 0
+
+    def my_views(self, num_views: int) -> list[int]:
+        return list(range(self.rank, num_views, self.world))
+
+    def set_lights(self, positions, lights, light_count: int, src: int = 0):
+        """positions / lights: float32 [L,4] device tensors (contents matter on rank `src` only): broadcast once per frame"""
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.broadcast(positions, src, group=self.group)
+            dist.broadcast(lights, src, group=self.group)
+        self.positions, self.lights, self.light_count = positions, lights, light_count
+
+    def __call__(self, frames: dict, on_view=None):
+        """frames: {view index: (camera, view16, depth, normals or None)} for THIS rank's views.  Runs them in view order on
+        the current stream; on_view(view index, cluster_and_shade) is called after each view has been enqueued (copy out what
+        you need: the buffers are reused by the next view).  Returns {view index: int32[8] device tensor} =
+        {cluster count, 1, 1, key overflow, assigned lights, index overflow, node tests, leaf tests}."""
+        out = {}
+        for v in sorted(frames):
+            camera, view16, depth, normals = frames[v]
+            self.cs(self.width, self.height, camera, view16, depth, normals, self.positions, self.lights, self.light_count)
+            out[v] = torch.cat([self.cs.dispatch_params, self.cs.status])
+            if on_view is not None:
+                on_view(v, self.cs)
+        return out
