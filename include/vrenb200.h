@@ -90,19 +90,22 @@ int vrenb200_blelloch_downsweep_u32(vrenb200_stream_t stream, uint32_t* buf, uin
  * there is no global selection state.  The defaults can be overridden through the environment, read once:
  * VRENB200_SORT_RANKING=match|verified|sampled|atomic, VRENB200_SORT_TILE_IDS=block|ticket. */
 enum {
-    VRENB200_RANKING_AUTO = 0,               /* = ATOMIC_VERIFIED */
+    VRENB200_RANKING_AUTO = 0,               /* = ATOMIC_SAMPLED */
     VRENB200_RANKING_MATCH = 1,              /* warp-ballot digit match: order by construction */
     VRENB200_RANKING_ATOMIC_VERIFIED = 2,    /* one returning shared atomic per pair; EVERY row is checked against the ballot match
-                                                off the critical path, and a pass that fails the check is repeated by the match
-                                                kernel before the next pass starts: correct whatever order the hardware serves
-                                                same-address lanes in (PTX does not specify it) */
-    VRENB200_RANKING_ATOMIC_SAMPLED = 3,     /* same, one row in eight checked */
+                                                and a pass that fails the check is repeated by the match kernel before the next
+                                                pass starts: correct whatever order the hardware serves same-address lanes in (PTX
+                                                does not specify it); slower than MATCH on B200, kept for validation */
+    VRENB200_RANKING_ATOMIC_SAMPLED = 3,     /* same with one row in eight checked (the checks run in production, on every sort:
+                                                ~10^5 checked rows with lane collisions per 2^28-pair pass): 1.5 % slower than
+                                                unchecked; a device that does not serve the lanes in order is caught in the
+                                                first tile and every such pass is redone by construction */
     VRENB200_RANKING_ATOMIC_UNVERIFIED = 4,  /* no check: relies on ascending lane order of same-address shared atomics */
     VRENB200_RANKING_SELFTEST_REDO = 5       /* tests: the verified kernels report a failed check and write nothing, so the
                                                 result is what the repeat pass alone produces */
 };
 enum {
-    VRENB200_TILE_IDS_AUTO = 0,              /* = BLOCK_INDEX, or TICKET under MPS / compute-sanitizer / a debugger (environment) */
+    VRENB200_TILE_IDS_AUTO = 0,              /* = TICKET (1.3 % slower than BLOCK_INDEX at 2^28 pairs) */
     VRENB200_TILE_IDS_BLOCK_INDEX = 1,       /* tile = block index: assumes CTAs of a 1-D grid start in index order (as CUB's
                                                 decoupled-look-back scan does) */
     VRENB200_TILE_IDS_TICKET = 2             /* tile = value of an atomic counter taken when the CTA starts: forward progress of
@@ -175,7 +178,8 @@ int vrenb200_sort_profile_read(vrenb200_sort_profile* p, float* ms_out);
  *               + 256 tiles for balanced keys); a plan that does not fit sets status[0] and leaves the output untouched
  *   rounds      1..8: how many pieces the exchange is cut into; the transfer of a piece overlaps the sorting of the one before
  *   peer_regions[r]  base of rank r's symmetric region as addressable from THIS rank (256-byte aligned), r = 0..world-1
- *   local       device scratch of this rank, vrenb200_sharded_sort_local_bytes(max_n, capacity) bytes, 256-byte aligned
+ *   local       device scratch of this rank, vrenb200_sharded_sort_local_bytes(max_n, capacity, cfg) bytes, 256-byte aligned
+ *               (the same cfg as create() gets: the tile of the passes depends on it)
  * create() zeroes this rank's flag words with a synchronous memset: call it on every rank, then synchronise the ranks once
  * (any barrier) before the first sort.  key_bits (32, 24, 16 or 8): how many low bits of the key take part (16 = the
  * bucket-sort key of bucket_sort.hpp:15-16; the whole 32-bit word is carried).
@@ -184,7 +188,7 @@ int vrenb200_sort_profile_read(vrenb200_sort_profile* p, float* ms_out);
  * bit 1: a round exceeds its launch bound (retry with rounds = 1 or a larger capacity). */
 typedef struct vrenb200_sharded_sort vrenb200_sharded_sort;
 size_t vrenb200_sharded_sort_symmetric_bytes(uint32_t capacity);
-size_t vrenb200_sharded_sort_local_bytes(uint32_t max_n, uint32_t capacity);
+size_t vrenb200_sharded_sort_local_bytes(uint32_t max_n, uint32_t capacity, const vrenb200_sort_config* cfg);
 int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_t rank, uint32_t world, uint32_t max_n, uint32_t capacity,
                                  uint32_t rounds, void* const* peer_regions, void* local, size_t local_bytes,
                                  const vrenb200_sort_config* cfg);

@@ -97,8 +97,9 @@ def test_sort_kernel_selection(handle):
         c = lib.SortConfig(**cfg)
         return handle.vrenb200_radix_sort_selected_variant_name(n, kv, C.addressof(c)).decode()
 
-    # default: atomic ranking with every row verified and a by-construction redo pass
-    assert "F_RANK_ATOMIC" in name(1 << 24, 1) and "F_VERIFY_ALL" in name(1 << 24, 1)
+    # default: atomic ranking with one row in eight verified and a by-construction redo pass
+    assert "F_RANK_ATOMIC" in name(1 << 24, 1) and "F_VERIFY_SAMPLED" in name(1 << 24, 1)
+    assert "F_VERIFY_ALL" in name(1 << 24, 1, ranking=lib.RANKING_ATOMIC_VERIFIED)
     assert handle.vrenb200_radix_sort_selected_variant_name(1 << 24, 1, None).decode() == name(1 << 24, 1)
     m = dict(ranking=lib.RANKING_MATCH)
     assert name(1 << 24, 1, **m).startswith("256x46/") and "F_RANK_LEADER" in name(1 << 24, 1, **m) and "ATOMIC" not in name(1 << 24, 1, **m)

@@ -89,9 +89,11 @@ struct sort_variant
     int (*preload)(int layout, bool segmented);
 };
 
-// what VRENB200_RANKING_AUTO / VRENB200_TILE_IDS_AUTO resolve to (measured choices)
-#define VRENB200_RANKING_DEFAULT VRENB200_RANKING_ATOMIC_VERIFIED
-#define VRENB200_TILE_IDS_DEFAULT VRENB200_TILE_IDS_BLOCK_INDEX
+// what VRENB200_RANKING_AUTO / VRENB200_TILE_IDS_AUTO resolve to (measured, profiles/r2d_sort_variant_sweep.log, 2^28 pairs):
+// atomic ranking unchecked 71.1 Gpairs/s, one row in eight checked 70.1, every row checked 54.3 (its match work spills and
+// fills the ALU pipe), ballot match 61.7; tickets instead of block indices cost 1.3 %
+#define VRENB200_RANKING_DEFAULT VRENB200_RANKING_ATOMIC_SAMPLED
+#define VRENB200_TILE_IDS_DEFAULT VRENB200_TILE_IDS_TICKET
 
 struct sort_options
 {

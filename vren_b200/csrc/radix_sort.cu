@@ -979,10 +979,6 @@ sort_options resolve_options(const vrenb200_sort_config* cfg)
                       : !std::strcmp(e, "atomic") ? VRENB200_RANKING_ATOMIC_UNVERIFIED : VRENB200_RANKING_AUTO;
         if (const char* e = std::getenv("VRENB200_SORT_TILE_IDS"))
             o.tile_ids = !std::strcmp(e, "ticket") ? VRENB200_TILE_IDS_TICKET : !std::strcmp(e, "block") ? VRENB200_TILE_IDS_BLOCK_INDEX : VRENB200_TILE_IDS_AUTO;
-        // a time-sliced / MPS / debugged context is where in-order CTA dispatch is least certain: tickets there
-        if (o.tile_ids == VRENB200_TILE_IDS_AUTO && (std::getenv("CUDA_MPS_PIPE_DIRECTORY") || std::getenv("CUDA_MPS_LOG_DIRECTORY") ||
-                                                     std::getenv("NV_COMPUTE_SANITIZER_INJECTION") || std::getenv("CUDA_DEBUGGER_SOFTWARE_PREEMPTION")))
-            o.tile_ids = VRENB200_TILE_IDS_TICKET;
         return o;
     }();
     sort_options o = env;
@@ -1004,9 +1000,9 @@ const sort_variant& pick_variant(uint32_t n, int layout, const sort_options& opt
     switch (opt.ranking)
     {
     case VRENB200_RANKING_MATCH: group = 0; break;
-    case VRENB200_RANKING_ATOMIC_SAMPLED: group = 2; break;
     case VRENB200_RANKING_ATOMIC_UNVERIFIED: group = 3; break;
-    default: group = 1; break;   // ATOMIC_VERIFIED, SELFTEST
+    case VRENB200_RANKING_ATOMIC_VERIFIED: group = 1; break;
+    default: group = 2; break;   // ATOMIC_SAMPLED (the default), SELFTEST
     }
     const int size = n < kSmallTileBelow ? 0 : (layout == LAYOUT_KEYS ? 1 : 2);
     return g_variants[group * 3 + size];

@@ -10,18 +10,20 @@
 //                 result on every rank): the partition digit p* = highest byte in which the keys differ at all, contiguous
 //                 ranges of its 256 values per rank balanced by count, where every (source, digit) block lands in its owner's
 //                 receive buffer, rounds -> local PARTITION of the shard by digit p* (one onesweep pass)
-//   copy stream   per round: TRANSFER kernel — plain coalesced peer stores of the round's (digit, source) blocks into their
-//                 owners' receive buffers, 128-byte lines of the destination per warp; while it copies a block it counts the
-//                 lower digits of the keys (shared atomics) and adds them to the OWNER's per-segment histograms (remote
-//                 atomics), so the receiver never re-reads what it received; the last CTA raises the round's flag in every peer
-//   sort stream   per round: wait for the round's flags of all sources -> scan the segment histograms -> p* SEGMENTED onesweep
-//                 passes (radix_sort.cu, F_SEGMENTED) over the round's tile-aligned segments; the last pass writes the
-//                 segments back to back into the output.
+//   copy stream   per round: TRANSFER kernel — a few one-warp CTAs, each driving a ring of TMA bulk copies: global -> shared
+//                 (local HBM) and shared -> global (the owner's receive buffer, a peer-mapped address over NVLink).  It needs
+//                 no registers or load/store slots to speak of, so the SMs stay with the passes it overlaps; the local
+//                 partition is laid out so that every block is 16-byte co-aligned with its destination; the last CTA raises
+//                 the round's flag in every peer
+//   sort stream   per round: wait for the round's flags of all sources -> digit histograms of the round's segments (one read of
+//                 the received keys) -> scan -> p* SEGMENTED onesweep passes (radix_sort.cu, F_SEGMENTED) over the round's
+//                 tile-aligned segments; the last pass writes the segments back to back into the output.
 // The receive buffer is laid out by digit, inside a digit by source rank, inside a source in input order: concatenating the
 // ranks' outputs gives the stable sort of the concatenated input.  Transfers of round k+1 overlap the sorting of round k
-// (NVLink-bound against HBM-bound work).  Per pair and GPU: 4 (histogram) + 16 (partition) + 16 (transfer) + 16 p* bytes of
-// HBM traffic and 8 (G-1)/G bytes each way over NVLink.
+// (NVLink-bound against HBM-bound work).  Per pair and GPU: 4 (histogram) + 16 (partition) + 16 (transfer) + 4 (segment
+// histograms) + 16 p* bytes of HBM traffic and 8 (G-1)/G bytes each way over NVLink.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -31,9 +33,14 @@ namespace vrenb200 {
 namespace {
 
 constexpr int kMaxRanks = 32;
-constexpr int kXferThreads = 256;   // == kRadix: one thread per digit value in the table steps
-constexpr int kXferWarps = kXferThreads / 32;
-constexpr int kXferCtasPerSm = 4;
+// The transfer kernel is NVLink-bound and must leave the SMs to the segmented passes it overlaps with: one warp per CTA drives a
+// ring of TMA bulk copies (kXferStages x 2 x kXferChunk x 4 bytes of shared memory); one CTA of the pass kernel still fits
+// next to it on an SM.
+constexpr int kXferChunk = 2048;          // pairs per stage: 8 KB of keys + 8 KB of values
+constexpr int kXferStages = 6;
+constexpr int kXferDefaultCtas = 32;
+constexpr size_t kXferSmem = (size_t) kXferStages * 2 * kXferChunk * sizeof(uint32_t) + 256;
+constexpr uint32_t kPartSlack = 1024;     // the local partition leaves up to 3 pairs of padding in front of every digit
 
 // ---- symmetric region ---------------------------------------------------------------------------------------------------------
 struct sym_header
@@ -57,7 +64,7 @@ struct xfer_plan
     uint32_t dst_off[kRadix];      // where this rank's block of the digit starts in the owner's receive buffer
     uint8_t owner[kRadix];
     uint8_t round_of[kRadix];
-    uint32_t cum_lines[kMaxRounds][kRadix];   // per round: inclusive prefix over the digit values of the 128-byte destination lines
+    uint32_t cum_pairs[kMaxRounds][kRadix];   // per round: inclusive prefix over the digit values of the pairs this rank sends
     uint32_t finished[kMaxRounds];            // CTAs of the round's transfer kernel that are done (reset by the last one)
 };
 
@@ -111,7 +118,7 @@ publish_histograms_kernel(const sort_control* ctl, peer_table peers, shard_param
 // One CTA of 256 threads, thread d owns the value d of every digit.  Every rank runs it on the same all-gathered
 // histograms and gets the same ranges, owners, segment layouts and rounds.
 __global__ void __launch_bounds__(kRadix)
-plan_kernel(sym_header* mine, const sort_control* ctl_part, shard_params sp, seg_plan* plan, xfer_plan* xp, uint16_t* tile_seg,
+plan_kernel(sym_header* mine, sort_control* ctl_part, shard_params sp, seg_plan* plan, xfer_plan* xp, uint16_t* tile_seg,
             uint32_t* status)
 {
     __shared__ unsigned long long s_cum[kRadix];     // inclusive prefix of the counts of the partition digit
@@ -231,20 +238,35 @@ plan_kernel(sym_header* mine, const sort_control* ctl_part, shard_params sp, seg
     uint32_t round_of = 0;
     for (uint32_t k = 1; k < sp.rounds; k++) round_of += s_round_digit[owner][k] <= d;
 
-    // sender side: where my block of digit d goes and how many 128-byte destination lines it covers
+    // sender side: where my block of digit d goes.  The local partition pass scatters digit d to ctl_part->hist[pstar][d];
+    // those offsets are re-laid here with up to 3 pairs of padding in front of every digit, so that a block starts at the
+    // same offset modulo 16 bytes in the partitioned shard and in its owner's receive buffer (bulk copies need both aligned)
+    __shared__ uint32_t s_len[kRadix], s_dst[kRadix];
     uint32_t before_me = 0;
     for (uint32_t s = 0; s < sp.rank; s++) before_me += mine->hist_all[s][pstar][d];
     const uint32_t my_len = mine->hist_all[sp.rank][pstar][d];
     const uint32_t dst_off = first_tile * sp.tile + before_me;
-    xp->src_off[d] = ctl_part->hist[pstar][d];      // exclusive offsets of the local shard (the partition pass scatters to them)
+    s_len[d] = my_len;
+    s_dst[d] = dst_off;
     xp->len[d] = my_len;
     xp->dst_off[d] = dst_off;
     xp->owner[d] = (uint8_t) owner;
     xp->round_of[d] = (uint8_t) round_of;
-    const uint32_t lines = my_len ? ((dst_off & 31u) + my_len + 31u) / 32u : 0u;
+    __syncthreads();
+    if (d == 0)
+    {
+        uint32_t cur = 0;
+        for (uint32_t i = 0; i < kRadix; i++)
+        {
+            cur += (s_dst[i] - cur) & 3u;
+            xp->src_off[i] = cur;
+            ctl_part->hist[pstar][i] = cur;
+            cur += s_len[i];
+        }
+    }
     for (uint32_t k = 0; k < sp.rounds; k++)
     {
-        uint32_t linc = round_of == k ? lines : 0u;
+        uint32_t linc = round_of == k ? my_len : 0u;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1)
         {
@@ -255,7 +277,7 @@ plan_kernel(sym_header* mine, const sort_control* ctl_part, shard_params sp, seg
         if (lane == 31) s_warp[warp] = linc;
         __syncthreads();
         for (unsigned w = 0; w < warp; w++) linc += s_warp[w];
-        xp->cum_lines[k][d] = linc;
+        xp->cum_pairs[k][d] = linc;
     }
 
     // receiver side: my segments
@@ -307,100 +329,219 @@ plan_kernel(sym_header* mine, const sort_control* ctl_part, shard_params sp, seg
 }
 
 // ---- TRANSFER of one round --------------------------------------------------------------------------------------------------------
-// Persistent CTAs; the round's destination lines (128 bytes of a receive buffer) are split evenly, in order, over the CTAs, so a
-// CTA works on one or two digits and flushes its lower-digit histograms once per digit.
-__global__ void __launch_bounds__(kXferThreads, kXferCtasPerSm)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+// One warp per CTA.  The pairs this rank sends in the round are split evenly, in digit order, over the CTAs.  Inside a
+// (digit, source) block the 16-byte-aligned body moves in chunks through a ring in shared memory: lane 0 keeps
+// kXferStages - 2 chunk loads in flight (cp.async.bulk global -> shared, local HBM) and stores every landed chunk with
+// cp.async.bulk shared -> global into the owner's receive buffer (local, or a peer's over NVLink); the up to 3 pairs before
+// and after the aligned body go through registers.
+__global__ void __launch_bounds__(32, 1)
 transfer_round_kernel(const uint32_t* __restrict__ part_keys, const uint32_t* __restrict__ part_vals, const seg_plan* plan,
                       xfer_plan* xp, peer_table peers, shard_params sp, uint32_t round)
 {
-    __shared__ uint32_t s_hist[kPasses - 1][kRadix];
+    extern __shared__ __align__(128) unsigned char xfer_smem[];
+    uint32_t* ring_k = reinterpret_cast<uint32_t*>(xfer_smem);                       // [stages][chunk]
+    uint32_t* ring_v = ring_k + kXferStages * kXferChunk;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring_v + kXferStages * kXferChunk); // one mbarrier per stage
     __shared__ uint32_t s_cum[kRadix];
-    __shared__ bool s_last;
-    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool skip = plan->error != 0;
-    const uint32_t pstar = plan->pstar;
-    if (!skip)
+    __shared__ uint32_t* s_dst_k[kXferStages];
+    __shared__ uint32_t* s_dst_v[kXferStages];
+    __shared__ uint32_t s_count[kXferStages];
+    const unsigned lane = threadIdx.x;
+    if (plan->error == 0)
     {
-        s_cum[tid] = xp->cum_lines[round][tid];
-#pragma unroll
-        for (int p = 0; p < kPasses - 1; p++) s_hist[p][tid] = 0;
-        __syncthreads();
-        const uint32_t total_lines = s_cum[kRadix - 1];
-        const uint32_t begin = (uint32_t) ((unsigned long long) total_lines * blockIdx.x / gridDim.x);
-        const uint32_t end = (uint32_t) ((unsigned long long) total_lines * (blockIdx.x + 1) / gridDim.x);
-        uint32_t line = begin;
-        while (line < end)
+        for (uint32_t i = lane; i < kRadix; i += 32) s_cum[i] = xp->cum_pairs[round][i];
+        if (lane == 0)
         {
-            // the digit this line belongs to: first value whose inclusive prefix exceeds it
-            uint32_t lo = 0, hi = kRadix - 1;
+            for (int s = 0; s < kXferStages; s++) mbar_init_(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        const uint32_t total = s_cum[kRadix - 1];
+        const uint32_t begin = (uint32_t) ((unsigned long long) total * blockIdx.x / gridDim.x);
+        const uint32_t end = (uint32_t) ((unsigned long long) total * (blockIdx.x + 1) / gridDim.x);
+        uint32_t issued = 0, stored = 0;      // chunks (lane 0)
+        auto store_one = [&]() {
+            const uint32_t st = stored % kXferStages;
+            mbar_wait_(&full[st], (stored / kXferStages) & 1u);
+            bulk_s2g(s_dst_k[st], ring_k + st * kXferChunk, s_count[st] * 4u);
+            bulk_s2g(s_dst_v[st], ring_v + st * kXferChunk, s_count[st] * 4u);
+            bulk_commit();
+            stored++;
+        };
+        uint32_t pos = begin;
+        while (pos < end)
+        {
+            uint32_t lo = 0, hi = kRadix - 1;            // the digit of pair `pos`: first value whose inclusive prefix exceeds it
             while (lo < hi)
             {
                 const uint32_t mid = (lo + hi) / 2;
-                if (s_cum[mid] <= line) lo = mid + 1; else hi = mid;
+                if (s_cum[mid] <= pos) lo = mid + 1; else hi = mid;
             }
             const uint32_t dgt = lo;
-            const uint32_t digit_first = dgt > 0 ? s_cum[dgt - 1] : 0u;
-            const uint32_t piece_end = s_cum[dgt] < end ? s_cum[dgt] : end;          // lines [line, piece_end) of digit dgt
-            const uint32_t len = xp->len[dgt], dst_off = xp->dst_off[dgt], owner = xp->owner[dgt];
-            const uint32_t* src_k = part_keys + xp->src_off[dgt];
-            const uint32_t* src_v = part_vals + xp->src_off[dgt];
+            const uint32_t first = dgt > 0 ? s_cum[dgt - 1] : 0u;
+            const uint32_t piece_end = s_cum[dgt] < end ? s_cum[dgt] : end;
+            const uint32_t e0 = pos - first, e1 = piece_end - first;      // pairs [e0, e1) of this rank's block of the digit
+            const uint32_t owner = xp->owner[dgt], dst_off = xp->dst_off[dgt], src_off = xp->src_off[dgt];
+            const uint32_t* src_k = part_keys + src_off;
+            const uint32_t* src_v = part_vals + src_off;
             uint32_t* dst_k = peers.recv_keys[owner] + dst_off;
             uint32_t* dst_v = peers.recv_vals[owner] + dst_off;
-            const int32_t mis = (int32_t) (dst_off & 31u);                            // elements past a 128-byte line of the destination
-            constexpr int U = 4;
-            for (uint32_t j0 = line - digit_first + warp; j0 < piece_end - digit_first; j0 += kXferWarps * U)
+            // aligned body [b0, b1): (dst_off + e) % 4 == 0 at b0 (and (src_off + e) % 4 == 0 too: the plan made them congruent)
+            uint32_t b0 = e0 + ((4u - ((dst_off + e0) & 3u)) & 3u);
+            if (b0 > e1) b0 = e1;
+            const uint32_t b1 = b0 + ((e1 - b0) & ~3u);
+            // head and tail through registers
+            for (uint32_t e = e0 + lane; e < b0; e += 32) { dst_k[e] = src_k[e]; dst_v[e] = src_v[e]; }
+            for (uint32_t e = b1 + lane; e < e1; e += 32) { dst_k[e] = src_k[e]; dst_v[e] = src_v[e]; }
+            if (lane == 0)
             {
-                uint32_t k[U], v[U];
-                int32_t e[U];
-#pragma unroll
-                for (int u = 0; u < U; u++)
+                for (uint32_t c0 = b0; c0 < b1; c0 += kXferChunk)
                 {
-                    const uint32_t j = j0 + u * kXferWarps;
-                    e[u] = (int32_t) (j * 32u) - mis + (int32_t) lane;
-                    const bool in = j < piece_end - digit_first && e[u] >= 0 && e[u] < (int32_t) len;
-                    if (!in) e[u] = -1;
-                    k[u] = in ? ldg_stream_u32(src_k + e[u]) : 0u;
-                    v[u] = in ? ldg_stream_u32(src_v + e[u]) : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (e[u] >= 0)
-                    {
-                        dst_k[e[u]] = k[u];
-                        dst_v[e[u]] = v[u];
-                        if (pstar > 0) atomicAdd(&s_hist[0][k[u] & 0xFFu], 1u);
-                        if (pstar > 1) atomicAdd(&s_hist[1][(k[u] >> 8) & 0xFFu], 1u);
-                        if (pstar > 2) atomicAdd(&s_hist[2][(k[u] >> 16) & 0xFFu], 1u);
-                    }
-            }
-            __syncthreads();
-            // this CTA's share of the digit's lower-digit histograms goes to the segment's owner
-            uint32_t* remote = &peers.hdr[owner]->seg_hist[dgt][0][0];
-#pragma unroll
-            for (int p = 0; p < kPasses - 1; p++)
-            {
-                const uint32_t c = s_hist[p][tid];
-                if (c != 0)
-                {
-                    atomicAdd(remote + p * kRadix + tid, c);
-                    s_hist[p][tid] = 0;
+                    const uint32_t count = b1 - c0 < (uint32_t) kXferChunk ? b1 - c0 : (uint32_t) kXferChunk;
+                    // the stage is free once the store that last used it has read it: stores complete in order, and all but
+                    // the two most recent chunks have been stored before a new load is issued
+                    while (stored + (kXferStages - 2) < issued) store_one();
+                    if (issued >= (uint32_t) kXferStages) bulk_wait_read<1>();
+                    const uint32_t st = issued % kXferStages;
+                    s_dst_k[st] = dst_k + c0;
+                    s_dst_v[st] = dst_v + c0;
+                    s_count[st] = count;
+                    mbar_expect_tx_(&full[st], count * 8u);
+                    bulk_g2s(ring_k + st * kXferChunk, src_k + c0, count * 4u, &full[st]);
+                    bulk_g2s(ring_v + st * kXferChunk, src_v + c0, count * 4u, &full[st]);
+                    issued++;
                 }
             }
-            __syncthreads();
-            line = piece_end;
+            pos = piece_end;
         }
+        if (lane == 0)
+        {
+            while (stored < issued) store_one();
+            bulk_wait_all();
+            asm volatile("fence.proxy.async;" ::: "memory");   // the bulk stores went through the async proxy: order them before the flag
+        }
+        __syncwarp();
     }
     // completion: the last CTA of the round tells every peer that this rank's part of the round has arrived
     __threadfence_system();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&xp->finished[round], 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (s_last)
+    __syncwarp();
+    uint32_t last = 0;
+    if (lane == 0) last = atomicAdd(&xp->finished[round], 1u) == gridDim.x - 1;
+    last = __shfl_sync(kFullMask, last, 0);
+    if (last)
     {
         __threadfence_system();
-        if (tid < sp.world) st_release_sys(&peers.hdr[tid]->round_ready[round][sp.rank], sp.epoch);
-        if (tid == 0) xp->finished[round] = 0;
+        if (lane < sp.world) st_release_sys(&peers.hdr[lane]->round_ready[round][sp.rank], sp.epoch);
+        if (lane == 0) xp->finished[round] = 0;
     }
+}
+
+// ---- digit histograms of the round's segments (receiver side) --------------------------------------------------------------------
+// One read of the received keys: per segment (value of the partition digit) the 256-bin histograms of the digits below it.
+// Conflict-free columns as in radix_histogram_columns_kernel (every lane owns a column of every counter); a CTA takes a
+// contiguous range of the round's tiles and flushes its counters to the segment's table whenever the segment changes.
+constexpr int kSegHistThreads = 1024;
+constexpr size_t kSegHistSmem = (size_t) (kPasses - 1) * kRadix * 32 * sizeof(uint32_t);
+
+__global__ void __launch_bounds__(kSegHistThreads, 1)
+segment_histograms_kernel(const uint32_t* __restrict__ recv_keys, sym_header* mine, const seg_plan* plan, const uint16_t* __restrict__ tile_seg,
+                          uint32_t tile, uint32_t round)
+{
+    extern __shared__ __align__(128) uint32_t s_cols[];   // [3][256][32]
+    const uint32_t pstar = plan->pstar;
+    if (plan->error != 0 || pstar == 0) return;
+    const uint32_t t0 = plan->round_tile[round], t1 = plan->round_tile[round + 1];
+    const uint32_t begin = t0 + (uint32_t) ((unsigned long long) (t1 - t0) * blockIdx.x / gridDim.x);
+    const uint32_t end = t0 + (uint32_t) ((unsigned long long) (t1 - t0) * (blockIdx.x + 1) / gridDim.x);
+    if (begin >= end) return;
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t i = tid; i < (kPasses - 1) * kRadix * 32; i += kSegHistThreads) s_cols[i] = 0;
+    __syncthreads();
+    uint32_t* col = s_cols + lane;
+    auto count = [&](uint32_t k) {
+        atomicAdd(&col[(0 * kRadix + (k & 0xFF)) * 32], 1u);
+        if (pstar > 1) atomicAdd(&col[(1 * kRadix + ((k >> 8) & 0xFF)) * 32], 1u);
+        if (pstar > 2) atomicAdd(&col[(2 * kRadix + ((k >> 16) & 0xFF)) * 32], 1u);
+    };
+    auto flush = [&](uint32_t seg) {
+        __syncthreads();
+        if (tid < (kPasses - 1) * kRadix)
+        {
+            uint32_t sum = 0;
+#pragma unroll 8
+            for (uint32_t k = 0; k < 32; k++)
+            {
+                const uint32_t idx = tid * 32 + ((k + tid) & 31);
+                sum += s_cols[idx];
+                s_cols[idx] = 0;
+            }
+            if (sum != 0) atomicAdd(&mine->seg_hist[seg][0][0] + tid, sum);
+        }
+        __syncthreads();
+    };
+    uint32_t cur_seg = tile_seg[begin];
+    for (uint32_t t = begin; t < end; t++)
+    {
+        const uint32_t seg = tile_seg[t];
+        if (seg != cur_seg)
+        {
+            flush(cur_seg);
+            cur_seg = seg;
+        }
+        const seg_desc sd = plan->seg[seg];
+        const uint32_t left = sd.len - (t - sd.first_tile) * tile;
+        const uint32_t valid = left < tile ? left : tile;
+        const uint4* k4 = reinterpret_cast<const uint4*>(recv_keys + (size_t) t * tile);
+        const uint32_t n4 = valid / 4;
+        uint32_t i = tid;
+        for (; i + kSegHistThreads < n4; i += 2 * kSegHistThreads)
+        {
+            const uint4 a = ldg_stream_u4(k4 + i), b = ldg_stream_u4(k4 + i + kSegHistThreads);
+            count(a.x); count(a.y); count(a.z); count(a.w);
+            count(b.x); count(b.y); count(b.z); count(b.w);
+        }
+        for (; i < n4; i += kSegHistThreads)
+        {
+            const uint4 a = ldg_stream_u4(k4 + i);
+            count(a.x); count(a.y); count(a.z); count(a.w);
+        }
+        for (uint32_t e = n4 * 4 + tid; e < valid; e += kSegHistThreads) count(recv_keys[(size_t) t * tile + e]);
+    }
+    flush(cur_seg);
 }
 
 // ---- small stream-ordering kernels ----------------------------------------------------------------------------------------------
@@ -474,6 +615,7 @@ struct vrenb200_sharded_sort
     uint32_t max_n, capacity;
     sort_options opt;
     const sort_variant* var_seg;
+    uint32_t xfer_ctas;
     cudaStream_t copy_stream, sort_stream;
     cudaEvent_t ev_part, ev_copy, ev_sort;
     int device;
@@ -502,13 +644,13 @@ size_t seg_control_bytes(uint32_t cap_tiles)
 
 extern "C" size_t vrenb200_sharded_sort_symmetric_bytes(uint32_t capacity) { return sym_bytes(capacity); }
 
-extern "C" size_t vrenb200_sharded_sort_local_bytes(uint32_t max_n, uint32_t capacity)
+extern "C" size_t vrenb200_sharded_sort_local_bytes(uint32_t max_n, uint32_t capacity, const vrenb200_sort_config* cfg)
 {
-    const sort_options opt = resolve_options(nullptr);
+    const sort_options opt = resolve_options(cfg);
     const uint32_t tile = segment_variant(capacity, opt).tile;
     const uint32_t cap_tiles = capacity / tile;
     size_t b = 0;
-    b += 2 * align_up((size_t) max_n * 4, 256);               // locally partitioned shard
+    b += 2 * align_up(((size_t) max_n + kPartSlack) * 4, 256);  // locally partitioned shard (digits padded to their destinations' alignment)
     b += 4 * align_up((size_t) capacity * 4, 256);            // ping-pong partner of the receive buffers, output
     b += control_bytes(max_n) + seg_control_bytes(cap_tiles);
     b += align_up(sizeof(uint32_t) * kMaxRounds * (kPasses - 1), 256) + align_up(sizeof(seg_plan), 256) + align_up(sizeof(xfer_plan), 256);
@@ -523,7 +665,7 @@ extern "C" int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_
     if (out == nullptr || peer_regions == nullptr || local == nullptr) return VRENB200_EINVAL_ARG;
     if (world == 0 || world > (uint32_t) kMaxRanks || rank >= world || rounds == 0 || rounds > (uint32_t) kMaxRounds) return VRENB200_EINVAL_ARG;
     if (max_n >= (1u << 30) || capacity >= (1u << 30)) return VRENB200_ELIMIT;
-    if (local_bytes < vrenb200_sharded_sort_local_bytes(max_n, capacity)) return VRENB200_ESCRATCH;
+    if (local_bytes < vrenb200_sharded_sort_local_bytes(max_n, capacity, cfg)) return VRENB200_ESCRATCH;
     if (reinterpret_cast<uintptr_t>(local) & 255) return VRENB200_EALIGN;
     vrenb200_sharded_sort* c = new (std::nothrow) vrenb200_sharded_sort();
     if (c == nullptr) return VRENB200_ECUDA;
@@ -549,8 +691,8 @@ extern "C" int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_
         c->peers.recv_vals[r] = reinterpret_cast<uint32_t*>(base + sym_recv_offset() + align_up((size_t) capacity * 4, 256));
     }
     scratch_carver carve(local);
-    c->part_keys = carve.take<uint32_t>(max_n);
-    c->part_vals = carve.take<uint32_t>(max_n);
+    c->part_keys = carve.take<uint32_t>((size_t) max_n + kPartSlack);
+    c->part_vals = carve.take<uint32_t>((size_t) max_n + kPartSlack);
     c->alt_keys = carve.take<uint32_t>(capacity);
     c->alt_vals = carve.take<uint32_t>(capacity);
     c->out_keys = carve.take<uint32_t>(capacity);
@@ -562,8 +704,17 @@ extern "C" int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_
     c->xp = carve.take<xfer_plan>(1);
     c->tile_seg = carve.take<uint16_t>(c->sp.cap_tiles + 1);
     c->status = carve.take<uint32_t>(8);
-    if (cudaGetDevice(&c->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->sort_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    c->xfer_ctas = kXferDefaultCtas;   // one warp each; 32 keep ~2 MB of copies in flight
+    if (const char* e = std::getenv("VRENB200_XFER_CTAS"))     // measurement knob, read when the context is created
+    {
+        const long v = std::strtol(e, nullptr, 10);
+        if (v >= 1 && v <= 4 * kNumSMs) c->xfer_ctas = (uint32_t) v;
+    }
+    // the copy stream outranks the sort stream: when an SM frees room, a waiting transfer CTA takes it before the next pass CTA
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaGetDevice(&c->device) != cudaSuccess || cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->sort_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_part, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_sort, cudaEventDisableTiming) != cudaSuccess)
@@ -579,9 +730,12 @@ extern "C" int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_
         if (st == VRENB200_OK) st = preload_sort_kernels(LAYOUT_SOA, true, c->opt);
         const void* kernels[] = {(const void*) publish_histograms_kernel, (const void*) plan_kernel, (const void*) transfer_round_kernel,
                                  (const void*) wait_round_kernel, (const void*) wait_peers_done_kernel, (const void*) signal_done_kernel,
-                                 (const void*) scan_segment_histograms_kernel, (const void*) compact_segments_kernel};
+                                 (const void*) scan_segment_histograms_kernel, (const void*) compact_segments_kernel,
+                                 (const void*) segment_histograms_kernel};
         for (const void* k : kernels)
             if (st == VRENB200_OK) st = check_cuda(cudaFuncGetAttributes(&attr, k));
+        if (st == VRENB200_OK) st = check_cuda(cudaFuncSetAttribute(transfer_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kXferSmem));
+        if (st == VRENB200_OK) st = check_cuda(cudaFuncSetAttribute(segment_histograms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSegHistSmem));
         if (st != VRENB200_OK)
         {
             delete c;
@@ -673,7 +827,7 @@ extern "C" int vrenb200_sharded_sort_pairs(vrenb200_sharded_sort* c, vrenb200_st
     VRENB200_TRY(check_launch());
     for (uint32_t k = 0; k < sp.rounds; k++)
     {
-        transfer_round_kernel<<<kNumSMs * kXferCtasPerSm, kXferThreads, 0, c->copy_stream>>>(c->part_keys, c->part_vals, c->plan, c->xp, c->peers, sp, k);
+        transfer_round_kernel<<<c->xfer_ctas, 32, kXferSmem, c->copy_stream>>>(c->part_keys, c->part_vals, c->plan, c->xp, c->peers, sp, k);
         VRENB200_TRY(check_launch());
     }
     VRENB200_TRY(check_cuda(cudaEventRecord(c->ev_copy, c->copy_stream)));
@@ -683,6 +837,9 @@ extern "C" int vrenb200_sharded_sort_pairs(vrenb200_sharded_sort* c, vrenb200_st
     for (uint32_t k = 0; k < sp.rounds; k++)
     {
         wait_round_kernel<<<1, 32, 0, c->sort_stream>>>(mine, sp, k);
+        VRENB200_TRY(check_launch());
+        segment_histograms_kernel<<<kNumSMs, kSegHistThreads, kSegHistSmem, c->sort_stream>>>(c->peers.recv_keys[sp.rank], mine, c->plan, c->tile_seg,
+                                                                                              sp.tile, k);
         VRENB200_TRY(check_launch());
         scan_segment_histograms_kernel<<<kRadix * (kPasses - 1), kRadix, 0, c->sort_stream>>>(mine, c->plan, k);
         VRENB200_TRY(check_launch());

@@ -209,7 +209,8 @@ class ShardedSort:
         self.rank, self.world, self.max_n, self.capacity, self.rounds = rank, world, max_n, capacity, rounds
         self.regions = regions
         dev = regions[rank].device
-        self.local = torch.empty(self.lib.vrenb200_sharded_sort_local_bytes(max_n, capacity), dtype=torch.uint8, device=dev)
+        cfg_ptr = C.addressof(config) if config is not None else None
+        self.local = torch.empty(self.lib.vrenb200_sharded_sort_local_bytes(max_n, capacity, cfg_ptr), dtype=torch.uint8, device=dev)
         ptrs = (C.c_void_p * world)(*[int(r.data_ptr()) for r in regions])
         handle = C.c_void_p()
         self.config = config

@@ -110,7 +110,7 @@ def load() -> C.CDLL:
 _vp, _u32, _sz, _i32 = C.c_void_p, C.c_uint32, C.c_size_t, C.c_int
 _LATE_SIGS = [
     ("vrenb200_sharded_sort_symmetric_bytes", _sz, (_u32,)),
-    ("vrenb200_sharded_sort_local_bytes", _sz, (_u32, _u32)),
+    ("vrenb200_sharded_sort_local_bytes", _sz, (_u32, _u32, _vp)),
     ("vrenb200_sharded_sort_create", _i32, (_vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _sz, _vp)),
     ("vrenb200_sharded_sort_destroy", None, (_vp,)),
     ("vrenb200_sharded_sort_pairs", _i32, (_vp, _vp, _vp, _vp, _u32, _i32)),
