@@ -432,6 +432,7 @@ def run_ours(args):
         barrier()
     # ---- correctness of the last timed step
     violation = 0
+    phases = None
     if world == 1:
         verify_sorted_shard(keys, vals, "output")
         assert torch.equal(keys0[(vals.to(torch.int64) & 0xFFFFFFFF)], keys), "bench: pairs broken"
@@ -439,6 +440,7 @@ def run_ours(args):
         violation = int(scratch[word: word + 4].view(torch.int32).item())
         out_sum = checksum(keys, vals)
     else:
+        phases = sorter.phases()
         ok, ov = sorter.result()
         verify_sorted_shard(ok, ov, f"shard of rank {rank}")
         out_sum = checksum(ok, ov)
@@ -601,6 +603,7 @@ def run_ours(args):
             "gpu_launches": (launches_single if world == 1 else launches_multi) * args.steps,
             "verification": "sortedness + stability + pair integrity" if world == 1 else
                             "2^22/rank global sort == oracle.sort_pairs; timed output: all-reduced pair-multiset checksum, per-shard sortedness and stability, cross-rank boundary order",
+            "phases_rank0_last_step": phases,
             "secondary": secondary,
             "clocks": clocks.summary(),
         }

@@ -198,6 +198,9 @@ int vrenb200_sharded_sort_pairs(vrenb200_sharded_sort* ctx, vrenb200_stream_t st
 const uint32_t* vrenb200_sharded_sort_out_keys(const vrenb200_sharded_sort* ctx);
 const uint32_t* vrenb200_sharded_sort_out_values(const vrenb200_sharded_sort* ctx);
 const uint32_t* vrenb200_sharded_sort_status(const vrenb200_sharded_sort* ctx);
+/* phases of the last call from CUDA events (after the stream has been synchronised): ms_out[3] = {histograms + plan + local
+ * partition, the transfers, the segmented passes}; the last two start together and overlap */
+int vrenb200_sharded_sort_phases(const vrenb200_sharded_sort* ctx, float* ms_out);
 
 #ifdef VRENB200_TUNING
 /* tuning builds only (VRENB200_TUNING=1 python -m vren_b200.build): process-global selection of experimental scan kernels.

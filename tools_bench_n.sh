@@ -6,7 +6,7 @@ for extra in "$@"; do
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('N=$N', '$extra', 'Gpairs/s %.2f' % d['value'], 'ms %.3f' % d['ms_per_step'], 'e2e %.2f' % d['e2e']['value'], 'pass_ms %.3f' % d['roofline']['kernel_ms'])
+        d = json.loads(l); print('N=$N', '$extra', 'Gpairs/s %.2f' % d['value'], 'ms %.3f' % d['ms_per_step'], 'e2e %.2f' % d['e2e']['value'], 'pass_ms %.3f' % d['roofline']['kernel_ms'], d.get('phases_rank0_last_step'))
     elif 'rror' in l or 'assert' in l: print(l.strip())
 "
 done

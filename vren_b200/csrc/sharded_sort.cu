@@ -34,12 +34,15 @@ namespace {
 
 constexpr int kMaxRanks = 32;
 // The transfer kernel is NVLink-bound and must leave the SMs to the segmented passes it overlaps with: one warp per CTA drives a
-// ring of TMA bulk copies (kXferStages x 2 x kXferChunk x 4 bytes of shared memory); one CTA of the pass kernel still fits
-// next to it on an SM.
+// ring of TMA bulk copies (stages x 2 x kXferChunk x 4 bytes of shared memory).
 constexpr int kXferChunk = 2048;          // pairs per stage: 8 KB of keys + 8 KB of values
-constexpr int kXferStages = 6;
-constexpr int kXferDefaultCtas = 32;
-constexpr size_t kXferSmem = (size_t) kXferStages * 2 * kXferChunk * sizeof(uint32_t) + 256;
+constexpr int kXferMaxStages = 13;        // 13 x 16 KB = 208 KB: the CTA then has its SM to itself
+// measured at N = 4 (profiles/r2j_bench_n4_exclusive.log): 24 CTAs with the whole shared memory of their SM each (nothing else
+// fits next to them: the passes see uniform SMs, and a tile that crawls next to a copy no longer holds up the look-back chain
+// of all the tiles behind it) 5.94 ms per sort; 32 CTAs of 96 KB next to one pass CTA each 6.14; 16 / 32 exclusive CTAs 6.36 / 6.29
+constexpr int kXferDefaultStages = 13;
+constexpr int kXferDefaultCtas = 24;
+constexpr size_t xfer_smem_bytes(uint32_t stages) { return (size_t) stages * 2 * kXferChunk * sizeof(uint32_t) + 256; }
 constexpr uint32_t kPartSlack = 1024;     // the local partition leaves up to 3 pairs of padding in front of every digit
 
 // ---- symmetric region ---------------------------------------------------------------------------------------------------------
@@ -370,23 +373,23 @@ __device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity)
 // and after the aligned body go through registers.
 __global__ void __launch_bounds__(32, 1)
 transfer_round_kernel(const uint32_t* __restrict__ part_keys, const uint32_t* __restrict__ part_vals, const seg_plan* plan,
-                      xfer_plan* xp, peer_table peers, shard_params sp, uint32_t round)
+                      xfer_plan* xp, peer_table peers, shard_params sp, uint32_t round, uint32_t kXferStages)
 {
     extern __shared__ __align__(128) unsigned char xfer_smem[];
     uint32_t* ring_k = reinterpret_cast<uint32_t*>(xfer_smem);                       // [stages][chunk]
     uint32_t* ring_v = ring_k + kXferStages * kXferChunk;
     uint64_t* full = reinterpret_cast<uint64_t*>(ring_v + kXferStages * kXferChunk); // one mbarrier per stage
     __shared__ uint32_t s_cum[kRadix];
-    __shared__ uint32_t* s_dst_k[kXferStages];
-    __shared__ uint32_t* s_dst_v[kXferStages];
-    __shared__ uint32_t s_count[kXferStages];
+    __shared__ uint32_t* s_dst_k[kXferMaxStages];
+    __shared__ uint32_t* s_dst_v[kXferMaxStages];
+    __shared__ uint32_t s_count[kXferMaxStages];
     const unsigned lane = threadIdx.x;
     if (plan->error == 0)
     {
         for (uint32_t i = lane; i < kRadix; i += 32) s_cum[i] = xp->cum_pairs[round][i];
         if (lane == 0)
         {
-            for (int s = 0; s < kXferStages; s++) mbar_init_(&full[s], 1);
+            for (uint32_t s = 0; s < kXferStages; s++) mbar_init_(&full[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -435,7 +438,7 @@ transfer_round_kernel(const uint32_t* __restrict__ part_keys, const uint32_t* __
                     // the stage is free once the store that last used it has read it: stores complete in order, and all but
                     // the two most recent chunks have been stored before a new load is issued
                     while (stored + (kXferStages - 2) < issued) store_one();
-                    if (issued >= (uint32_t) kXferStages) bulk_wait_read<1>();
+                    if (issued >= kXferStages) bulk_wait_read<1>();
                     const uint32_t st = issued % kXferStages;
                     s_dst_k[st] = dst_k + c0;
                     s_dst_v[st] = dst_v + c0;
@@ -615,9 +618,9 @@ struct vrenb200_sharded_sort
     uint32_t max_n, capacity;
     sort_options opt;
     const sort_variant* var_seg;
-    uint32_t xfer_ctas;
+    uint32_t xfer_ctas, xfer_stages;
     cudaStream_t copy_stream, sort_stream;
-    cudaEvent_t ev_part, ev_copy, ev_sort;
+    cudaEvent_t ev_start, ev_part, ev_copy, ev_sort;
     int device;
     // carved from the caller's local scratch
     uint32_t *part_keys, *part_vals, *alt_keys, *alt_vals, *out_keys, *out_vals;
@@ -710,14 +713,19 @@ extern "C" int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_
         const long v = std::strtol(e, nullptr, 10);
         if (v >= 1 && v <= 4 * kNumSMs) c->xfer_ctas = (uint32_t) v;
     }
+    c->xfer_stages = kXferDefaultStages;
+    if (const char* e = std::getenv("VRENB200_XFER_STAGES"))
+    {
+        const long v = std::strtol(e, nullptr, 10);
+        if (v >= 3 && v <= kXferMaxStages) c->xfer_stages = (uint32_t) v;
+    }
     // the copy stream outranks the sort stream: when an SM frees room, a waiting transfer CTA takes it before the next pass CTA
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaGetDevice(&c->device) != cudaSuccess || cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->sort_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_part, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_sort, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_part) != cudaSuccess ||
+        cudaEventCreate(&c->ev_copy) != cudaSuccess || cudaEventCreate(&c->ev_sort) != cudaSuccess)
     {
         delete c;
         return VRENB200_ECUDA;
@@ -734,7 +742,7 @@ extern "C" int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_
                                  (const void*) segment_histograms_kernel};
         for (const void* k : kernels)
             if (st == VRENB200_OK) st = check_cuda(cudaFuncGetAttributes(&attr, k));
-        if (st == VRENB200_OK) st = check_cuda(cudaFuncSetAttribute(transfer_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kXferSmem));
+        if (st == VRENB200_OK) st = check_cuda(cudaFuncSetAttribute(transfer_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) xfer_smem_bytes(kXferMaxStages)));
         if (st == VRENB200_OK) st = check_cuda(cudaFuncSetAttribute(segment_histograms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSegHistSmem));
         if (st != VRENB200_OK)
         {
@@ -760,6 +768,7 @@ extern "C" void vrenb200_sharded_sort_destroy(vrenb200_sharded_sort* c)
     cudaStreamSynchronize(c->sort_stream);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->sort_stream);
+    cudaEventDestroy(c->ev_start);
     cudaEventDestroy(c->ev_part);
     cudaEventDestroy(c->ev_copy);
     cudaEventDestroy(c->ev_sort);
@@ -769,6 +778,17 @@ extern "C" void vrenb200_sharded_sort_destroy(vrenb200_sharded_sort* c)
 extern "C" const uint32_t* vrenb200_sharded_sort_out_keys(const vrenb200_sharded_sort* c) { return c ? c->out_keys : nullptr; }
 extern "C" const uint32_t* vrenb200_sharded_sort_out_values(const vrenb200_sharded_sort* c) { return c ? c->out_vals : nullptr; }
 extern "C" const uint32_t* vrenb200_sharded_sort_status(const vrenb200_sharded_sort* c) { return c ? c->status : nullptr; }
+
+// phases of the LAST call on this rank, from CUDA events on the three streams (call after the stream has been synchronised):
+// ms_out[3] = {histograms + publish + plan + local partition, first transfer -> last transfer done, first -> last segmented
+// pass}; the last two start together and overlap
+extern "C" int vrenb200_sharded_sort_phases(const vrenb200_sharded_sort* c, float* ms_out)
+{
+    if (c == nullptr || ms_out == nullptr) return VRENB200_EINVAL_ARG;
+    VRENB200_TRY(check_cuda(cudaEventElapsedTime(&ms_out[0], c->ev_start, c->ev_part)));
+    VRENB200_TRY(check_cuda(cudaEventElapsedTime(&ms_out[1], c->ev_part, c->ev_copy)));
+    return check_cuda(cudaEventElapsedTime(&ms_out[2], c->ev_part, c->ev_sort));
+}
 
 extern "C" int vrenb200_sharded_sort_pairs(vrenb200_sharded_sort* c, vrenb200_stream_t stream, const uint32_t* keys,
                                            const uint32_t* values, uint32_t n, int key_bits)
@@ -791,6 +811,7 @@ extern "C" int vrenb200_sharded_sort_pairs(vrenb200_sharded_sort* c, vrenb200_st
     const int selftest = c->opt.ranking == VRENB200_RANKING_SELFTEST_REDO;
 
     // ---- main stream: histograms -> publish -> plan -> local partition ----
+    VRENB200_TRY(check_cuda(cudaEventRecord(c->ev_start, s)));
     VRENB200_TRY(check_cuda(cudaMemsetAsync(c->ctl_part, 0, sizeof(sort_control) + (size_t) std::max(part_tiles, 1u) * kRadix * sizeof(uint32_t), s)));
     VRENB200_TRY(check_cuda(cudaMemsetAsync(c->ctl_seg, 0, sizeof(sort_control) + (size_t) sp.cap_tiles * kRadix * sizeof(uint32_t), s)));
     VRENB200_TRY(check_cuda(cudaMemsetAsync(c->tickets, 0, sizeof(uint32_t) * kMaxRounds * (kPasses - 1), s)));
@@ -827,7 +848,8 @@ extern "C" int vrenb200_sharded_sort_pairs(vrenb200_sharded_sort* c, vrenb200_st
     VRENB200_TRY(check_launch());
     for (uint32_t k = 0; k < sp.rounds; k++)
     {
-        transfer_round_kernel<<<c->xfer_ctas, 32, kXferSmem, c->copy_stream>>>(c->part_keys, c->part_vals, c->plan, c->xp, c->peers, sp, k);
+        transfer_round_kernel<<<c->xfer_ctas, 32, xfer_smem_bytes(c->xfer_stages), c->copy_stream>>>(c->part_keys, c->part_vals, c->plan, c->xp, c->peers, sp, k,
+                                                                                                        c->xfer_stages);
         VRENB200_TRY(check_launch());
     }
     VRENB200_TRY(check_cuda(cudaEventRecord(c->ev_copy, c->copy_stream)));

@@ -279,6 +279,12 @@ class ShardedSort:
         n = int(st[1])
         return self.out_keys[:n], self.out_vals[:n]
 
+    def phases(self):
+        """CUDA-event milliseconds of the last sort on this rank (after a synchronise): {plan + partition, transfers, passes}"""
+        ms = (C.c_float * 3)()
+        self.vlib.check(self.lib.vrenb200_sharded_sort_phases(self.handle, ms), "vrenb200_sharded_sort_phases")
+        return {"plan_and_partition_ms": float(ms[0]), "transfers_ms": float(ms[1]), "segmented_passes_ms": float(ms[2])}
+
     def owned_digits(self):
         st = self.status.cpu().numpy().view("uint32")
         return int(st[2]), int(st[3]), int(st[4])

@@ -117,6 +117,7 @@ _LATE_SIGS = [
     ("vrenb200_sharded_sort_out_keys", _vp, (_vp,)),
     ("vrenb200_sharded_sort_out_values", _vp, (_vp,)),
     ("vrenb200_sharded_sort_status", _vp, (_vp,)),
+    ("vrenb200_sharded_sort_phases", _i32, (_vp, C.POINTER(C.c_float))),
     ("vrenb200_cluster_tests", _i32, (_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp)),
     ("vrenb200_light_list_hash_scratch_bytes", _sz, (_u32,)),
     ("vrenb200_light_list_hash", _i32, (_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _sz)),
