@@ -4,6 +4,8 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <memory>
+#include <vector>
 
 #include "../../vrenb200.h"
 
@@ -22,13 +24,17 @@ namespace vren
     }
     inline uint32_t divide_and_ceil(uint32_t value, uint32_t divider) { return vrenb200_divide_and_ceil(value, divider); }
 
-    // base/resource_container.hpp:8-38 — kept as a parameter so reference call sites port 1:1; nothing to park:
-    // the CUDA path allocates no per-call objects
+    // base/resource_container.hpp:8-38: per-call objects (pooled descriptor sets in the reference, pooled scratch blocks
+    // here) are parked in it until the command buffer — the stream — they were recorded into has retired; the caller
+    // clears or destroys the container after synchronising, exactly as with the reference (reduce.cpp:64-78).
     class resource_container
     {
+        std::vector<std::shared_ptr<void>> m_resources;
+
     public:
-        template <typename... _t> void add_resources(_t&&...) {}
-        template <typename _t> void add_resource(_t&&) {}
-        void clear() {}
+        template <typename _t> void add_resource(std::shared_ptr<_t> resource) { m_resources.push_back(std::move(resource)); }
+        template <typename... _t> void add_resources(std::shared_ptr<_t>... resources) { (add_resource(std::move(resources)), ...); }
+        void clear() { m_resources.clear(); }
+        size_t size() const { return m_resources.size(); }
     };
 }

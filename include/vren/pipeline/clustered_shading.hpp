@@ -78,19 +78,25 @@ namespace vren
 
         class find_unique_cluster_list // clustered_shading.hpp:52-74
         {
-            vren::scratch_arena m_scratch;
+            vren::scratch_pool m_scratch;
 
         public:
             explicit find_unique_cluster_list(vren::context const&) {}
+            void reserve_scratch(uint32_t width, uint32_t height, size_t frames_in_flight = 1)
+            {
+                m_scratch.reserve(vrenb200_find_unique_clusters_scratch_bytes(width, height), frames_in_flight);
+            }
 
             // clustered_shading.cpp:363-448; cluster_key_dispatch_params = uvec4 {count, 1, 1, overflow flag}
-            void operator()(uint32_t /*frame_idx*/, VkCommandBuffer command_buffer, vren::resource_container&, vren::uvec2 const& screen,
+            void operator()(uint32_t /*frame_idx*/, VkCommandBuffer command_buffer, vren::resource_container& resource_container, vren::uvec2 const& screen,
                             vren::camera const& camera, vren::gbuffer const& gbuffer, vren::vk_utils::depth_buffer_t const& depth_buffer,
                             vren::vk_utils::buffer const& cluster_key_buffer, vren::vk_utils::buffer const& cluster_key_dispatch_params_buffer,
                             vren::vk_utils::combined_image_view const& cluster_reference_buffer)
             {
                 const size_t bytes = vrenb200_find_unique_clusters_scratch_bytes(screen.x, screen.y);
-                void* scratch = m_scratch.reserve(bytes);
+                std::shared_ptr<void> lease = m_scratch.acquire(bytes);
+                void* scratch = lease.get();
+                resource_container.add_resource(lease);
                 const vrenb200_camera cam = camera.abi();
                 check_status(vrenb200_find_unique_clusters((vrenb200_stream_t) command_buffer, depth_buffer.m_image.ptr<float>(),
                                                            gbuffer.m_normal_buffer.m_ptr, screen.x, screen.y, &cam,
@@ -103,13 +109,17 @@ namespace vren
 
         class assign_lights // clustered_shading.hpp:80-108
         {
-            vren::scratch_arena m_scratch;
+            vren::scratch_pool m_scratch;
 
         public:
             explicit assign_lights(vren::context const&) {}
+            void reserve_scratch(uint32_t max_keys, uint32_t max_assigned, size_t frames_in_flight = 1)
+            {
+                m_scratch.reserve(vrenb200_assign_lights_scratch_bytes(max_keys, max_assigned), frames_in_flight);
+            }
 
             // clustered_shading.cpp:473-690
-            void operator()(uint32_t /*frame_idx*/, VkCommandBuffer command_buffer, vren::resource_container&, vren::uvec2 const& screen,
+            void operator()(uint32_t /*frame_idx*/, VkCommandBuffer command_buffer, vren::resource_container& resource_container, vren::uvec2 const& screen,
                             vren::camera const& camera, vren::vk_utils::buffer const& cluster_key_buffer,
                             vren::vk_utils::buffer const& cluster_key_dispatch_params_buffer, vren::vk_utils::buffer const& light_bvh_buffer,
                             uint32_t light_bvh_root_index, uint32_t light_count, vren::vk_utils::buffer const& light_index_buffer,
@@ -119,7 +129,9 @@ namespace vren
             {
                 const uint32_t max_keys = (uint32_t) (assigned_light_counts_buffer.m_size / 4);
                 const size_t bytes = vrenb200_assign_lights_scratch_bytes(max_keys, (uint32_t) (assigned_light_indices_buffer.m_size / 4));
-                void* scratch = m_scratch.reserve(bytes);
+                std::shared_ptr<void> lease = m_scratch.acquire(bytes);
+                void* scratch = lease.get();
+                resource_container.add_resource(lease);
                 const vrenb200_camera cam = camera.abi();
                 check_status(vrenb200_assign_lights((vrenb200_stream_t) command_buffer, screen.x, screen.y, &cam, cluster_key_buffer.ptr<uint32_t>(),
                                                     cluster_key_dispatch_params_buffer.ptr<uint32_t>(), max_keys, light_bvh_buffer.m_ptr,
@@ -177,6 +189,10 @@ namespace vren
             m_assigned_light_offsets_buffer(vk_utils::alloc_device_only_buffer(c, (size_t) l.max_unique_cluster_key_count * 4)),
             m_status_buffer(vk_utils::alloc_device_only_buffer(c, 16))
         {
+            // the stages' scratch for the largest frame is ready before the first frame is recorded (two frames in flight):
+            // nothing is allocated while recording
+            m_find_unique_cluster_list.reserve_scratch(l.max_screen_width, l.max_screen_height, 2);
+            m_assign_lights.reserve_scratch(l.max_unique_cluster_key_count, l.max_assigned_light_count, 2);
         }
 
         // steps 1-3 of clustered_shading.cpp:975-1147 (step 4, shade, is out of scope)

@@ -12,7 +12,7 @@ namespace vren
         inline static const uint32_t k_max_items = 1;
 
     private:
-        vren::scratch_arena m_scratch; // look-back status words of the single-pass scan
+        vren::scratch_pool m_scratch; // look-back status words of the single-pass scan
 
     public:
         explicit blelloch_scan(vren::context const&) {}
@@ -33,7 +33,9 @@ namespace vren
         {
             if (!vren::is_power_of_2(length)) throw std::invalid_argument("vren::blelloch_scan: length must be a power of 2"); // :67
             const size_t bytes = vrenb200_scan_scratch_bytes(length);
-            void* scratch = m_scratch.reserve(bytes);
+            std::shared_ptr<void> lease = m_scratch.acquire(bytes);
+            void* scratch = lease.get();
+            resource_container.add_resource(lease);
             uint32_t* data = buffer.ptr<uint32_t>(offset);
             check_status(vrenb200_exclusive_scan_u32((vrenb200_stream_t) command_buffer, data, data, length, scratch, bytes), "vren::blelloch_scan");
             if (blocks_num > 1)

@@ -15,7 +15,7 @@ namespace vren
         inline static const uint32_t k_key_mask = k_key_size - 1;
 
     private:
-        vren::scratch_arena m_scratch; // ping-pong pair buffer + look-back state
+        vren::scratch_pool m_scratch; // ping-pong pair buffer + look-back state
 
     public:
         explicit bucket_sort(vren::context const&) {}
@@ -23,7 +23,7 @@ namespace vren
         static size_t get_required_output_buffer_size(uint32_t length) { return vrenb200_bucket_sort_output_bytes(length); } // bucket_sort.cpp:67-70
 
         // bucket_sort.cpp:72-161. Ties keep input order (the reference's atomics leave it unspecified).
-        void operator()(VkCommandBuffer command_buffer, vren::resource_container&, vren::vk_utils::buffer const& input_buffer,
+        void operator()(VkCommandBuffer command_buffer, vren::resource_container& resource_container, vren::vk_utils::buffer const& input_buffer,
                         uint32_t input_buffer_length, size_t input_buffer_offset, vren::vk_utils::buffer const& output_buffer,
                         size_t output_buffer_offset)
         {
@@ -32,7 +32,9 @@ namespace vren
             if (output_buffer.m_size - output_buffer_offset < get_required_output_buffer_size(input_buffer_length))
                 check_status(VRENB200_ESCRATCH, "vren::bucket_sort: output buffer too small");           // bucket_sort.cpp:84
             const size_t bytes = vrenb200_bucket_sort_scratch_bytes(input_buffer_length);
-            void* scratch = m_scratch.reserve(bytes);
+            std::shared_ptr<void> lease = m_scratch.acquire(bytes);
+            void* scratch = lease.get();
+            resource_container.add_resource(lease);
             check_status(vrenb200_bucket_sort((vrenb200_stream_t) command_buffer, input_buffer.ptr<>(input_buffer_offset), input_buffer_length,
                                               output_buffer.ptr<>(output_buffer_offset), scratch, bytes),
                          "vren::bucket_sort");

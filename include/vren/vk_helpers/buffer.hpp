@@ -5,9 +5,11 @@
 #include <cuda_runtime.h>
 
 #include <cstddef>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include "../../vrenb200.h"
 
@@ -76,26 +78,55 @@ namespace vren
         }
     }
 
-    // grow-only device scratch owned by a primitive (the analogue of the reference's pooled descriptor sets)
-    class scratch_arena
+    // Device scratch of a primitive: a pool of blocks, the analogue of the reference's descriptor pools
+    // (pool/object_pool.hpp:60-117).  operator() LEASES a block and parks the lease in the caller's resource_container; the
+    // block returns to the pool when the container lets go of it (after the stream has retired).  Calls in flight never share
+    // a block, nothing is freed or synchronised while recording, and a pool that was given its size up front
+    // (reserve(), e.g. from the constructor) never allocates while recording either.
+    class scratch_pool
     {
-        void* m_ptr = nullptr;
-        size_t m_size = 0;
+        struct block { void* ptr; size_t size; };
+        struct state { std::vector<block> free_blocks; ~state() { for (block& b : free_blocks) cudaFree(b.ptr); } };
+        std::shared_ptr<state> m_state = std::make_shared<state>();
+
+        static block allocate(size_t bytes)
+        {
+            block b{nullptr, bytes < 256 ? 256 : bytes};
+            if (cudaMalloc(&b.ptr, b.size) != cudaSuccess) throw std::runtime_error("cudaMalloc failed");
+            return b;
+        }
 
     public:
-        scratch_arena() = default;
-        scratch_arena(scratch_arena const&) = delete;
-        ~scratch_arena() { if (m_ptr) cudaFree(m_ptr); }
-        void* reserve(size_t bytes)
+        scratch_pool() = default;
+        scratch_pool(scratch_pool const&) = delete;
+
+        // make sure `count` blocks of at least `bytes` are ready (constructors / set-up code)
+        void reserve(size_t bytes, size_t count = 1)
         {
-            if (bytes > m_size)
-            {
-                if (m_ptr) { cudaDeviceSynchronize(); cudaFree(m_ptr); }
-                if (cudaMalloc(&m_ptr, bytes) != cudaSuccess) { m_ptr = nullptr; m_size = 0; throw std::runtime_error("cudaMalloc failed"); }
-                m_size = bytes;
-            }
-            return m_ptr;
+            size_t have = 0;
+            for (block const& b : m_state->free_blocks) have += b.size >= bytes;
+            for (; have < count; have++) m_state->free_blocks.push_back(allocate(bytes));
         }
-        size_t size() const { return m_size; }
+
+        // a block of at least `bytes`, owned by the returned lease (park it in the resource_container of the call)
+        std::shared_ptr<void> acquire(size_t bytes)
+        {
+            block got{nullptr, 0};
+            std::vector<block>& fb = m_state->free_blocks;
+            for (size_t i = 0; i < fb.size(); i++)
+                if (fb[i].size >= bytes && (got.ptr == nullptr || fb[i].size < got.size)) got = fb[i];
+            if (got.ptr != nullptr)
+            {
+                for (size_t i = 0; i < fb.size(); i++)
+                    if (fb[i].ptr == got.ptr) { fb.erase(fb.begin() + i); break; }
+            }
+            else
+                got = allocate(bytes);
+            std::weak_ptr<state> pool = m_state;
+            return std::shared_ptr<void>(got.ptr, [pool, got](void*) {
+                if (auto p = pool.lock()) p->free_blocks.push_back(got);      // back to the pool
+                else cudaFree(got.ptr);                                        // the primitive is gone
+            });
+        }
     };
 }

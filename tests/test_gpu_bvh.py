@@ -157,6 +157,19 @@ def test_construct_point_light_bvh_matches_oracle(vren, L, external_scratch):
     nodes_equal(got_nodes, wnodes)
 
 
+@pytest.mark.parametrize("L", [1000000, 1 << 20])
+def test_construct_point_light_bvh_c4_sizes(vren, L):
+    """BASELINE C4 through the whole a6 chain: 10^6 and 2^20 lights (both pad to 2^20 leaves, 4 levels)"""
+    pos, lights = make_lights(L, 4100 + (L & 0xFF))
+    view = view_matrix(-0.7, 0.2, (5.0, -1.0, 2.0))
+    wvp, wnodes, wpairs = oracle.construct_point_light_bvh(pos, lights, view)
+    vp, bvh, idx = vren.construct_point_light_bvh(to_dev(pos), to_dev(lights), view.tolist())
+    assert np.array_equal(vp.cpu().numpy().view(np.uint32), wvp.view(np.uint32))
+    assert np.array_equal(idx[: L * 8].cpu().numpy().view(np.uint32).reshape(L, 2), wpairs)
+    nodes_equal(bvh[: wnodes.size * 32].cpu().numpy().view(oracle.BVH_NODE), wnodes)
+    assert wnodes.size == 1082401
+
+
 def test_light_bvh_degenerate_axis(vren):
     """all lights share y: (p - min)/(max - min) = 0/0 -> canonical bin 0"""
     L = 500

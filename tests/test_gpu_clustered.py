@@ -76,18 +76,22 @@ def test_find_unique_clusters_background_and_overflow(vren):
     assert np.array_equal(host_u32(keys)[:cap], want_keys[:cap])
 
 
-def run_chain(vren, w, h, L, seed, intensity=(1.0, 1.0), max_keys=1 << 17, max_assigned=1 << 23, yaw=0.0):
+def run_chain(vren, w, h, L, seed, intensity=(1.0, 1.0), max_keys=1 << 17, max_assigned=1 << 23, yaw=0.0, with_normals=False):
     depth = synthetic.depth_buffer(w, h, seed=seed)
+    normals = synthetic.normal_buffer(w, h, seed=seed + 9) if with_normals else None
     pos, lights = synthetic.point_lights(L, seed=seed + 1, aspect=w / h, intensity=intensity)
     view = synthetic.view_matrix(yaw, 0.0, (0.0, 0.0, 0.0))
     oc, vc = both_cameras(vren, w, h)
     # oracle chain
     wvp, wnodes, wpairs = oracle.construct_point_light_bvh(pos, lights, view)
-    wkeys, wref = oracle.find_unique_clusters(depth, None, oc)
+    wkeys, wref = oracle.find_unique_clusters(depth, normals, oc)
     wcounts, woffsets, windices, wtotal = oracle.assign_lights(w, h, oc, wkeys, max_keys, wnodes, L, wpairs, wvp, max_assigned)
     # CUDA chain (a9 order: a6 -> a7 -> a8)
+    import torch
+
     vp, bvh, idx = vren.construct_point_light_bvh(dev(pos), dev(lights), view.tolist())
-    keys, disp, ref = vren.find_unique_clusters(dev(depth), None, vc, max_keys=max_keys)
+    dn = None if normals is None else torch.from_numpy(normals.view(np.int16)).cuda().view(torch.float16)
+    keys, disp, ref = vren.find_unique_clusters(dev(depth), dn, vc, max_keys=max_keys)
     counts, offsets, indices, status = vren.assign_lights(w, h, vc, keys, disp, bvh, L, idx, vp, max_keys=max_keys, max_assigned=max_assigned)
     return (wkeys, wcounts, woffsets, windices, wtotal), (host_u32(keys), host_u32(counts), host_u32(offsets), host_u32(indices), host_u32(status))
 
@@ -182,3 +186,53 @@ def test_light_list_consumer_n1(vren, w, h, L):
     want = oracle.light_list_hash(host_u32(ref).reshape(h, w), host_u32(counts), host_u32(offsets), host_u32(indices))
     assert np.array_equal(got, want)
     assert int(got[..., 0].max()) > 0
+
+
+@pytest.mark.parametrize("view_index", range(8))
+def test_cluster_chain_c5_eight_views_with_normals(vren, view_index):
+    """BASELINE C5 as SURVEY 8d spells it: 3840x2160, 65 536 lights, the 8 views of a batch (yaw += 45 degrees per view, a
+    depth buffer per view; views 0 and 3 with RGBA16F normals, which multiply the clusters): keys, counts, offsets and
+    ordered light lists bit-exact vs the oracle"""
+    yaw = math.radians(45.0) * view_index
+    (wkeys, wcounts, woffsets, windices, wtotal), (keys, counts, offsets, indices, status) = run_chain(
+        vren, 3840, 2160, 65536, seed=2024 + view_index, yaw=yaw, with_normals=view_index in (0, 3), max_keys=1 << 20)
+    assert np.array_equal(keys[: wkeys.size], wkeys)
+    assert np.array_equal(counts, wcounts) and np.array_equal(offsets, woffsets)
+    assert status[0] == wtotal and status[1] == 0
+    assert np.array_equal(indices[:wtotal], windices[:wtotal])
+
+
+def test_view_batch_single_gpu_matches_per_view_oracle(vren):
+    """vren_b200.pipeline.ViewBatch with no process group: all views on this GPU, same results as view-by-view oracle runs"""
+    import torch
+
+    from vren_b200.pipeline import ViewBatch
+
+    w, h, L, views = 640, 360, 4000, 4
+    oc, vc = both_cameras(vren, w, h)
+    pos0, lights0 = synthetic.point_lights(L, seed=71, aspect=w / h, intensity=(0.5, 3.0))
+    vb = ViewBatch(w, h, L)
+    vb.set_lights(dev(pos0), dev(lights0), L)
+    frames, inputs = {}, {}
+    for v in vb.my_views(views):
+        view = synthetic.view_matrix(math.radians(45.0) * v, 0.0, (0.0, 0.0, 0.0))
+        depth = synthetic.depth_buffer(w, h, seed=80 + v)
+        frames[v] = (vc, view.tolist(), dev(depth), None)
+        inputs[v] = (view, depth)
+    got = {}
+
+    def on_view(v, cs):
+        got[v] = (host_u32(cs.cluster_keys).copy(), host_u32(cs.counts).copy(), host_u32(cs.offsets).copy(), host_u32(cs.indices).copy())
+
+    res = vb(frames, on_view)
+    torch.cuda.synchronize()
+    assert sorted(res) == list(range(views))
+    for v, (view, depth) in inputs.items():
+        wvp, wnodes, wpairs = oracle.construct_point_light_bvh(pos0, lights0, view)
+        wkeys, _ = oracle.find_unique_clusters(depth, None, oc)
+        wcounts, woffsets, windices, wtotal = oracle.assign_lights(w, h, oc, wkeys, vb.cs.max_keys, wnodes, L, wpairs, wvp, vb.cs.max_assigned)
+        keys, counts, offsets, indices = got[v]
+        r = res[v].cpu().numpy().view(np.uint32)
+        assert r[0] == wkeys.size and r[4] == wtotal
+        assert np.array_equal(keys[: wkeys.size], wkeys) and np.array_equal(counts, wcounts) and np.array_equal(offsets, woffsets)
+        assert np.array_equal(indices[:wtotal], windices[:wtotal])

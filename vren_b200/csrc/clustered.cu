@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <vector>
 
@@ -83,8 +84,8 @@ struct slice_table
 
 // Device copies of the small per-camera tables (slice thresholds, near_k), keyed by (device, kind, two floats): the
 // tables only change with the camera, so a frame re-uses them instead of paying a host->device copy (and, for near_k,
-// 1024 powf calls) per call.  Filled with a synchronous copy; the oldest entry is freed when the cache is full
-// (cudaFree waits for the kernels that may still read it).
+// 1024 powf calls) per call.  A new camera is filled in with a synchronous copy (the one host synchronisation of the
+// clustered path, once per camera and device); entries live as long as the library.
 struct device_table
 {
     int device, kind;
@@ -94,7 +95,8 @@ struct device_table
 };
 
 std::mutex g_table_mutex;
-std::vector<device_table> g_tables;
+constexpr size_t kMaxDeviceTables = 512;
+std::deque<device_table> g_tables;    // deque: growing it never moves the entries other threads hold pointers to
 
 const device_table* find_device_table(int kind, float p0, float p1)
 {
@@ -109,11 +111,9 @@ const device_table* add_device_table(int kind, float p0, float p1, const float* 
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    if (g_tables.size() >= 16)
-    {
-        cudaFree(g_tables.front().data);
-        g_tables.erase(g_tables.begin());
-    }
+    // entries are never freed while the library is loaded: their pointers live in CUDA graphs recorded by callers and in
+    // kernels already enqueued.  A table is <= 64 KB; 512 distinct (device, camera) pairs is the (generous) limit.
+    if (g_tables.size() >= kMaxDeviceTables) return nullptr;
     device_table t{dev, kind, p0, p1, nullptr, count};
     if (cudaMalloc(&t.data, (size_t) count * sizeof(float)) != cudaSuccess) return nullptr;
     if (cudaMemcpy(t.data, host, (size_t) count * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
