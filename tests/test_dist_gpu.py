@@ -116,3 +116,74 @@ def test_sharded_sort_bucket_sort_and_scan(vren, tmp_path, world, case, n, round
         got = np.concatenate([np.load(tmp_path / f"b{r}.npy").reshape(-1, 2) for r in range(world)])
         assert np.array_equal(got, want)
         assert np.array_equal(np.load(tmp_path / "ends.npy").astype(np.uint32), counters)
+
+
+def _view_worker(rank, world, port, out_dir, w, h, L, views):
+    import math
+
+    import torch
+    import torch.distributed as dist
+
+    from vren_b200 import lib as vlib
+    from vren_b200 import synthetic
+    from vren_b200.pipeline import ViewBatch
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        vlib.load()
+        oc = oracle.default_camera(w, h)
+        vc = vlib.Camera(oc.fov_y, oc.aspect_ratio, oc.near_plane, oc.far_plane)
+        vb = ViewBatch(w, h, L)
+        pos = torch.zeros(L, 4, dtype=torch.float32, device="cuda")
+        lights = torch.zeros(L, 4, dtype=torch.float32, device="cuda")
+        if rank == 0:       # only the source rank has the frame's lights; the others get them by broadcast
+            p0, l0 = synthetic.point_lights(L, seed=71, aspect=w / h, intensity=(0.5, 3.0))
+            pos, lights = torch.from_numpy(p0).cuda(), torch.from_numpy(l0).cuda()
+        vb.set_lights(pos, lights, L, src=0)
+        frames = {v: (vc, synthetic.view_matrix(math.radians(45.0) * v, 0.0, (0.0, 0.0, 0.0)).tolist(),
+                      torch.from_numpy(synthetic.depth_buffer(w, h, seed=80 + v)).cuda(), None) for v in vb.my_views(views)}
+
+        def on_view(v, cs):
+            torch.cuda.synchronize()
+            n = int(cs.dispatch_params[0])
+            total = int(cs.status.cpu().numpy().view(np.uint32)[0])
+            np.savez(os.path.join(out_dir, f"view{v}.npz"), keys=cs.cluster_keys[:n].cpu().numpy().view(np.uint32),
+                     counts=cs.counts.cpu().numpy().view(np.uint32), offsets=cs.offsets.cpu().numpy().view(np.uint32),
+                     indices=cs.indices[:total].cpu().numpy().view(np.uint32), rank=np.array([rank]))
+
+        vb(frames, on_view)
+        torch.cuda.synchronize()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_view_batch_one_view_per_gpu(vren, tmp_path, world):
+    """SURVEY 8e row 4 (C5 batched): 8 views (yaw += 45 degrees) over the ranks, lights broadcast once from rank 0; every view's
+    cluster keys, counts, offsets and ordered light lists bit-exact vs the oracle run view by view"""
+    import math
+
+    import torch
+    import torch.multiprocessing as mp
+
+    from vren_b200 import synthetic
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    w, h, L, views = 640, 360, 4000, 8
+    mp.spawn(_view_worker, args=(world, _free_port(), str(tmp_path), w, h, L, views), nprocs=world, join=True)
+    oc = oracle.default_camera(w, h)
+    pos, lights = synthetic.point_lights(L, seed=71, aspect=w / h, intensity=(0.5, 3.0))
+    for v in range(views):
+        got = np.load(tmp_path / f"view{v}.npz")
+        assert int(got["rank"][0]) == v % world
+        view = synthetic.view_matrix(math.radians(45.0) * v, 0.0, (0.0, 0.0, 0.0))
+        wvp, wnodes, wpairs = oracle.construct_point_light_bvh(pos, lights, view)
+        wkeys, _ = oracle.find_unique_clusters(synthetic.depth_buffer(w, h, seed=80 + v), None, oc)
+        wcounts, woffsets, windices, wtotal = oracle.assign_lights(w, h, oc, wkeys, 1 << 17, wnodes, L, wpairs, wvp, 1 << 23)
+        assert np.array_equal(got["keys"], wkeys) and np.array_equal(got["counts"], wcounts) and np.array_equal(got["offsets"], woffsets)
+        assert np.array_equal(got["indices"], windices[:wtotal])
