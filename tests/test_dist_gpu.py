@@ -1,6 +1,7 @@
 """multi-GPU parity of the sharded sort / bucket sort / scan against the oracle: one process per GPU, NVLink peer stores
 through torch symmetric memory (the product path, vren_b200.dist.ShardedSort) and the NCCL baseline.  World sizes 2, 4, 8:
 a case is skipped when the box has fewer GPUs (gpurun --gpus N; logs under profiles/r2*_pytest_dist_gpu_n*.log)."""
+import datetime
 import os
 import socket
 
@@ -38,7 +39,7 @@ def _worker(rank, world, port, sizes, case, out_dir, path, rounds):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank), timeout=datetime.timedelta(seconds=90))
     try:
         keys, vals = _shard(rank, sizes[rank], case)
         tk = torch.from_numpy(keys.view(np.int32).copy()).cuda()
@@ -131,7 +132,7 @@ def _view_worker(rank, world, port, out_dir, w, h, L, views):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank), timeout=datetime.timedelta(seconds=90))
     try:
         vlib.load()
         oc = oracle.default_camera(w, h)

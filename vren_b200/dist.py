@@ -63,12 +63,16 @@ class CudaOps:
 
     def reduce_add(self, x: torch.Tensor) -> int:
         n = x.numel()
+        if n == 0:              # an empty shard contributes the identity
+            return 0
         out = self.vlib.reduce(x, n, "u32", "add", mode="final")
         P = self.lib.vrenb200_round_to_next_power_of_2(n)
         return int(out[P - 1].item()) & 0xFFFFFFFF
 
     def exclusive_scan(self, x: torch.Tensor, base: int) -> torch.Tensor:
         n = x.numel()
+        if n == 0:
+            return x
         sb = self.lib.vrenb200_scan_scratch_bytes(n)
         scratch = torch.empty(max(sb, 256), dtype=torch.uint8, device=x.device)
         self.vlib.check(self.lib.vrenb200_exclusive_scan_u32_base(self._stream(), x.data_ptr(), x.data_ptr(), n, base & 0xFFFFFFFF,
