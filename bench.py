@@ -135,6 +135,11 @@ def workload_string(log2n):
     return f"radix sort of 2^{log2n} uint32 key-value pairs per GPU (uniform keys, value=index)"
 
 
+def config_object(log2n):
+    """the same object in both arms (byte-identical): what is sorted, and how L2 is kept cold between steps"""
+    return {"workload": workload_string(log2n), "l2": f"inputs larger than L2: {(8 << log2n) >> 20} MiB of pairs per GPU and step, 126 MB of L2"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU check (std::stable_sort by key; oracle port) on all host threads, on the SAME
     size as the headline configuration (2^log2n pairs per step)"""
@@ -147,7 +152,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_string(args.log2n), "l2": "inputs larger than L2"},
+        "config": config_object(args.log2n),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"std::stable_sort by key (vren_test radix_sort.cpp:88 check, pairs extension) of 2^{args.log2n} "
                                    f"pairs per step on {threads} threads (chunk sort + parallel merges); one shard's size at every N"},
@@ -560,10 +565,12 @@ def run_ours(args):
     secondary = None
     if not args.no_secondary:
         torch.cuda.empty_cache()
-        if world == 1:
-            secondary = secondary_metrics(lib, vlib, dev)
-        else:
-            secondary = secondary_metrics_multi(lib, vlib, dev, sorter, rank, world)
+        # the headline line must survive a failure in the secondary rows (at N > 1 every rank takes part in their collectives,
+        # so a failure is agreed on before anyone moves on)
+        try:
+            secondary = secondary_metrics(lib, vlib, dev) if world == 1 else secondary_metrics_multi(lib, vlib, dev, sorter, rank, world)
+        except Exception as exc:  # noqa: BLE001
+            secondary = {"error": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         peak, peak_src = measured_peaks()
         pass_avg_ms = sum(pass_ms) / len(pass_ms)
@@ -573,9 +580,14 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, sec = cpu_sort_sample(args.log2n, threads)
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"std::stable_sort by key of 2^{args.log2n} pairs (the whole step), {threads} threads, {sec:.1f} s"}
+            try:
+                v, sec = cpu_sort_sample(args.log2n, threads)
+                cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                       "sample": f"std::stable_sort by key of 2^{args.log2n} pairs (the whole step), {threads} threads, {sec:.1f} s"}
+            except MemoryError:     # a host with less than ~8 GB free: a quarter of the step
+                v, sec = cpu_sort_sample(args.log2n - 2, threads)
+                cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                       "sample": f"std::stable_sort by key of 2^{args.log2n - 2} pairs (host memory too small for the whole step), {threads} threads, {sec:.1f} s"}
         traffic = ncu_traffic(pass_kernel, args.log2n)
         passes = 4
         launches_single = 2 + 2 * passes                                   # histogram, offsets, 4 passes + their (idle) redo kernels
@@ -584,13 +596,12 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_string(args.log2n),
-                       "l2": "inputs larger than L2 (2 GiB per GPU, restored or left untouched between steps)",
-                       "variant": variant_name,
-                       "ranking_check_failures": violation,
-                       "parallelism": "1 GPU" if world == 1 else
-                       f"one global sort of {world}x2^{args.log2n} pairs: device plan, local partition by the top digit, {args.rounds} rounds of "
-                       "NVLink peer-store transfers overlapped with segmented 3-pass onesweep of what has arrived (no NCCL on the data path)"},
+            "config": config_object(args.log2n),
+            "details": {"variant": variant_name,
+                        "ranking_check_failures": violation,
+                        "parallelism": "1 GPU" if world == 1 else
+                        f"one global sort of {world}x2^{args.log2n} pairs: device plan, local partition by the top digit, {args.rounds} rounds of "
+                        "NVLink peer-store transfers overlapped with segmented 3-pass onesweep of what has arrived (no NCCL on the data path)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
                          "traffic_source": traffic, "kernel": pass_kernel, "peak_source": peak_src,

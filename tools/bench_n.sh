@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_bench_n.sh N "extra bench args" ... : one bench line per extra-args string, compact summary
+# usage: tools/bench_n.sh N "extra bench args" ... : one bench line per extra-args string, compact summary
 N=$1; shift
 for extra in "$@"; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 6 --warmup 3 --no-secondary $extra 2>&1 | python -c "

@@ -1,6 +1,6 @@
 // Micro-benchmark: shared-memory pipe cost of the operations the onesweep pass is built from, at the pass kernel's own
 // occupancy (2 CTAs x 384 threads per SM, per-warp 256-entry counters, random 8-bit digits).
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/smem_ops tools_micro/smem_ops.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/smem_ops tools/micro/smem_ops.cu
 // Prints SM cycles per warp instruction (both CTAs of an SM running) for every operation.
 #include <cstdint>
 #include <cstdio>

@@ -1,5 +1,5 @@
 """summarise ncu CSV exports (raw + source pages) into markdown: key metrics per kernel + hottest source lines.
-usage: python tools_ncu_summary.py gpurun_out/<tag> [cu-file-stem for line mapping]"""
+usage: python tools/ncu_summary.py gpurun_out/<tag> [cu-file-stem for line mapping]"""
 import collections
 import csv
 import re

@@ -1,6 +1,6 @@
 """Peer-store bandwidth ceiling between GPUs of one node: every rank copies a 1 GiB buffer into the next rank's
 symmetric-memory buffer with a plain vectorised copy kernel (torch .copy_ on the peer-mapped tensor), all ranks at once.
-Run: torchrun --nproc-per-node N tools_p2p_bw.py"""
+Run: torchrun --nproc-per-node N tools/p2p_bw.py"""
 import json
 import os
 

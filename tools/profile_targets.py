@@ -37,11 +37,8 @@ g = torch.Generator(device=dev)
 g.manual_seed(1)
 keys = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
 vals = torch.arange(n, dtype=torch.int32, device=dev)
-if "VREN_SORT_VARIANT" in os.environ:
-    vlib.check(lib.vrenb200_radix_sort_set_variant(int(os.environ["VREN_SORT_VARIANT"])), "variant")
-if "VREN_PREFETCH_TILES" in os.environ:
-    vlib.check(lib.vrenb200_radix_sort_set_prefetch_tiles(int(os.environ["VREN_PREFETCH_TILES"])), "prefetch distance")
+cfg = vlib.SortConfig(vlib.RANKING_AUTO, vlib.TILE_IDS_AUTO, int(os.environ.get("VREN_SORT_VARIANT", "0")))
 for _ in range(2):
-    vlib.radix_sort_pairs(keys, vals)
+    vlib.radix_sort_pairs(keys, vals, config=cfg)
 torch.cuda.synchronize()
 print("done")

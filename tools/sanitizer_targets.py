@@ -1,10 +1,12 @@
 """Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
-compute-sanitizer --tool memcheck python tools_sanitizer_targets.py"""
+compute-sanitizer --tool memcheck python tools/sanitizer_targets.py   (from the repo root)"""
 import math
+import sys
 
 import numpy as np
 import torch
 
+sys.path.insert(0, ".")
 from vren_b200 import lib as vlib, synthetic
 from vren_b200.pipeline import ClusterAndShade
 
@@ -24,19 +26,23 @@ n = 3 * 8192 + 1234
 k = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
 import os  # noqa: E402
 only = [int(a) for a in os.environ.get("VREN_SANITIZER_VARIANTS", "").split(",") if a]
-for var in only or range(lib.vrenb200_radix_sort_num_variants()):
-    if b"FAKE" in lib.vrenb200_radix_sort_variant_name(var) or b"[retired]" in lib.vrenb200_radix_sort_variant_name(var):
-        continue
-    vlib.check(lib.vrenb200_radix_sort_set_variant(var), "variant")
-    kk, vv = k.clone(), torch.arange(n, dtype=torch.int32, device=dev)
-    vlib.radix_sort_pairs(kk, vv)
-    u = kk.to(torch.int64) & 0xFFFFFFFF
-    assert bool((u[1:] >= u[:-1]).all()) and torch.equal(k[vv.long()], kk), ("pairs", var)
-    kk = k.clone()
-    vlib.radix_sort_keys(kk)
-    u = kk.to(torch.int64) & 0xFFFFFFFF
-    assert bool((u[1:] >= u[:-1]).all()), ("keys", var)
-vlib.check(lib.vrenb200_radix_sort_set_variant(0), "variant")
+for var in only or range(1, lib.vrenb200_radix_sort_num_variants() + 1):
+    keys_only_tile = b"x64/" in lib.vrenb200_radix_sort_variant_name(var)
+    for tile_ids in (vlib.TILE_IDS_BLOCK_INDEX, vlib.TILE_IDS_TICKET):
+        cfg = vlib.SortConfig(vlib.RANKING_AUTO, tile_ids, var)
+        if not keys_only_tile:
+            kk, vv = k.clone(), torch.arange(n, dtype=torch.int32, device=dev)
+            vlib.radix_sort_ex(kk, vv, cfg)
+            u = kk.to(torch.int64) & 0xFFFFFFFF
+            assert bool((u[1:] >= u[:-1]).all()) and torch.equal(k[vv.long()], kk), ("pairs", var)
+        kk = k.clone()
+        vlib.radix_sort_ex(kk, None, cfg)
+        u = kk.to(torch.int64) & 0xFFFFFFFF
+        assert bool((u[1:] >= u[:-1]).all()), ("keys", var)
+# the repeat passes of the verified ranking
+kk, vv = k.clone(), torch.arange(n, dtype=torch.int32, device=dev)
+assert vlib.radix_sort_ex(kk, vv, vlib.SortConfig(vlib.RANKING_SELFTEST_REDO, 0, 0)) == 0xF
+assert torch.equal(k[vv.long()], kk)
 # variant 0 takes the small tile below 2^21 pairs: exercise the default large tiles too (ragged last tile)
 n = (1 << 21) + 12345
 k = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
@@ -49,13 +55,11 @@ vlib.radix_sort_keys(kk)
 u = kk.to(torch.int64) & 0xFFFFFFFF
 assert bool((u[1:] >= u[:-1]).all()), "keys, default tile"
 # bucket sort: END offsets by search in the sorted output (the path of inputs >= 2^20 pairs), then by counting
-vlib.check(lib.vrenb200_bucket_sort_set_search_min(0), "search_min")
 pairs = torch.randint(0, 1 << 16, (50001, 2), dtype=torch.int32, device=dev, generator=g)
-_, sorted_pairs, counters = vlib.bucket_sort(pairs)
+_, sorted_pairs, counters = vlib.bucket_sort(pairs, end_offsets=1)
 assert int(counters[-1]) == 50001
-vlib.check(lib.vrenb200_bucket_sort_set_search_min(1 << 20), "search_min")
 pairs = torch.randint(0, 1 << 16, (50001, 2), dtype=torch.int32, device=dev, generator=g)
-_, sorted_pairs, counters = vlib.bucket_sort(pairs)
+_, sorted_pairs, counters = vlib.bucket_sort(pairs, end_offsets=0)
 keys16 = sorted_pairs[:, 0] & 0xFFFF
 assert bool((keys16[1:] >= keys16[:-1]).all()) and int(counters[-1]) == 50001
 # reduce

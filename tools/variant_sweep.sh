@@ -5,7 +5,7 @@ for v in 2 3 5 6 8 9 11 12; do
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('variant $v', d['config']['variant'], 'Gpairs/s %.2f' % d['value'], 'ms %.3f' % d['ms_per_step'], 'pass_ms %.3f' % d['roofline']['kernel_ms'], 'frac %.3f' % d['roofline']['frac'])
+        d = json.loads(l); print('variant $v', d['details']['variant'], 'Gpairs/s %.2f' % d['value'], 'ms %.3f' % d['ms_per_step'], 'pass_ms %.3f' % d['roofline']['kernel_ms'], 'frac %.3f' % d['roofline']['frac'])
     elif 'rror' in l: print(l.strip())
 "
 done
@@ -14,7 +14,7 @@ for t in block ticket; do for r in verified sampled unverified match; do
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('ranking $r tile-ids $t', 'Gpairs/s %.2f' % d['value'], 'ms %.3f' % d['ms_per_step'], 'pass_ms %.3f' % d['roofline']['kernel_ms'], 'frac %.3f' % d['roofline']['frac'], 'violations', d['config']['ranking_check_failures'])
+        d = json.loads(l); print('ranking $r tile-ids $t', 'Gpairs/s %.2f' % d['value'], 'ms %.3f' % d['ms_per_step'], 'pass_ms %.3f' % d['roofline']['kernel_ms'], 'frac %.3f' % d['roofline']['frac'], 'violations', d['details']['ranking_check_failures'])
     elif 'rror' in l: print(l.strip())
 "
 done; done
