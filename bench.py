@@ -227,6 +227,32 @@ def secondary_metrics(lib, vlib, dev):
     out["radix_sort_keys_2p28"] = {"ms": ms, "Gkeys/s": n / ms / 1e6, "GB/s": 36 * n / ms / 1e6, "frac_hbm": 36 * n / ms / 1e6 / peak,
                                    "bytes_per_key": 36, "note": "time of (restore + sort) minus time of restore"}
     del keys, shuffled, kscr
+    # C1 (BASELINE configs[0]: the reference's own radix-sort sizes, vren_test radix_sort.cpp:82-143): launch-bound small sorts.
+    # "auto" is what a caller gets (ballot-match passes below 2^21 elements: no repeat kernel behind a pass); "sampled" is the
+    # large-input default forced onto the same size, for comparison
+    try:
+        for log2s in (10, 20):
+            ns = 1 << log2s
+            src = torch.randint(-(1 << 31), (1 << 31) - 1, (ns,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+            work = src.clone()
+            sb_s = lib.vrenb200_radix_sort_scratch_bytes(ns, 0)
+            scr_s = torch.empty(sb_s, dtype=torch.uint8, device=dev)
+            row = {}
+            t_restore = timed(lambda: work.copy_(src), iters=30)
+            for label, cfg_s in (("auto", vlib.SortConfig(vlib.RANKING_AUTO, vlib.TILE_IDS_AUTO, 0)),
+                                 ("sampled", vlib.SortConfig(vlib.RANKING_ATOMIC_SAMPLED, vlib.TILE_IDS_AUTO, 0))):
+                def sort_small():
+                    work.copy_(src)
+                    vlib.check(lib.vrenb200_radix_sort_ex(stream, work.data_ptr(), None, ns, scr_s.data_ptr(), sb_s, C.addressof(cfg_s), None), "radix_sort_ex")
+
+                row[f"us_{label}"] = (timed(sort_small, iters=30) - t_restore) * 1e3
+            wk = (work ^ torch.tensor(-(1 << 31), dtype=torch.int32, device=dev)).to(torch.int64)
+            assert bool((wk[1:] >= wk[:-1]).all()), "bench: small sort not sorted"
+            row["note"] = "keys only, one call on an idle stream; time of (restore + sort) minus time of restore"
+            out[f"radix_sort_keys_2p{log2s}"] = row
+            del src, work, scr_s
+    except Exception as exc:  # noqa: BLE001 - rows added without a GPU at hand: they must not take the other rows with them
+        out["radix_sort_keys_small"] = {"error": f"{type(exc).__name__}: {exc}"}
     nb = 1 << 26
     pairs = torch.randint(0, 1 << 16, (nb, 2), dtype=torch.int32, device=dev, generator=g)
     ob = lib.vrenb200_bucket_sort_output_bytes(nb)

@@ -108,6 +108,9 @@ def test_sort_kernel_selection(handle):
     assert "F_RANK_ATOMIC" in name(1 << 24, 1, **u) and "VERIFY" not in name(1 << 24, 1, **u)
     assert "F_VERIFY_SAMPLED" in name(1 << 24, 1, ranking=lib.RANKING_ATOMIC_SAMPLED)
     assert name((1 << 21) - 1, 1).startswith("256x16/") and not name(1 << 21, 1).startswith("256x16/")   # small-tile switch
+    # launch-bound sizes: left to the library, the ranking is the ballot match (no repeat kernel behind every pass); asked for, it is honoured
+    assert "F_RANK_LEADER" in name(1 << 20, 1) and "F_RANK_LEADER" in name(1 << 10, 0) and "ATOMIC" not in name(1 << 20, 1)
+    assert "F_VERIFY_SAMPLED" in name(1 << 20, 1, ranking=lib.RANKING_ATOMIC_SAMPLED) and "F_VERIFY_ALL" in name(1000, 0, ranking=lib.RANKING_ATOMIC_VERIFIED)
     # an explicit table entry wins over the ranking mode; entries are 1-based, 0 = automatic
     assert name(1 << 24, 1, variant=3) == handle.vrenb200_radix_sort_variant_name(3).decode()
     assert handle.vrenb200_radix_sort_variant_name(0) == b"" and handle.vrenb200_radix_sort_variant_name(handle.vrenb200_radix_sort_num_variants() + 1) == b""
@@ -120,3 +123,27 @@ def test_release_library_exports_no_process_global_hooks(handle):
     for name in ("vrenb200_radix_sort_set_variant", "vrenb200_radix_sort_set_ranking", "vrenb200_scan_set_variant",
                  "vrenb200_bucket_sort_set_search_min", "vrenb200_radix_partition_set_shape", "vrenb200_radix_sort_set_prefetch_tiles"):
         assert not hasattr(handle, name), name
+
+
+def test_python_callers_match_the_declared_signatures(handle):
+    """every `lib.vrenb200_*(...)` call in bench.py, the package, the driver entry and the tests passes as many arguments as the
+    ctypes binding of include/vrenb200.h declares — the bench and smoke paths run on the GPU box only, an ABI drift must show here"""
+    import ast
+
+    files = [ROOT / "bench.py", ROOT / "__graft_entry__.py"] + sorted((ROOT / "vren_b200").glob("*.py")) + \
+        sorted((ROOT / "tests").glob("*.py")) + sorted((ROOT / "tools").glob("*.py"))
+    optional = {"vrenb200_scan_set_variant"}          # tuning builds only; callers guard with hasattr
+    checked = 0
+    for path in files:
+        for node in ast.walk(ast.parse(path.read_text())):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("vrenb200_")):
+                continue
+            name = node.func.attr
+            if name in optional or any(isinstance(a, ast.Starred) for a in node.args):
+                continue
+            fn = getattr(handle, name, None)
+            assert fn is not None, f"{path.name}:{node.lineno}: {name} is not exported"
+            assert fn.argtypes is not None, f"{name}: no argtypes declared in vren_b200/lib.py"
+            assert len(fn.argtypes) == len(node.args), f"{path.name}:{node.lineno}: {name} called with {len(node.args)} arguments, declared {len(fn.argtypes)}"
+            checked += 1
+    assert checked > 100

@@ -100,6 +100,7 @@ struct sort_options
     int ranking;    // VRENB200_RANKING_*
     int tile_ids;   // VRENB200_TILE_IDS_*
     int variant;    // tuning builds: index into the variant table (0 = automatic)
+    bool ranking_auto;   // the caller (and the environment) left the ranking to the library: pick_variant may choose by size
 };
 
 sort_options resolve_options(const vrenb200_sort_config* cfg);

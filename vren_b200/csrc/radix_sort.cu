@@ -971,7 +971,7 @@ sort_options resolve_options(const vrenb200_sort_config* cfg)
 {
     // the defaults can be overridden through the environment (read once, never written again)
     static const sort_options env = []() {
-        sort_options o{VRENB200_RANKING_AUTO, VRENB200_TILE_IDS_AUTO, 0};
+        sort_options o{VRENB200_RANKING_AUTO, VRENB200_TILE_IDS_AUTO, 0, false};
         if (const char* e = std::getenv("VRENB200_SORT_RANKING"))
             o.ranking = !std::strcmp(e, "match") ? VRENB200_RANKING_MATCH
                       : !std::strcmp(e, "verified") ? VRENB200_RANKING_ATOMIC_VERIFIED
@@ -988,6 +988,7 @@ sort_options resolve_options(const vrenb200_sort_config* cfg)
         if (cfg->tile_ids != VRENB200_TILE_IDS_AUTO) o.tile_ids = cfg->tile_ids;
         o.variant = cfg->variant;
     }
+    o.ranking_auto = o.ranking == VRENB200_RANKING_AUTO;
     if (o.ranking == VRENB200_RANKING_AUTO) o.ranking = VRENB200_RANKING_DEFAULT;
     if (o.tile_ids == VRENB200_TILE_IDS_AUTO) o.tile_ids = VRENB200_TILE_IDS_DEFAULT;
     return o;
@@ -1005,6 +1006,10 @@ const sort_variant& pick_variant(uint32_t n, int layout, const sort_options& opt
     default: group = 2; break;   // ATOMIC_SAMPLED (the default), SELFTEST
     }
     const int size = n < kSmallTileBelow ? 0 : (layout == LAYOUT_KEYS ? 1 : 2);
+    // Small inputs are launch-bound (profiles/r1z_size_sweep.log: 41-67 us from 2^10 to 2^20 elements, the kernels themselves a
+    // few microseconds each), so when the ranking is left to the library they take the ballot-match kernel: ordered by
+    // construction, hence no repeat kernel behind every pass (4 launches fewer per radix sort, 2 per bucket sort)
+    if (size == 0 && opt.ranking_auto) group = 0;
     return g_variants[group * 3 + size];
 }
 
