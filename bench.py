@@ -617,7 +617,7 @@ def run_ours(args):
         traffic = ncu_traffic(pass_kernel, args.log2n)
         passes = 4
         launches_single = 2 + 2 * passes                                   # histogram, offsets, 4 passes + their (idle) redo kernels
-        launches_multi = 4 + 2 + 1 + args.rounds * (1 + 2 + 6) + 2         # hist, publish, offsets, plan, partition + redo, wait, per round: transfer + wait + scan + 3 passes + 3 redos, compact, done
+        launches_multi = 4 + 2 + 1 + args.rounds * (1 + 3 + 6) + 2         # hist, publish, offsets, plan, partition + redo, wait, per round: transfer + wait + segment histograms + scan + 3 passes + 3 redos, compact, done
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -750,10 +750,14 @@ def main():
     ap.add_argument("--variant", type=int, default=None, help="1-based entry of the kernel table (vrenb200_sort_config::variant)")
     ap.add_argument("--ranking", default="auto", choices=["auto", "match", "verified", "sampled", "unverified"])
     ap.add_argument("--tile-ids", default="auto", choices=["auto", "block", "ticket"])
-    ap.add_argument("--rounds", type=int, default=4, help="N>1: pieces the exchange is cut into (transfer of one overlaps the sorting of the previous)")
+    ap.add_argument("--rounds", type=int, default=None,
+                    help="N>1: pieces the exchange is cut into (transfer of one overlaps the sorting of the previous); default 2 at N = 2, else 4 "
+                         "(measured: profiles/r2g_bench_n2_tma.log, r2j_bench_n4_exclusive.log, r2h_bench_n8_tma.log)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
+    if args.rounds is None:
+        args.rounds = 2 if int(os.environ.get("WORLD_SIZE", "1")) == 2 else 4
     if args.impl == "reference":
         run_reference(args)
     else:
