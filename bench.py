@@ -328,6 +328,30 @@ def secondary_metrics(lib, vlib, dev):
     verts = torch.empty(lib.vrenb200_visualize_bvh_vertex_count(levels), 4, dtype=torch.float32, device=dev)
     ms = timed(lambda: vlib.check(lib.vrenb200_visualize_bvh(stream, nodes.data_ptr(), levels, verts.data_ptr()), "visualize_bvh"))
     out["visualize_bvh_2p20_leaves"] = {"ms": ms, "GB/s": 416 * length / ms / 1e6, "frac_hbm": 416 * length / ms / 1e6 / peak, "bytes_per_node": 416}
+    # LAST (a fault here must not cost any other row): the opt-in single-CTA sort (csrc/small_sort.cu, one launch for n <= 8192), never
+    # run on hardware before the round's final driver run — tests/test_small_sort.py is its parity check
+    try:
+        cfg_1 = vlib.SortConfig(vlib.RANKING_AUTO, vlib.TILE_IDS_AUTO, vlib.SORT_VARIANT_SINGLE_CTA)
+        row = {}
+        for log2s in (10, 13):
+            ns = 1 << log2s
+            src = torch.randint(-(1 << 31), (1 << 31) - 1, (ns,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+            work = src.clone()
+            sb_s = lib.vrenb200_radix_sort_scratch_bytes(ns, 0)
+            scr_s = torch.empty(sb_s, dtype=torch.uint8, device=dev)
+            t_restore = timed(lambda: work.copy_(src), iters=30)
+
+            def sort_one_cta():
+                work.copy_(src)
+                vlib.check(lib.vrenb200_radix_sort_ex(stream, work.data_ptr(), None, ns, scr_s.data_ptr(), sb_s, C.addressof(cfg_1), None), "radix_sort_ex")
+
+            us = (timed(sort_one_cta, iters=30) - t_restore) * 1e3
+            want = torch.sort(src.to(torch.int64) & 0xFFFFFFFF).values
+            row[f"us_2p{log2s}_keys"] = us if torch.equal(work.to(torch.int64) & 0xFFFFFFFF, want) else "WRONG RESULT"
+        row["note"] = "opt-in (vrenb200_sort_config::variant = -1): all four passes in one CTA, one launch; time of (restore + sort) minus restore"
+        out["radix_sort_single_cta"] = row
+    except Exception as exc:  # noqa: BLE001
+        out["radix_sort_single_cta"] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
 
 
@@ -586,7 +610,8 @@ def run_ours(args):
     te = torch.tensor([e2e_step_ms, single_ms, float(d2h_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n / (float(te[0].item()) * 1e-3) / 1e9
+    te = [float(x) for x in te.tolist()]          # host numbers from here on: nothing below may need the device to print the line
+    e2e_value = world * n / (te[0] * 1e-3) / 1e9
 
     secondary = None
     if not args.no_secondary:
@@ -634,9 +659,9 @@ def run_ours(args):
                          "kernel_ms": pass_avg_ms, "histogram_ms": sum(hist_ms) / len(hist_ms),
                          "whole_sort_frac": BYTES_PER_PAIR_SORT * n / (ms_max * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": int(te[2].item()),
-                    "ms_per_step": float(te[0].item()), "steps": e2e_steps, "issue": e2e_note,
-                    "single_call_ms": float(te[1].item()), "single_call_value": world * n / (float(te[1].item()) * 1e-3) / 1e9},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": int(te[2]),
+                    "ms_per_step": te[0], "steps": e2e_steps, "issue": e2e_note,
+                    "single_call_ms": te[1], "single_call_value": world * n / (te[1] * 1e-3) / 1e9},
             "gpu_launches": (launches_single if world == 1 else launches_multi) * args.steps,
             "verification": "sortedness + stability + pair integrity" if world == 1 else
                             "2^22/rank global sort == oracle.sort_pairs; timed output: all-reduced pair-multiset checksum, per-shard sortedness and stability, cross-rank boundary order",

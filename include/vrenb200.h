@@ -114,8 +114,14 @@ enum {
 typedef struct vrenb200_sort_config {
     int ranking;
     int tile_ids;
-    int variant;     /* 0 = automatic; else 1-based index into the kernel table (vrenb200_radix_sort_variant_name) */
+    int variant;     /* 0 = automatic; > 0: 1-based index into the kernel table (vrenb200_radix_sort_variant_name);
+                        VRENB200_SORT_VARIANT_SINGLE_CTA: see below */
 } vrenb200_sort_config;
+/* vrenb200_radix_sort_ex only, n <= 8192: the whole sort (all four passes) in ONE launch of ONE CTA, in shared memory — the
+ * reference's own test size (1024 keys, vren_test radix_sort.cpp:130-143) without the 7 launches of the tiled path.  Opt-in:
+ * written after the round's GPU time was spent, its body has run on the host CTA emulator only (tests/cpp/cta_emulator.hpp),
+ * first hardware run = tests/test_small_sort.py.  Larger n, or a profiled call, silently takes the tiled path. */
+#define VRENB200_SORT_VARIANT_SINGLE_CTA (-1)
 
 /* one scratch blob holds the ping-pong buffers, digit histograms and look-back state. n < 2^30 */
 size_t vrenb200_radix_sort_scratch_bytes(uint32_t n, int with_values);

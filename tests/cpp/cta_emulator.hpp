@@ -1,0 +1,126 @@
+// Host execution of a CUDA kernel BODY, thread for thread: one OS thread per CUDA thread of ONE CTA, __syncthreads() and the
+// warp-synchronous intrinsics built on pthread barriers.  A body written against threadIdx.x, __syncthreads, __syncwarp,
+// __shfl_sync, __shfl_up_sync, __match_any_sync, __popc and __clz (full masks, convergent warps) compiles unchanged with g++
+// when this header is included BEFORE it.  Built with -fsanitize=thread, a missing barrier between two accesses of the same
+// shared word shows up as a data race (pthread barriers are synchronisation ThreadSanitizer understands) — the host-side
+// stand-in for compute-sanitizer's racecheck when no GPU is at hand.
+// Test infrastructure only (tests/test_small_sort_emulation.py); nothing of the product includes it.
+#pragma once
+
+#include <pthread.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <vector>
+
+#define __device__
+#define __global__
+#define __forceinline__ inline
+
+struct emu_uint3 { unsigned x, y, z; };
+static thread_local emu_uint3 threadIdx = {0, 0, 0};
+
+namespace cta_emu {
+
+struct warp_state
+{
+    pthread_barrier_t bar;
+    uint32_t slot[32];
+};
+
+struct cta_state
+{
+    pthread_barrier_t bar;
+    std::vector<warp_state> warps;
+};
+
+static thread_local cta_state* cta = nullptr;
+
+inline warp_state& my_warp() { return cta->warps[threadIdx.x >> 5]; }
+inline unsigned my_lane() { return threadIdx.x & 31u; }
+
+struct thread_arg
+{
+    cta_state* cta;
+    unsigned tid;
+    const std::function<void()>* body;
+};
+
+inline void* thread_main(void* p)
+{
+    thread_arg* a = static_cast<thread_arg*>(p);
+    threadIdx.x = a->tid;
+    cta = a->cta;
+    (*a->body)();
+    return nullptr;
+}
+
+// runs `body` once per thread of a CTA of `threads` threads (a multiple of 32)
+inline void run_cta(unsigned threads, const std::function<void()>& body)
+{
+    cta_state st;
+    st.warps.resize(threads / 32);
+    pthread_barrier_init(&st.bar, nullptr, threads);
+    for (auto& w : st.warps) pthread_barrier_init(&w.bar, nullptr, 32);
+    std::vector<pthread_t> ids(threads);
+    std::vector<thread_arg> args(threads);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 512 * 1024);
+    for (unsigned t = 0; t < threads; t++)
+    {
+        args[t] = thread_arg{&st, t, &body};
+        if (pthread_create(&ids[t], &attr, thread_main, &args[t]) != 0)
+        {
+            std::fprintf(stderr, "cta_emulator: pthread_create failed at thread %u\n", t);
+            std::exit(2);
+        }
+    }
+    for (unsigned t = 0; t < threads; t++) pthread_join(ids[t], nullptr);
+    pthread_attr_destroy(&attr);
+    pthread_barrier_destroy(&st.bar);
+    for (auto& w : st.warps) pthread_barrier_destroy(&w.bar);
+}
+
+} // namespace cta_emu
+
+inline void __syncthreads() { pthread_barrier_wait(&cta_emu::cta->bar); }
+inline void __syncwarp(unsigned = 0xFFFFFFFFu) { pthread_barrier_wait(&cta_emu::my_warp().bar); }
+
+inline uint32_t __shfl_sync(unsigned, uint32_t v, int src_lane)
+{
+    cta_emu::warp_state& w = cta_emu::my_warp();
+    w.slot[cta_emu::my_lane()] = v;
+    pthread_barrier_wait(&w.bar);
+    const uint32_t r = w.slot[(unsigned) src_lane & 31u];
+    pthread_barrier_wait(&w.bar);
+    return r;
+}
+
+inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned delta)
+{
+    cta_emu::warp_state& w = cta_emu::my_warp();
+    const unsigned lane = cta_emu::my_lane();
+    w.slot[lane] = v;
+    pthread_barrier_wait(&w.bar);
+    const uint32_t r = lane >= delta ? w.slot[lane - delta] : v;
+    pthread_barrier_wait(&w.bar);
+    return r;
+}
+
+inline unsigned __match_any_sync(unsigned, uint32_t v)
+{
+    cta_emu::warp_state& w = cta_emu::my_warp();
+    w.slot[cta_emu::my_lane()] = v;
+    pthread_barrier_wait(&w.bar);
+    unsigned m = 0;
+    for (unsigned i = 0; i < 32; i++)
+        if (w.slot[i] == v) m |= 1u << i;
+    pthread_barrier_wait(&w.bar);
+    return m;
+}
+
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned) x); }

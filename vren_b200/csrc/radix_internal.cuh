@@ -110,5 +110,8 @@ size_t control_bytes(uint32_t n);
 int launch_digit_histograms(cudaStream_t s, const uint32_t* keys, uint32_t n, sort_control* ctl);
 int launch_scan_histograms(cudaStream_t s, sort_control* ctl, int passes);
 int preload_sort_kernels(int layout, bool segmented, const sort_options& opt);   // every kernel a sort with these options may launch
+// small_sort.cu: the whole sort in one CTA (in place, vals may be nullptr), for 1 <= n <= single_cta_sort_max()
+uint32_t single_cta_sort_max();
+int launch_single_cta_sort(cudaStream_t s, uint32_t* keys, uint32_t* vals, uint32_t n, int first_pass, int num_passes);
 
 } // namespace vrenb200

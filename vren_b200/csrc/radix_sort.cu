@@ -1177,6 +1177,12 @@ extern "C" int vrenb200_radix_sort_ex(vrenb200_stream_t stream, uint32_t* keys, 
     if (keys == nullptr) return VRENB200_EINVAL_ARG;
     const int kv = values != nullptr;
     if (scratch == nullptr || scratch_bytes < vrenb200_radix_sort_scratch_bytes(n, kv)) return VRENB200_ESCRATCH;
+    // opt-in: the whole sort in one CTA, one launch (small_sort.cu); larger inputs and profiled calls take the tiled path
+    if (cfg != nullptr && cfg->variant == VRENB200_SORT_VARIANT_SINGLE_CTA && n <= single_cta_sort_max() && prof == nullptr)
+    {
+        if ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(values)) & 3) return VRENB200_EALIGN;
+        return launch_single_cta_sort(as_stream(stream), keys, values, n, 0, kPasses);
+    }
     char* p = static_cast<char*>(scratch);
     const size_t alt = align_up((size_t) n * 4, 256);
     return radix_sort_impl(as_stream(stream), keys, values, n, reinterpret_cast<uint32_t*>(p),

@@ -30,6 +30,7 @@ class VrenError(RuntimeError):
 
 RANKING_AUTO, RANKING_MATCH, RANKING_ATOMIC_VERIFIED, RANKING_ATOMIC_SAMPLED, RANKING_ATOMIC_UNVERIFIED, RANKING_SELFTEST_REDO = range(6)
 TILE_IDS_AUTO, TILE_IDS_BLOCK_INDEX, TILE_IDS_TICKET = range(3)
+SORT_VARIANT_SINGLE_CTA = -1      # vrenb200_sort_config::variant: the whole sort in one CTA (n <= 8192), opt-in
 
 
 class SortConfig(C.Structure):
