@@ -261,7 +261,9 @@ def secondary_metrics(lib, vlib, dev):
     bscr = torch.empty(bb, dtype=torch.uint8, device=dev)
     ms = timed(lambda: vlib.check(lib.vrenb200_bucket_sort(stream, pairs.data_ptr(), nb, bout.data_ptr(), bscr.data_ptr(), bb), "bucket_sort"))
     out["bucket_sort_2p26_uvec2"] = {"ms": ms, "Gpairs/s": nb / ms / 1e6, "GB/s": 40 * nb / ms / 1e6, "frac_hbm": 40 * nb / ms / 1e6 / peak,
-                                     "bytes_per_pair": 40}
+                                     "bytes_per_pair": 40, "frac_hbm_of_24_B_per_pair": 24 * nb / ms / 1e6 / peak,
+                                     "note": "40 B/pair = what this stable two-pass sort moves (8 histogram read + 2 x 16); SURVEY 8d's 24 B/pair is the "
+                                             "reference's unstable direct scatter (count + write), which a deterministic result cannot use"}
     del pairs, bout, bscr
 
     # C4: BuildBVH over 2^20 pre-filled leaves (33 B/leaf)
