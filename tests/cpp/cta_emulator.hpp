@@ -1,6 +1,7 @@
 // Host execution of a CUDA kernel BODY, thread for thread: one OS thread per CUDA thread of ONE CTA, __syncthreads() and the
-// warp-synchronous intrinsics built on pthread barriers.  A body written against threadIdx.x, __syncthreads, __syncwarp,
-// __shfl_sync, __shfl_up_sync, __match_any_sync, __popc and __clz (full masks, convergent warps) compiles unchanged with g++
+// warp-synchronous intrinsics built on pthread barriers.  A body written against threadIdx.x, __syncthreads, __syncthreads_count,
+// __syncwarp, __shfl_sync, __shfl_up_sync, __match_any_sync, atomicOr / atomicAdd, __shared__ variables, __popc and __clz (full
+// masks, convergent warps) compiles unchanged with g++
 // when this header is included BEFORE it.  Built with -fsanitize=thread, a missing barrier between two accesses of the same
 // shared word shows up as a data race (pthread barriers are synchronisation ThreadSanitizer understands) — the host-side
 // stand-in for compute-sanitizer's racecheck when no GPU is at hand.
@@ -15,9 +16,16 @@
 #include <functional>
 #include <vector>
 
+// (a translation unit that needs the CUDA runtime's host types includes <cuda_runtime.h> BEFORE this header: its host_defines.h
+// gives these qualifiers attribute meanings that g++ does not know)
+#undef __device__
+#undef __global__
+#undef __forceinline__
+#undef __shared__
 #define __device__
 #define __global__
 #define __forceinline__ inline
+#define __shared__ static      // one CTA at a time: a function-level static IS the CTA's shared variable
 
 struct emu_uint3 { unsigned x, y, z; };
 static thread_local emu_uint3 threadIdx = {0, 0, 0};
@@ -27,13 +35,14 @@ namespace cta_emu {
 struct warp_state
 {
     pthread_barrier_t bar;
-    uint32_t slot[32];
+    uint64_t slot[32];
 };
 
 struct cta_state
 {
     pthread_barrier_t bar;
     std::vector<warp_state> warps;
+    int vote = 0;               // __syncthreads_count
 };
 
 static thread_local cta_state* cta = nullptr;
@@ -89,23 +98,43 @@ inline void run_cta(unsigned threads, const std::function<void()>& body)
 inline void __syncthreads() { pthread_barrier_wait(&cta_emu::cta->bar); }
 inline void __syncwarp(unsigned = 0xFFFFFFFFu) { pthread_barrier_wait(&cta_emu::my_warp().bar); }
 
-inline uint32_t __shfl_sync(unsigned, uint32_t v, int src_lane)
+// number of threads of the CTA whose predicate is non-zero; a barrier like __syncthreads()
+inline int __syncthreads_count(int pred)
 {
+    cta_emu::cta_state* c = cta_emu::cta;
+    if (pred) __atomic_fetch_add(&c->vote, 1, __ATOMIC_RELAXED);
+    pthread_barrier_wait(&c->bar);
+    const int r = __atomic_load_n(&c->vote, __ATOMIC_RELAXED);
+    pthread_barrier_wait(&c->bar);
+    if (threadIdx.x == 0) __atomic_store_n(&c->vote, 0, __ATOMIC_RELAXED);
+    pthread_barrier_wait(&c->bar);
+    return r;
+}
+
+inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src_lane)
+{
+    static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
     cta_emu::warp_state& w = cta_emu::my_warp();
-    w.slot[cta_emu::my_lane()] = v;
+    w.slot[cta_emu::my_lane()] = (uint64_t) v;
     pthread_barrier_wait(&w.bar);
-    const uint32_t r = w.slot[(unsigned) src_lane & 31u];
+    const T r = (T) w.slot[(unsigned) src_lane & 31u];
     pthread_barrier_wait(&w.bar);
     return r;
 }
 
-inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned delta)
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, unsigned delta)
 {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
     cta_emu::warp_state& w = cta_emu::my_warp();
     const unsigned lane = cta_emu::my_lane();
-    w.slot[lane] = v;
+    w.slot[lane] = (uint64_t) v;
     pthread_barrier_wait(&w.bar);
-    const uint32_t r = lane >= delta ? w.slot[lane - delta] : v;
+    const T r = lane >= delta ? (T) w.slot[lane - delta] : v;
     pthread_barrier_wait(&w.bar);
     return r;
 }
@@ -117,7 +146,7 @@ inline unsigned __match_any_sync(unsigned, uint32_t v)
     pthread_barrier_wait(&w.bar);
     unsigned m = 0;
     for (unsigned i = 0; i < 32; i++)
-        if (w.slot[i] == v) m |= 1u << i;
+        if (w.slot[i] == (uint64_t) v) m |= 1u << i;
     pthread_barrier_wait(&w.bar);
     return m;
 }
