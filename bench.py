@@ -615,15 +615,8 @@ def run_ours(args):
     te = [float(x) for x in te.tolist()]          # host numbers from here on: nothing below may need the device to print the line
     e2e_value = world * n / (te[0] * 1e-3) / 1e9
 
-    secondary = None
-    if not args.no_secondary:
-        torch.cuda.empty_cache()
-        # the headline line must survive a failure in the secondary rows (at N > 1 every rank takes part in their collectives,
-        # so a failure is agreed on before anyone moves on)
-        try:
-            secondary = secondary_metrics(lib, vlib, dev) if world == 1 else secondary_metrics_multi(lib, vlib, dev, sorter, rank, world)
-        except Exception as exc:  # noqa: BLE001
-            secondary = {"error": f"{type(exc).__name__}: {exc}"}
+    # ---- the line: everything it needs is a host value from here on, so it can be printed whatever the secondary rows do
+    make_line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
         pass_avg_ms = sum(pass_ms) / len(pass_ms)
@@ -645,33 +638,63 @@ def run_ours(args):
         passes = 4
         launches_single = 2 + 2 * passes                                   # histogram, offsets, 4 passes + their (idle) redo kernels
         launches_multi = 4 + 2 + 1 + args.rounds * (1 + 3 + 6) + 2         # hist, publish, offsets, plan, partition + redo, wait, per round: transfer + wait + segment histograms + scan + 3 passes + 3 redos, compact, done
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic",
-            "config": config_object(args.log2n),
-            "details": {"variant": variant_name,
-                        "ranking_check_failures": violation,
-                        "parallelism": "1 GPU" if world == 1 else
-                        f"one global sort of {world}x2^{args.log2n} pairs: device plan, local partition by the top digit, {args.rounds} rounds of "
-                        "NVLink peer-store transfers overlapped with segmented 3-pass onesweep of what has arrived (no NCCL on the data path)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                         "traffic_source": traffic, "kernel": pass_kernel, "peak_source": peak_src,
-                         "kernel_ms": pass_avg_ms, "histogram_ms": sum(hist_ms) / len(hist_ms),
-                         "whole_sort_frac": BYTES_PER_PAIR_SORT * n / (ms_max * 1e-3) / 1e9 / peak},
-            "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": int(te[2]),
-                    "ms_per_step": te[0], "steps": e2e_steps, "issue": e2e_note,
-                    "single_call_ms": te[1], "single_call_value": world * n / (te[1] * 1e-3) / 1e9},
-            "gpu_launches": (launches_single if world == 1 else launches_multi) * args.steps,
-            "verification": "sortedness + stability + pair integrity" if world == 1 else
-                            "2^22/rank global sort == oracle.sort_pairs; timed output: all-reduced pair-multiset checksum, per-shard sortedness and stability, cross-rank boundary order",
-            "phases_rank0_last_step": phases,
-            "secondary": secondary,
-            "clocks": clocks.summary(),
-        }
-        print(json.dumps(line), flush=True)
+        clock_summary = clocks.summary()
+
+        def make_line(secondary):
+            return {
+                "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32", "data": "synthetic",
+                "config": config_object(args.log2n),
+                "details": {"variant": variant_name,
+                            "ranking_check_failures": violation,
+                            "parallelism": "1 GPU" if world == 1 else
+                            f"one global sort of {world}x2^{args.log2n} pairs: device plan, local partition by the top digit, {args.rounds} rounds of "
+                            "NVLink peer-store transfers overlapped with segmented 3-pass onesweep of what has arrived (no NCCL on the data path)"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                             "traffic_source": traffic, "kernel": pass_kernel, "peak_source": peak_src,
+                             "kernel_ms": pass_avg_ms, "histogram_ms": sum(hist_ms) / len(hist_ms),
+                             "whole_sort_frac": BYTES_PER_PAIR_SORT * n / (ms_max * 1e-3) / 1e9 / peak},
+                "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": int(te[2]),
+                        "ms_per_step": te[0], "steps": e2e_steps, "issue": e2e_note,
+                        "single_call_ms": te[1], "single_call_value": world * n / (te[1] * 1e-3) / 1e9},
+                "gpu_launches": (launches_single if world == 1 else launches_multi) * args.steps,
+                "verification": "sortedness + stability + pair integrity" if world == 1 else
+                                "2^22/rank global sort == oracle.sort_pairs; timed output: all-reduced pair-multiset checksum, per-shard sortedness and stability, cross-rank boundary order",
+                "phases_rank0_last_step": phases,
+                "secondary": secondary,
+                "clocks": clock_summary,
+            }
+
+    # ---- secondary rows (the other BASELINE configs).  They come after the headline has been measured and must not be able to
+    # lose it: an exception becomes an "error" entry, and a watchdog on every rank prints the line without them and ends the
+    # process if they have not finished in time (a rank that failed alone would leave the others waiting in a collective)
+    secondary = None
+    if not args.no_secondary:
+        finished = threading.Event()
+
+        def bail():
+            if finished.is_set():
+                return
+            if rank == 0:
+                print(json.dumps(make_line({"error": f"the secondary rows did not finish within {args.secondary_timeout} s and were abandoned; "
+                                                     "every other entry of this line was measured before they started"})), flush=True)
+            os._exit(0)
+
+        watchdog = threading.Timer(args.secondary_timeout, bail)
+        watchdog.daemon = True
+        watchdog.start()
+        torch.cuda.empty_cache()
+        try:
+            secondary = secondary_metrics(lib, vlib, dev) if world == 1 else secondary_metrics_multi(lib, vlib, dev, sorter, rank, world)
+        except Exception as exc:  # noqa: BLE001
+            secondary = {"error": f"{type(exc).__name__}: {exc}"}
+        finished.set()
+        watchdog.cancel()
+    if rank == 0:
+        print(json.dumps(make_line(secondary)), flush=True)
     lib.vrenb200_sort_profile_destroy(prof)
     if world > 1:
         sorter.close()
@@ -782,6 +805,7 @@ def main():
                          "(measured: profiles/r2g_bench_n2_tma.log, r2j_bench_n4_exclusive.log, r2h_bench_n8_tma.log)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--secondary-timeout", type=float, default=300.0, help="seconds the secondary rows may take before the line is printed without them")
     args = ap.parse_args()
     if args.rounds is None:
         args.rounds = 2 if int(os.environ.get("WORLD_SIZE", "1")) == 2 else 4
