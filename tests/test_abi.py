@@ -81,6 +81,18 @@ def test_facade_headers_compile(built):
     assert exe.exists()
 
 
+def test_sharded_sort_cxx_host_builds(handle):
+    """the C++ host of INTEGRATION.md's multi-GPU sketch (tests/cpp/sharded_sort_host.cpp) compiles and links against the
+    C ABI alone; without a device it must fail loudly, not fall back to anything"""
+    exe = build.build_sharded_sort_host(force=True)
+    assert exe.exists()
+    import torch
+
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(exe), "2", "1000"], capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0 and "FAIL" in r.stdout
+
+
 @pytest.mark.gpu
 def test_facade_reference_style_tests(vren):
     exe = build.build_facade_test()

@@ -51,3 +51,17 @@ def test_sharded_sort_emulated_ranking_modes(vren, ranking):
     """ballot-match kernels, the repeat passes of the verified ranking (segmented form included) and ticket tile ids"""
     run(2, 2, "uniform", [(1 << 21) + 3, 1 << 21], ranking=ranking)
     run(3, 1, "below_2p24", [40000, 50000, 60000], ranking=ranking)
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first hardware run; the same library calls are covered from Python above")
+@pytest.mark.parametrize("world,n,rounds", [(2, 300001, 2), (4, 1 << 21, 4)])
+def test_sharded_sort_from_a_cxx_host(vren, world, n, rounds):
+    """the multi-GPU sort driven by a C++ program through the C ABI alone (tests/cpp/sharded_sort_host.cpp — INTEGRATION.md's
+    sketch made real): one GPU per rank when the box has enough of them, all ranks on device 0 otherwise"""
+    from vren_b200 import build
+
+    exe = build.build_sharded_sort_host()
+    r = subprocess.run([str(exe), str(world), str(n), str(rounds)], capture_output=True, text=True, timeout=180,
+                       env=dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32"))
+    sys.stdout.write(r.stdout[-1500:])
+    assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -105,6 +105,24 @@ def build_facade_test(force: bool = False) -> Path:
     return FACADE_TEST
 
 
+SHARDED_HOST = ROOT / "build" / "sharded_sort_host"
+
+
+def build_sharded_sort_host(force: bool = False) -> Path:
+    """tests/cpp/sharded_sort_host.cpp: a C++ host driving the multi-GPU sort through the C ABI alone (INTEGRATION.md's sketch)"""
+    src = ROOT / "tests" / "cpp" / "sharded_sort_host.cpp"
+    deps = [src, LIB] + sorted((ROOT / "include").glob("*.h"))
+    if not force and _newer(SHARDED_HOST, deps):
+        return SHARDED_HOST
+    SHARDED_HOST.parent.mkdir(parents=True, exist_ok=True)
+    cuda_home = Path(_nvcc()).resolve().parent.parent
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", f"-I{ROOT / 'include'}", f"-I{cuda_home / 'include'}", str(src), "-o", str(SHARDED_HOST),
+           f"-L{LIB.parent}", "-lvrenb200", f"-L{cuda_home / 'lib64'}", "-lcudart", f"-Wl,-rpath,{LIB.parent}",
+           f"-Wl,-rpath,{cuda_home / 'lib64'}"]
+    subprocess.run(cmd, check=True)
+    return SHARDED_HOST
+
+
 def build_reference_extract(force: bool = False):
     """oracle/_ref: the few reference functions that compile standalone (see oracle/ref_extract.py)."""
     script = ORACLE_DIR / "ref_extract.py"
