@@ -50,24 +50,39 @@ static thread_local cta_state* cta = nullptr;
 inline warp_state& my_warp() { return cta->warps[threadIdx.x >> 5]; }
 inline unsigned my_lane() { return threadIdx.x & 31u; }
 
+// threads start behind a gate, so that a host that cannot create all of them (thread limit of a container) is reported
+// instead of leaving the ones that did start waiting at their first barrier
+struct start_gate
+{
+    pthread_mutex_t mutex = PTHREAD_MUTEX_INITIALIZER;
+    pthread_cond_t cond = PTHREAD_COND_INITIALIZER;
+    int state = 0;      // 0 wait, 1 run the body, 2 give up
+};
+
 struct thread_arg
 {
     cta_state* cta;
     unsigned tid;
     const std::function<void()>* body;
+    start_gate* gate;
 };
 
 inline void* thread_main(void* p)
 {
     thread_arg* a = static_cast<thread_arg*>(p);
+    pthread_mutex_lock(&a->gate->mutex);
+    while (a->gate->state == 0) pthread_cond_wait(&a->gate->cond, &a->gate->mutex);
+    const int state = a->gate->state;
+    pthread_mutex_unlock(&a->gate->mutex);
+    if (state != 1) return nullptr;
     threadIdx.x = a->tid;
     cta = a->cta;
     (*a->body)();
     return nullptr;
 }
 
-// runs `body` once per thread of a CTA of `threads` threads (a multiple of 32)
-inline void run_cta(unsigned threads, const std::function<void()>& body)
+// runs `body` once per thread of a CTA of `threads` threads (a multiple of 32); false: the host could not create the threads
+inline bool run_cta(unsigned threads, const std::function<void()>& body)
 {
     cta_state st;
     st.warps.resize(threads / 32);
@@ -75,22 +90,26 @@ inline void run_cta(unsigned threads, const std::function<void()>& body)
     for (auto& w : st.warps) pthread_barrier_init(&w.bar, nullptr, 32);
     std::vector<pthread_t> ids(threads);
     std::vector<thread_arg> args(threads);
+    start_gate gate;
     pthread_attr_t attr;
     pthread_attr_init(&attr);
     pthread_attr_setstacksize(&attr, 512 * 1024);
-    for (unsigned t = 0; t < threads; t++)
+    unsigned created = 0;
+    for (; created < threads; created++)
     {
-        args[t] = thread_arg{&st, t, &body};
-        if (pthread_create(&ids[t], &attr, thread_main, &args[t]) != 0)
-        {
-            std::fprintf(stderr, "cta_emulator: pthread_create failed at thread %u\n", t);
-            std::exit(2);
-        }
+        args[created] = thread_arg{&st, created, &body, &gate};
+        if (pthread_create(&ids[created], &attr, thread_main, &args[created]) != 0) break;
     }
-    for (unsigned t = 0; t < threads; t++) pthread_join(ids[t], nullptr);
+    pthread_mutex_lock(&gate.mutex);
+    gate.state = created == threads ? 1 : 2;
+    pthread_cond_broadcast(&gate.cond);
+    pthread_mutex_unlock(&gate.mutex);
+    for (unsigned t = 0; t < created; t++) pthread_join(ids[t], nullptr);
     pthread_attr_destroy(&attr);
     pthread_barrier_destroy(&st.bar);
     for (auto& w : st.warps) pthread_barrier_destroy(&w.bar);
+    if (created != threads) std::fprintf(stderr, "cta_emulator: this host allows only %u of the %u threads of the CTA\n", created, threads);
+    return created == threads;
 }
 
 } // namespace cta_emu

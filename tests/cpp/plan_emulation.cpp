@@ -46,7 +46,7 @@ extern "C" int emu_plan(const uint32_t* hist_all, uint32_t world, uint32_t rank,
     seg_plan* pl = plan.get();
     xfer_plan* x = xp.get();
     uint32_t* st = status;
-    cta_emu::run_cta(kRadix, [=]() { plan_body(h, c, sp, pl, x, tile_seg, st); });
+    if (!cta_emu::run_cta(kRadix, [=]() { plan_body(h, c, sp, pl, x, tile_seg, st); })) return 2;
     scalars[0] = pl->pstar; scalars[1] = pl->error; scalars[2] = pl->num_tiles; scalars[3] = pl->out_count;
     scalars[4] = pl->digit_lo; scalars[5] = pl->digit_hi; scalars[6] = status[0]; scalars[7] = status[1];
     for (int d = 0; d < kRadix; d++)

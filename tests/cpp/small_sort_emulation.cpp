@@ -43,7 +43,7 @@ static bool run_case(uint32_t n, int pattern, uint32_t seed)
     unsigned char* raw = reinterpret_cast<unsigned char*>(smem.data());
     uint32_t* pk = gk.data() + 1;
     uint32_t* pv = HV ? gv.data() + 1 : nullptr;
-    cta_emu::run_cta(kSmallSortThreads, [=]() { single_cta_sort_body<HV>(raw, pk, pv, n, 0, 4); });
+    if (!cta_emu::run_cta(kSmallSortThreads, [=]() { single_cta_sort_body<HV>(raw, pk, pv, n, 0, 4); })) std::exit(3);
     bool ok = gk[0] == 0xDEADBEEFu && gk[n + 1] == 0xDEADBEEFu && gv[0] == 0xDEADBEEFu && gv[n + 1] == 0xDEADBEEFu;
     ok = ok && std::memcmp(pk, want_k.data(), n * 4) == 0;
     if (HV) ok = ok && std::memcmp(gv.data() + 1, want_v.data(), n * 4) == 0;

@@ -41,6 +41,8 @@ def device_plan(lib, hists, rank, key_digits, tile, rounds, cap_tiles, round_bou
            "round_tile": np.zeros(rounds + 1, np.uint32), "tile_seg": np.full(cap_tiles + 1, 0xFFFF, np.uint16), "part": np.zeros(256, np.uint32)}
     rc = lib.emu_plan(np.ascontiguousarray(hists, np.uint32), world, rank, key_digits, tile, rounds, cap_tiles, round_bound,
                       out["scalars"], out["seg"], out["xfer"], out["cum_pairs"], out["round_digit"], out["round_tile"], out["tile_seg"], out["part"])
+    if rc == 2:
+        pytest.skip("this host cannot run the 256 threads of the emulated CTA")
     assert rc == 0
     return out
 

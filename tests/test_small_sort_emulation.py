@@ -29,6 +29,8 @@ def build(name, src=SRC, tsan=False):
 
 def run(exe, with_values, sizes):
     r = subprocess.run([str(exe), str(int(with_values))] + [str(n) for n in sizes], capture_output=True, text=True, timeout=600)
+    if r.returncode == 3 and "cta_emulator: this host allows only" in r.stderr:
+        pytest.skip("this host cannot run the 1024 threads of the emulated CTA")
     return r.returncode, r.stdout + r.stderr
 
 
