@@ -609,6 +609,53 @@ def run_ours(args):
         assert bool((hkn[1:] >= hkn[:-1]).all()), "bench e2e: shard not sorted"
         d2h_bytes = 8 * m
         e2e_note = "sharded sort with host shards: H2D of the rank's shard, collective sort, D2H of the rank's sorted shard"
+        e2e_serial_ms = e2e_step_ms
+        # the same steps with the upload of step i+1 on a second stream and a second input buffer, so that it overlaps the
+        # download of step i (PCIe is full duplex; the N = 1 leg does the same with two lanes).  Added after the round's GPU time
+        # was spent: if anything goes wrong here the serial number above stands
+        try:
+            up = torch.cuda.Stream(device=dev)
+            main_stream = torch.cuda.current_stream()
+            bufs = [(dk, dv), (torch.empty_like(keys0), torch.empty_like(vals0))]
+            uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+            consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+            def e2e_pipelined(count):
+                for i in range(count):
+                    bk, bv = bufs[i % 2]
+                    with torch.cuda.stream(up):
+                        if i >= 2:
+                            up.wait_event(consumed[i % 2])      # the sort that read this buffer two steps ago has finished
+                        bk.copy_(hk_in, non_blocking=True)
+                        bv.copy_(hv_in, non_blocking=True)
+                        uploaded[i % 2].record(up)
+                    main_stream.wait_event(uploaded[i % 2])
+                    sorter.sort(bk, bv)
+                    consumed[i % 2].record(main_stream)
+                    hk_out[:m].copy_(sorter.out_keys[:m], non_blocking=True)    # on the sort's stream: the next sort starts after it
+                    hv_out[:m].copy_(sorter.out_vals[:m], non_blocking=True)
+
+            up.wait_stream(main_stream)
+            e2e_pipelined(2); barrier()
+            hk_out.zero_()
+            t0 = time.perf_counter()
+            e2e_pipelined(e2e_steps)
+            torch.cuda.synchronize()
+            piped_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+            hkn = hk_out[:m].numpy().view("uint32")
+            piped_ok = bool((hkn[1:] >= hkn[:-1]).all()) and bool(hkn.any())
+        except Exception as exc:  # noqa: BLE001
+            piped_ms, piped_ok = None, False
+            e2e_note += f" (pipelined form failed: {type(exc).__name__}: {exc})"
+        # every rank must take the same branch: agree on the outcome
+        agree = torch.tensor([1.0 if piped_ok else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        worst = torch.tensor([piped_ms if piped_ok else 0.0, e2e_serial_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        if float(agree[0].item()) == 1.0 and float(worst[0].item()) < float(worst[1].item()):
+            e2e_step_ms = piped_ms
+            e2e_note = ("sharded sort with host shards, steps pipelined: the H2D of step i+1 (second stream, second input buffer) overlaps "
+                        f"the D2H of step i; one step after the other: {e2e_serial_ms:.1f} ms on this rank")
     te = torch.tensor([e2e_step_ms, single_ms, float(d2h_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
