@@ -681,6 +681,14 @@ def run_ours(args):
                 v, sec = cpu_sort_sample(args.log2n - 2, threads)
                 cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                        "sample": f"std::stable_sort by key of 2^{args.log2n - 2} pairs (host memory too small for the whole step), {threads} threads, {sec:.1f} s"}
+        if cpu is not None:
+            # SURVEY 8d asks for the per-core figure beside the all-cores one: std::stable_sort on ONE thread (as vren_test runs its
+            # check), on a 2^24-pair sample so that it takes a couple of seconds (n log n: the full step is ~15 % slower per pair)
+            try:
+                v1, sec1 = cpu_sort_sample(min(args.log2n, 24), 1)
+                cpu["single_thread"] = {"value": v1, "unit": UNIT, "cores": 1, "sample": f"2^{min(args.log2n, 24)} pairs, {sec1:.1f} s"}
+            except Exception as exc:  # noqa: BLE001
+                cpu["single_thread"] = {"error": f"{type(exc).__name__}: {exc}"}
         traffic = ncu_traffic(pass_kernel, args.log2n)
         passes = 4
         launches_single = 2 + 2 * passes                                   # histogram, offsets, 4 passes + their (idle) redo kernels
