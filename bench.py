@@ -177,7 +177,7 @@ def secondary_metrics(lib, vlib, dev):
     out = {}
     stream = torch.cuda.current_stream().cuda_stream
 
-    def timed(fn, iters=10):
+    def timed(fn, iters=20):       # >= 20 iterations after 3 warm-ups, median
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
