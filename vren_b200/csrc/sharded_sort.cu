@@ -366,14 +366,24 @@ using namespace vrenb200;
 
 struct vrenb200_sharded_sort
 {
+    // releases whatever create() has made so far (null handles are skipped): used by its error paths and by destroy()
+    void release()
+    {
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (sort_stream) cudaStreamDestroy(sort_stream);
+        for (cudaEvent_t* e : {&ev_start, &ev_part, &ev_copy, &ev_sort})
+            if (*e) cudaEventDestroy(*e);
+        copy_stream = sort_stream = nullptr;
+        ev_start = ev_part = ev_copy = ev_sort = nullptr;
+    }
     shard_params sp;
     peer_table peers;
     uint32_t max_n, capacity;
     sort_options opt;
     const sort_variant* var_seg;
     uint32_t xfer_ctas, xfer_stages;
-    cudaStream_t copy_stream, sort_stream;
-    cudaEvent_t ev_start, ev_part, ev_copy, ev_sort;
+    cudaStream_t copy_stream = nullptr, sort_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_part = nullptr, ev_copy = nullptr, ev_sort = nullptr;
     int device;
     // carved from the caller's local scratch
     uint32_t *part_keys, *part_vals, *alt_keys, *alt_vals, *out_keys, *out_vals;
@@ -480,6 +490,7 @@ extern "C" int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_
         cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_part) != cudaSuccess ||
         cudaEventCreate(&c->ev_copy) != cudaSuccess || cudaEventCreate(&c->ev_sort) != cudaSuccess)
     {
+        c->release();
         delete c;
         return VRENB200_ECUDA;
     }
@@ -499,6 +510,7 @@ extern "C" int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_
         if (st == VRENB200_OK) st = check_cuda(cudaFuncSetAttribute(segment_histograms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSegHistSmem));
         if (st != VRENB200_OK)
         {
+            c->release();
             delete c;
             return st;
         }
@@ -507,6 +519,7 @@ extern "C" int vrenb200_sharded_sort_create(vrenb200_sharded_sort** out, uint32_
     // rank has returned from create before any rank sorts (one barrier)
     if (cudaMemset(c->peers.hdr[rank], 0, sizeof(sym_header)) != cudaSuccess || cudaMemset(c->xp, 0, sizeof(xfer_plan)) != cudaSuccess)
     {
+        c->release();
         delete c;
         return VRENB200_ECUDA;
     }
@@ -519,12 +532,7 @@ extern "C" void vrenb200_sharded_sort_destroy(vrenb200_sharded_sort* c)
     if (c == nullptr) return;
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamSynchronize(c->sort_stream);
-    cudaStreamDestroy(c->copy_stream);
-    cudaStreamDestroy(c->sort_stream);
-    cudaEventDestroy(c->ev_start);
-    cudaEventDestroy(c->ev_part);
-    cudaEventDestroy(c->ev_copy);
-    cudaEventDestroy(c->ev_sort);
+    c->release();
     delete c;
 }
 
