@@ -208,3 +208,22 @@ def test_exchange_plan_reports_what_does_not_fit():
     assert vdist.exchange_plan(hists, 4, 64, 1, 40, 40)["error"] == 0
     assert vdist.exchange_plan(hists, 4, 64, 1, 30, 30)["error"] & 1
     assert vdist.exchange_plan(hists, 4, 64, 2, 40, 20)["error"] & 2
+
+
+def test_required_capacity_is_the_smallest_that_fits():
+    """the documented overflow policy: a skewed input (two values of the top digit, 90 % in one) does not fit the default capacity — the plan
+    says so — and fits exactly from vdist.required_capacity on"""
+    rng = np.random.Generator(np.random.PCG64(5))
+    world, n, tile = 4, 2_000_000, 4096
+    keys = [(((rng.random(n) < 0.1).astype(np.uint64) << np.uint64(30)) | rng.integers(0, 1 << 12, size=n, dtype=np.uint64)).astype(np.uint32)
+            for _ in range(world)]                           # 90 % of all pairs share one value of the top digit
+    hists = np.stack([_digit_hists(k) for k in keys])
+    default = vdist.default_capacity(n, world)
+    assert vdist.exchange_plan(hists, 4, tile, 1, default // tile, default // tile)["error"] & 1
+    need = vdist.required_capacity(hists, 4, tile)
+    assert need % tile == 0 and need > default
+    assert vdist.exchange_plan(hists, 4, tile, 1, need // tile, need // tile)["error"] == 0
+    assert vdist.exchange_plan(hists, 4, tile, 1, need // tile - 1, need // tile)["error"] & 1
+    # balanced keys: the requirement stays below the default (25 % slack + a partial tile per segment)
+    uni = np.stack([_digit_hists(rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)) for _ in range(world)])
+    assert vdist.required_capacity(uni, 4, 12288) <= vdist.default_capacity(n, world)

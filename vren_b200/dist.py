@@ -192,6 +192,23 @@ def exchange_plan(hists, key_digits: int, tile: int, rounds: int, cap_tiles: int
             "dst_off": dst_off, "round_digit": round_digit, "out_count": out_count}
 
 
+def required_capacity(hists, key_digits: int = 4, tile: int = 12288) -> int:
+    """The overflow policy of the multi-GPU sort, host side: a plan that does not fit is REPORTED (status word, ShardedSort.result()
+    raises), never truncated; the caller then sizes a new context with this function.  hists: [G, 4, 256] digit counts of every
+    rank's shard (vrenb200_radix_digit_histograms, all-gathered — or what the ranks already know about their keys).  Returns the
+    smallest receive capacity, in pairs, with which the device plan fits on every rank: a value of the partition digit is the
+    unit of ownership (it cannot be split), so a hot value needs room for all of its pairs on its owner."""
+    import numpy as np
+
+    h = np.asarray(hists, dtype=np.int64)
+    world = h.shape[0]
+    big = 1 << 40
+    plan = exchange_plan(h, key_digits, tile, 1, big, big)
+    tiles = (plan["seg_len"] + tile - 1) // tile
+    b = plan["bounds"]
+    return int(max(int(tiles[b[r]:b[r + 1]].sum()) for r in range(world)) * tile)
+
+
 def default_capacity(max_n: int, world: int, rounds: int = 1) -> int:
     """receive capacity for balanced keys: the rank's share with 25 % slack plus a partial tile per segment (256 segments
     of up to 12288 pairs in all) — see include/vrenb200.h"""
@@ -279,7 +296,8 @@ class ShardedSort:
         if st[0] != 0:
             raise RuntimeError(f"sharded sort: the exchange plan does not fit (status {int(st[0])}: "
                                f"{'receive capacity exceeded' if st[0] & 1 else 'a round exceeds its launch bound'}); "
-                               f"capacity {self.capacity}, rounds {self.rounds} — retry with rounds=1 and/or a larger capacity")
+                               f"capacity {self.capacity}, rounds {self.rounds} — retry with rounds=1 and/or a larger capacity "
+                               "(vren_b200.dist.required_capacity sizes it from the ranks' digit histograms)")
         n = int(st[1])
         return self.out_keys[:n], self.out_vals[:n]
 
