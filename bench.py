@@ -162,6 +162,59 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_secondary_baselines(small: bool = False):
+    """SURVEY 8d "CPU baseline beside it" for the secondary rows: the oracle's restatements of the reference's CPU checks (the
+    code vren_test compares the GPU results with), ONE host thread each as in vren_test, on bounded samples of the configurations
+    the GPU rows use.  Needs no GPU.  small=True: tiny sizes (the CPU test of this function)."""
+    import math
+
+    import numpy as np
+
+    import oracle
+    from vren_b200 import synthetic
+
+    def once(fn):
+        t0 = time.perf_counter()
+        r = fn()
+        return time.perf_counter() - t0, r
+
+    out = {"threads": 1, "kind": "port (oracle/), one thread as in vren_test"}
+    rng = np.random.Generator(np.random.PCG64(77))
+    n = 1 << (14 if small else 26)
+    x = rng.integers(0, 100, size=n, dtype=np.uint64).astype(np.uint32)
+    sec, _ = once(lambda: oracle.exclusive_scan(x))
+    out["scan_u32"] = {"sample": f"2^{int(math.log2(n))} u32", "ms": sec * 1e3, "GB/s": 8 * n / sec / 1e9, "what": "std::exclusive_scan (blelloch_scan.cpp:122-176 check)"}
+    sec, _ = once(lambda: oracle.reduce(x, n, "u32", "add"))
+    out["reduce_u32_add_tree"] = {"sample": f"2^{int(math.log2(n))} u32", "ms": sec * 1e3, "GB/s": 8 * n / sec / 1e9, "what": "run_cpu_reduce, whole padded tree (reduce.cpp:72-98)"}
+    n = 1 << (14 if small else 24)
+    k = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+    sec, _ = once(lambda: oracle.sort_keys(k))
+    out["radix_sort_keys"] = {"sample": f"2^{int(math.log2(n))} keys", "ms": sec * 1e3, "Gkeys/s": n / sec / 1e9, "what": "std::sort (radix_sort.cpp:88 check)"}
+    pairs = np.stack([rng.integers(0, 1 << 16, size=n, dtype=np.uint64).astype(np.uint32), np.arange(n, dtype=np.uint32)], axis=1)
+    sec, _ = once(lambda: oracle.bucket_sort(pairs))
+    out["bucket_sort_uvec2"] = {"sample": f"2^{int(math.log2(n))} pairs", "ms": sec * 1e3, "Gpairs/s": n / sec / 1e9, "what": "stable counting sort by the 16-bit key + END offsets"}
+    leaves = 1 << (10 if small else 20)
+    length = int(oracle.load().oracle_calc_bvh_buffer_length(leaves))
+    nodes = np.zeros(length, dtype=oracle.BVH_NODE)
+    nodes["min"][:leaves] = rng.random((leaves, 3), dtype=np.float32) * 100
+    nodes["max"][:leaves] = nodes["min"][:leaves] + rng.random((leaves, 3), dtype=np.float32) * 10
+    nodes["next"][:leaves] = 0xFFFFFFFF
+    sec, _ = once(lambda: oracle.build_bvh(nodes, leaves))
+    out["build_bvh"] = {"sample": f"{leaves} leaves (the GPU row's size)" if not small else f"{leaves} leaves", "ms": sec * 1e3, "what": "build_bvh.comp:32-55 level by level"}
+    w, h, L = (3840, 2160, 65536) if not small else (160, 96, 300)
+    depth = synthetic.depth_buffer(w, h, seed=2024)
+    pos, lights = synthetic.point_lights(L, seed=2025, aspect=w / h, intensity=(1.0, 1.0))
+    view = synthetic.view_matrix(0.0, 0.0, (0, 0, 0))
+    cam = oracle.default_camera(w, h)
+    s6, (vp, nd, pr) = once(lambda: oracle.construct_point_light_bvh(pos, lights, view))
+    s7, (keys, _) = once(lambda: oracle.find_unique_clusters(depth, None, cam))
+    s8, (_, _, _, total) = once(lambda: oracle.assign_lights(w, h, cam, keys, 1 << 17, nd, L, pr, vp, 1 << 23))
+    out["light_assign"] = {"sample": f"one {w}x{h} view, {L} lights (the GPU row's size)" if not small else f"one {w}x{h} view, {L} lights",
+                           "ms_per_view": (s6 + s7 + s8) * 1e3, "ms_light_bvh": s6 * 1e3, "ms_cluster_keys": s7 * 1e3, "ms_assign_lights": s8 * 1e3,
+                           "clusters": int(keys.size), "assigned_lights": int(total)}
+    return out
+
+
 def secondary_metrics(lib, vlib, dev):
     """the other BASELINE.json configs, each timed with CUDA events after 3 warm-ups (inputs larger than L2):
     C2 scan + reduce over 2^28 u32, C4 BuildBVH over 2^20 leaves, C5 clustered light assignment at 4K / 65 536 lights"""
@@ -689,6 +742,12 @@ def run_ours(args):
                 cpu["single_thread"] = {"value": v1, "unit": UNIT, "cores": 1, "sample": f"2^{min(args.log2n, 24)} pairs, {sec1:.1f} s"}
             except Exception as exc:  # noqa: BLE001
                 cpu["single_thread"] = {"error": f"{type(exc).__name__}: {exc}"}
+        secondary_cpu = None
+        if world == 1 and not args.no_cpu_baseline and not args.no_secondary:
+            try:
+                secondary_cpu = cpu_secondary_baselines()
+            except Exception as exc:  # noqa: BLE001
+                secondary_cpu = {"error": f"{type(exc).__name__}: {exc}"}
         traffic = ncu_traffic(pass_kernel, args.log2n)
         passes = 4
         launches_single = 2 + 2 * passes                                   # histogram, offsets, 4 passes + their (idle) redo kernels
@@ -720,6 +779,7 @@ def run_ours(args):
                                 "2^22/rank global sort == oracle.sort_pairs; timed output: all-reduced pair-multiset checksum, per-shard sortedness and stability, cross-rank boundary order",
                 "phases_rank0_last_step": phases,
                 "secondary": secondary,
+                "secondary_cpu_baseline": secondary_cpu,
                 "clocks": clock_summary,
             }
 

@@ -48,3 +48,17 @@ def test_gpu_arm_has_no_cpu_fallback():
         return
     r = run(["--steps", "1", "--warmup", "0", "--log2n", "12"])
     assert r.returncode != 0 and "no CUDA device" in (r.stdout + r.stderr)
+
+
+def test_cpu_baselines_of_the_secondary_rows():
+    """SURVEY 8d: the reference's CPU checks timed beside the GPU rows (scan, reduce tree, std::sort, bucket sort, BuildBVH, one view
+    of the light assignment) — the function runs without a GPU, here on tiny sizes"""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    r = bench.cpu_secondary_baselines(small=True)
+    for row in ("scan_u32", "reduce_u32_add_tree", "radix_sort_keys", "bucket_sort_uvec2", "build_bvh"):
+        assert r[row]["ms"] > 0 and "sample" in r[row]
+    la = r["light_assign"]
+    assert la["ms_per_view"] > 0 and la["clusters"] > 0 and la["assigned_lights"] > 0
+    json.dumps(r)
