@@ -1,4 +1,4 @@
-// vren::depth_buffer_pyramid / vren::depth_buffer_reductor facade — vren/vren/pipeline/depth_buffer_pyramid.hpp:20-121.
+// vren::depth_buffer_pyramid / vren::depth_buffer_reductor facade — vren/vren/pipeline/depth_buffer_pyramid.hpp:19-115.
 // The Vulkan mip-mapped R32F image becomes one flat float buffer with the levels back to back.
 #pragma once
 

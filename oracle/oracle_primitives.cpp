@@ -221,8 +221,8 @@ void oracle_blelloch_scan_u32(uint32_t* buf, uint32_t n, uint32_t blocks)
 // the reference test's check: std::sort (vren_test/.../radix_sort.cpp:88)
 void oracle_sort_keys(uint32_t* keys, uint32_t n) { std::sort(keys, keys + n); }
 
-// literal restatement of the reference algorithm (radix_sort.cpp:171-337; local_count.comp:49-70,
-// global_offset.comp:38-56, reorder.comp:55-113): 8 stable passes of 4 bits, per-workgroup (1024 keys) digit
+// literal restatement of the reference algorithm (radix_sort.cpp:171-337; radix_sort_local_count.comp:49-70,
+// radix_sort_global_offset.comp:38-56, radix_sort_reorder.comp:55-113): 8 stable passes of 4 bits, per-workgroup (1024 keys) digit
 // counts stored digit-major, exclusive scan across workgroups, 16-wide global offsets, stable scatter.
 void oracle_radix_sort_lsd4(uint32_t* keys, uint32_t n)
 {
