@@ -43,7 +43,8 @@ template <typename T> static std::vector<T> download(vren::vk_utils::buffer cons
     return v;
 }
 
-// TEST(reduce, var_length) + type_uint: whole padded tree equals run_cpu_reduce (reduce.cpp:72-98,245-291)
+// TEST(reduce, var_length) + TEST(reduce, type_uint): whole padded tree equals run_cpu_reduce (reduce.cpp:72-98,245-291);
+// TEST(reduce, type_vec4): component-wise vec4 max, in place
 static void test_reduce(vren::context& ctx)
 {
     for (uint32_t length : {1u, 10u, 100u, 1000u, 10000u, 100000u})

@@ -134,3 +134,15 @@ def test_bvh_node_layout_equals_the_reference():
     abi = strip_comments((ROOT / "include" / "vrenb200.h").read_text())
     node = re.search(r"typedef struct vrenb200_bvh_node\s*\{(.*?)\}", abi, flags=re.S).group(1)
     assert re.findall(r"(float|uint32_t)\s+\w+(\[3\])?\s*;", node) == [("float", "[3]"), ("uint32_t", ""), ("float", "[3]"), ("uint32_t", "")]
+
+
+def test_every_reference_test_has_a_facade_counterpart():
+    """vren_test's own test list (TEST(suite, name) in vren_test/vren_test/**) against tests/cpp/facade_test.cpp, which drives the
+    facade the way vren_test drives vren: each of them is named there by the function that restates it"""
+    names = set()
+    for f in (Path("/root/reference") / "vren_test" / "vren_test").rglob("*.cpp"):
+        names.update(re.findall(r"^\s*TEST\((\w+),\s*(\w+)\)", f.read_text(errors="replace"), flags=re.M))
+    assert len(names) >= 9
+    facade = (ROOT / "tests" / "cpp" / "facade_test.cpp").read_text()
+    for suite, name in sorted(names):
+        assert f"TEST({suite}, {name})" in facade, f"TEST({suite}, {name}) has no counterpart in tests/cpp/facade_test.cpp"
