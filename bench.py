@@ -215,7 +215,7 @@ def cpu_secondary_baselines(small: bool = False):
     return out
 
 
-def secondary_metrics(lib, vlib, dev):
+def secondary_metrics(lib, vlib, dev, out=None):
     """the other BASELINE.json configs, each timed with CUDA events after 3 warm-ups (inputs larger than L2):
     C2 scan + reduce over 2^28 u32, C4 BuildBVH over 2^20 leaves, C5 clustered light assignment at 4K / 65 536 lights"""
     import math
@@ -227,7 +227,7 @@ def secondary_metrics(lib, vlib, dev):
     from vren_b200.pipeline import ClusterAndShade
 
     peak, _ = measured_peaks()
-    out = {}
+    out = {} if out is None else out       # filled row by row: the caller's watchdog prints what is there if a later row hangs
     stream = torch.cuda.current_stream().cuda_stream
 
     def timed(fn, iters=20):       # >= 20 iterations after 3 warm-ups, median
@@ -407,6 +407,22 @@ def secondary_metrics(lib, vlib, dev):
         out["radix_sort_single_cta"] = row
     except Exception as exc:  # noqa: BLE001
         out["radix_sort_single_cta"] = {"error": f"{type(exc).__name__}: {exc}"}
+    # ... and the scan's opt-in safe mode (ticket tile ids, vrenb200_exclusive_scan_u32_ex): the chained register-tile kernel at
+    # every size; tests/test_scan_safe_mode.py is its parity check
+    try:
+        n = 1 << 28
+        x = torch.ones(n, dtype=torch.int32, device=dev)
+        y = torch.empty_like(x)
+        sb = lib.vrenb200_scan_scratch_bytes(n)
+        scr = torch.empty(sb, dtype=torch.uint8, device=dev)
+        ms = timed(lambda: vlib.check(lib.vrenb200_exclusive_scan_u32_ex(stream, x.data_ptr(), y.data_ptr(), n, 0, scr.data_ptr(), sb,
+                                                                         vlib.SCAN_TILE_IDS_TICKET), "scan_ex"))
+        ok = bool(torch.equal(y[-4:].cpu(), torch.arange(n - 4, n, dtype=torch.int32))) and int(y[0].item()) == 0
+        out["scan_u32_2p28_safe_mode"] = {"ms": ms if ok else "WRONG RESULT", "GB/s": 8 * n / ms / 1e6, "frac_hbm": 8 * n / ms / 1e6 / peak, "bytes_per_elt": 8,
+                                          "note": "opt-in: ticket tile ids, no assumption about the CTA dispatch order"}
+        del x, y, scr
+    except Exception as exc:  # noqa: BLE001
+        out["scan_u32_2p28_safe_mode"] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
 
 
@@ -789,13 +805,16 @@ def run_ours(args):
     secondary = None
     if not args.no_secondary:
         finished = threading.Event()
+        rows = {}            # filled row by row by secondary_metrics*
 
         def bail():
             if finished.is_set():
                 return
             if rank == 0:
-                print(json.dumps(make_line({"error": f"the secondary rows did not finish within {args.secondary_timeout} s and were abandoned; "
-                                                     "every other entry of this line was measured before they started"})), flush=True)
+                partial = dict(rows)
+                partial["error"] = (f"the secondary rows did not finish within {args.secondary_timeout} s and were abandoned after the rows above; "
+                                    "every other entry of this line was measured before they started")
+                print(json.dumps(make_line(partial)), flush=True)
             os._exit(0)
 
         watchdog = threading.Timer(args.secondary_timeout, bail)
@@ -803,9 +822,10 @@ def run_ours(args):
         watchdog.start()
         torch.cuda.empty_cache()
         try:
-            secondary = secondary_metrics(lib, vlib, dev) if world == 1 else secondary_metrics_multi(lib, vlib, dev, sorter, rank, world)
+            secondary = secondary_metrics(lib, vlib, dev, rows) if world == 1 else secondary_metrics_multi(lib, vlib, dev, sorter, rank, world, rows)
         except Exception as exc:  # noqa: BLE001
-            secondary = {"error": f"{type(exc).__name__}: {exc}"}
+            secondary = dict(rows)
+            secondary["error"] = f"{type(exc).__name__}: {exc} (rows above were measured before the failure)"
         finished.set()
         watchdog.cancel()
     if rank == 0:
@@ -816,7 +836,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def secondary_metrics_multi(lib, vlib, dev, sorter, rank, world):
+def secondary_metrics_multi(lib, vlib, dev, sorter, rank, world, out=None):
     """N > 1: the other sharded paths of SURVEY 8e, device-timed (max over ranks): sharded exclusive scan and reduce over
     2^28 u32 per GPU, sharded bucket sort (16-bit key) of 2^26 pairs per GPU, clustered shading of 8 views at 4K over the ranks"""
     import math
@@ -830,7 +850,7 @@ def secondary_metrics_multi(lib, vlib, dev, sorter, rank, world):
     from vren_b200.pipeline import ViewBatch
 
     peak, _ = measured_peaks()
-    out = {}
+    out = {} if out is None else out
 
     def timed(fn, iters=5):
         ts = []

@@ -80,6 +80,16 @@ int vrenb200_exclusive_scan_u32(vrenb200_stream_t stream, const uint32_t* in, ui
 /* out[i] = base + sum_{k<i} in[k]: local step of the sharded scan */
 int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const uint32_t* in, uint32_t* out, uint32_t n,
                                      uint32_t base, void* scratch, size_t scratch_bytes);
+/* the same with flags.  VRENB200_SCAN_TILE_IDS_TICKET ("safe mode"): tile ids come from an atomic ticket taken when a CTA starts
+ * instead of the block index, so the look-back of the chained scan never waits for a tile whose CTA has not started — no
+ * assumption about the order in which the hardware dispatches CTAs (MPS, time slicing, debuggers).  It uses the chained
+ * register-tile kernel at every size (the faster run-ahead kernel for n >= 2^24 ties its roles to the block index).
+ * VRENB200_SCAN_TILE_IDS=ticket in the environment makes it the default of the process.  Opt-in: written after the round's
+ * GPU time was spent; the kernel text runs on the host CTA emulator (tests/test_scan_emulation.py), first hardware run =
+ * tests/test_scan_safe_mode.py. */
+#define VRENB200_SCAN_TILE_IDS_TICKET 1u
+int vrenb200_exclusive_scan_u32_ex(vrenb200_stream_t stream, const uint32_t* in, uint32_t* out, uint32_t n,
+                                   uint32_t base, void* scratch, size_t scratch_bytes, uint32_t flags);
 /* blelloch_scan::downsweep (blelloch_scan.cpp:57-139): turns `blocks` up-sweep trees of pow2 length n
  * into exclusive scans (+root when clear_last==0), in place */
 int vrenb200_blelloch_downsweep_u32(vrenb200_stream_t stream, uint32_t* buf, uint32_t n, uint32_t blocks,

@@ -1,7 +1,8 @@
 // Host execution of a CUDA kernel BODY, thread for thread: one OS thread per CUDA thread of ONE CTA, __syncthreads() and the
 // warp-synchronous intrinsics built on pthread barriers.  A body written against threadIdx.x, __syncthreads, __syncthreads_count,
-// __syncwarp, __shfl_sync, __shfl_up_sync, __match_any_sync, atomicOr / atomicAdd, __shared__ variables, __popc and __clz (full
-// masks, convergent warps) compiles unchanged with g++
+// __syncwarp, __shfl_sync, __shfl_up_sync, __match_any_sync, __ballot_sync, __reduce_add_sync, atomicOr / atomicAdd, __shared__
+// variables, blockIdx.x (CTAs of a grid run one after the other), __popc, __clz, __ffs (full masks, convergent warps) compiles
+// unchanged with g++
 // when this header is included BEFORE it.  Built with -fsanitize=thread, a missing barrier between two accesses of the same
 // shared word shows up as a data race (pthread barriers are synchronisation ThreadSanitizer understands) — the host-side
 // stand-in for compute-sanitizer's racecheck when no GPU is at hand.
@@ -9,6 +10,7 @@
 #pragma once
 
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 
 #include <cstdio>
@@ -29,6 +31,7 @@
 
 struct emu_uint3 { unsigned x, y, z; };
 static thread_local emu_uint3 threadIdx = {0, 0, 0};
+static thread_local emu_uint3 blockIdx = {0, 0, 0};      // set by run_cta's `block` argument: CTAs of a grid run one after the other
 
 namespace cta_emu {
 
@@ -63,6 +66,7 @@ struct thread_arg
 {
     cta_state* cta;
     unsigned tid;
+    unsigned block;
     const std::function<void()>* body;
     start_gate* gate;
 };
@@ -76,13 +80,14 @@ inline void* thread_main(void* p)
     pthread_mutex_unlock(&a->gate->mutex);
     if (state != 1) return nullptr;
     threadIdx.x = a->tid;
+    blockIdx.x = a->block;
     cta = a->cta;
     (*a->body)();
     return nullptr;
 }
 
 // runs `body` once per thread of a CTA of `threads` threads (a multiple of 32); false: the host could not create the threads
-inline bool run_cta(unsigned threads, const std::function<void()>& body)
+inline bool run_cta(unsigned threads, const std::function<void()>& body, unsigned block = 0)
 {
     cta_state st;
     st.warps.resize(threads / 32);
@@ -97,7 +102,7 @@ inline bool run_cta(unsigned threads, const std::function<void()>& body)
     unsigned created = 0;
     for (; created < threads; created++)
     {
-        args[created] = thread_arg{&st, created, &body, &gate};
+        args[created] = thread_arg{&st, created, block, &body, &gate};
         if (pthread_create(&ids[created], &attr, thread_main, &args[created]) != 0) break;
     }
     pthread_mutex_lock(&gate.mutex);
@@ -170,5 +175,30 @@ inline unsigned __match_any_sync(unsigned, uint32_t v)
     return m;
 }
 
+inline unsigned __ballot_sync(unsigned, int pred)
+{
+    cta_emu::warp_state& w = cta_emu::my_warp();
+    w.slot[cta_emu::my_lane()] = pred ? 1u : 0u;
+    pthread_barrier_wait(&w.bar);
+    unsigned m = 0;
+    for (unsigned i = 0; i < 32; i++)
+        if (w.slot[i]) m |= 1u << i;
+    pthread_barrier_wait(&w.bar);
+    return m;
+}
+
+inline uint32_t __reduce_add_sync(unsigned, uint32_t v)
+{
+    cta_emu::warp_state& w = cta_emu::my_warp();
+    w.slot[cta_emu::my_lane()] = v;
+    pthread_barrier_wait(&w.bar);
+    uint32_t sum = 0;
+    for (unsigned i = 0; i < 32; i++) sum += (uint32_t) w.slot[i];
+    pthread_barrier_wait(&w.bar);
+    return sum;
+}
+
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline void __nanosleep(unsigned) { sched_yield(); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned) x); }

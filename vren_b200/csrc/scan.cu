@@ -10,6 +10,8 @@
 // downsweep(): kept for API parity (radix_sort.cpp:281-289 calls it directly): takes an up-sweep TREE and
 // turns it into the scan, 10 levels per launch in shared memory, top-down.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -17,6 +19,7 @@ namespace vrenb200 {
 
 namespace {
 
+// [[chained-scan-defs-begin]] (this block and the kernel body below are also compiled for the host: tests/test_scan_emulation.py)
 constexpr int kScanVecs = 8;                                        // uint4 per thread
 constexpr uint32_t kScanMinTile = 256 * kScanVecs * 4;              // smallest tile of any variant: sizes the status array
 constexpr uint32_t kWarpChunk = 32 * kScanVecs * 4;                 // 1024 contiguous elements per warp
@@ -26,24 +29,37 @@ constexpr uint64_t kFlagInclusive = 2ull << 32;
 
 struct scan_state
 {
-    uint32_t ticket;      // unused: tile id = block index (CTAs are dispatched in index order, so a tile only waits on
-                          // tiles that already started; saves an L2 atomic round trip before the first load)
+    uint32_t ticket;      // safe mode only (TICKET kernels): next tile id.  By default tile id = block index (CTAs are dispatched
+                          // in index order, so a tile only waits on tiles that already started; saves an L2 atomic round trip)
     uint32_t _pad[63];
     uint64_t status[1];   // [tiles]
 };
+// [[chained-scan-defs-end]]
 
 // THREADS sets the tile (THREADS x 32 elements).  The look-back walk is as long as the number of older tiles still in
 // flight, so for a fixed number of bytes in flight larger tiles mean proportionally fewer L2 round trips per tile.
-template <int THREADS>
+// TICKET (the "safe mode", vrenb200_exclusive_scan_u32_ex): the tile id is the value of an atomic counter taken when the
+// CTA starts instead of the block index, so a tile only ever waits for tiles whose CTAs HAVE started — forward progress of
+// the look-back without the assumption that CTAs are dispatched in index order (MPS, time slicing, debuggers).
+// (The text between the two marker comments is also compiled for the host: tests/test_scan_emulation.py.)
+template <int THREADS, bool TICKET>
 __global__ void __launch_bounds__(THREADS)
 exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_state* state, uint32_t base)
 {
+    // [[chained-scan-body-begin]]
     constexpr int kScanWarps = THREADS / 32;
     constexpr uint32_t kScanTile = THREADS * kScanVecs * 4;
     __shared__ uint32_t s_warp_total[kScanWarps];
     __shared__ uint32_t s_tile_prefix;
 
-    const uint32_t tile = blockIdx.x;
+    uint32_t tile = blockIdx.x;
+    if (TICKET)
+    {
+        __shared__ uint32_t s_ticket;
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&state->ticket, 1u);
+        __syncthreads();
+        tile = s_ticket;
+    }
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t warp_base = (uint64_t) tile * kScanTile + warp * kWarpChunk;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
@@ -161,6 +177,7 @@ exclusive_scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n, scan_st
             if (idx + 3 < n) out[idx + 3] = x[v].w;
         }
     }
+    // [[chained-scan-body-end]]
 }
 
 // ---- staged variant: the tile lives in shared memory, not in registers -------------------------------------------
@@ -684,13 +701,36 @@ extern "C" int vrenb200_exclusive_scan_u32(vrenb200_stream_t stream, const uint3
 extern "C" int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const uint32_t* in, uint32_t* out, uint32_t n,
                                                 uint32_t base, void* scratch, size_t scratch_bytes)
 {
+    // the environment can make the safe mode the default of a process (read once, never written again)
+    static const uint32_t env_flags = []() {
+        const char* e = std::getenv("VRENB200_SCAN_TILE_IDS");
+        return (e != nullptr && !std::strcmp(e, "ticket")) ? (uint32_t) VRENB200_SCAN_TILE_IDS_TICKET : 0u;
+    }();
+    return vrenb200_exclusive_scan_u32_ex(stream, in, out, n, base, scratch, scratch_bytes, env_flags);
+}
+
+extern "C" int vrenb200_exclusive_scan_u32_ex(vrenb200_stream_t stream, const uint32_t* in, uint32_t* out, uint32_t n,
+                                              uint32_t base, void* scratch, size_t scratch_bytes, uint32_t flags)
+{
     if (in == nullptr || out == nullptr) return VRENB200_EINVAL_ARG;
+    if ((flags & ~(uint32_t) VRENB200_SCAN_TILE_IDS_TICKET) != 0) return VRENB200_EINVAL_ARG;
     if (n == 0) return VRENB200_EINVAL_LENGTH;
     const size_t need = vrenb200_scan_scratch_bytes(n);
     if (scratch == nullptr || scratch_bytes < need) return VRENB200_ESCRATCH;
     if ((reinterpret_cast<uintptr_t>(scratch) & 7) != 0) return VRENB200_EALIGN;
     cudaStream_t s = as_stream(stream);
     VRENB200_TRY(check_cuda(cudaMemsetAsync(scratch, 0, need, s)));
+    if (flags & VRENB200_SCAN_TILE_IDS_TICKET)
+    {
+        // safe mode: the chained register-tile kernel with ticket tile ids at every size (the run-ahead kernel's roles are tied
+        // to the block index); the memset above has zeroed the ticket
+        const uint32_t tile = (n >= (1u << 22) ? 1024u : 256u) * kScanVecs * 4;
+        const uint32_t tiles = (uint32_t) (((size_t) n + tile - 1) / tile);
+        scan_state* st = static_cast<scan_state*>(scratch);
+        if (n >= (1u << 22)) exclusive_scan_u32_kernel<1024, true><<<tiles, 1024, 0, s>>>(in, out, n, st, base);
+        else exclusive_scan_u32_kernel<256, true><<<tiles, 256, 0, s>>>(in, out, n, st, base);
+        return check_launch();
+    }
     int threads = kScanVariantThreads[g_scan_variant];
     // default (profiles/r1v_scan_mid_sizes.log): the run-ahead kernel (256 + 256 tiles of distance, L2 residency hints)
     // from 2^24 elements, the register-tile kernel below that (no idle prologue CTAs), with 1024-thread CTAs from 2^22
@@ -735,9 +775,9 @@ extern "C" int vrenb200_exclusive_scan_u32_base(vrenb200_stream_t stream, const 
     const uint32_t tile = (uint32_t) threads * kScanVecs * 4;
     const uint32_t tiles = (uint32_t) (((size_t) n + tile - 1) / tile);
     scan_state* st = static_cast<scan_state*>(scratch);
-    if (threads == 256) exclusive_scan_u32_kernel<256><<<tiles, 256, 0, s>>>(in, out, n, st, base);
-    else if (threads == 512) exclusive_scan_u32_kernel<512><<<tiles, 512, 0, s>>>(in, out, n, st, base);
-    else exclusive_scan_u32_kernel<1024><<<tiles, 1024, 0, s>>>(in, out, n, st, base);
+    if (threads == 256) exclusive_scan_u32_kernel<256, false><<<tiles, 256, 0, s>>>(in, out, n, st, base);
+    else if (threads == 512) exclusive_scan_u32_kernel<512, false><<<tiles, 512, 0, s>>>(in, out, n, st, base);
+    else exclusive_scan_u32_kernel<1024, false><<<tiles, 1024, 0, s>>>(in, out, n, st, base);
     return check_launch();
 }
 

@@ -30,6 +30,7 @@ class VrenError(RuntimeError):
 
 RANKING_AUTO, RANKING_MATCH, RANKING_ATOMIC_VERIFIED, RANKING_ATOMIC_SAMPLED, RANKING_ATOMIC_UNVERIFIED, RANKING_SELFTEST_REDO = range(6)
 TILE_IDS_AUTO, TILE_IDS_BLOCK_INDEX, TILE_IDS_TICKET = range(3)
+SCAN_TILE_IDS_TICKET = 1          # vrenb200_exclusive_scan_u32_ex flag: the scan's safe mode, opt-in
 SORT_VARIANT_SINGLE_CTA = -1      # vrenb200_sort_config::variant: the whole sort in one CTA (n <= 8192), opt-in
 
 
@@ -131,6 +132,7 @@ _LATE_SIGS = [
     ("vrenb200_radix_top_digit_histogram", _i32, (_vp, _vp, _u32, _vp)),
     ("vrenb200_radix_partition_scatter", _i32, (_vp, _vp, _vp, _u32, _vp, _vp, _sz)),
     ("vrenb200_exclusive_scan_u32_base", _i32, (_vp, _vp, _vp, _u32, _u32, _vp, _sz)),
+    ("vrenb200_exclusive_scan_u32_ex", _i32, (_vp, _vp, _vp, _u32, _u32, _vp, _sz, _u32)),
     ("vrenb200_radix_digit_histograms", _i32, (_vp, _vp, _u32, _vp)),
     ("vrenb200_bounce_point_lights", _i32, (_vp, _vp, _vp, _u32, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_float, C.c_float)),
     ("vrenb200_radix_sort_pairs_host_async", _i32, (_vp, _vp, _vp, _vp, _vp, _u32, _vp, _sz)),
