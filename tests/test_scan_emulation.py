@@ -20,8 +20,7 @@ def extract(text, name):
     return m.group(1) + "\n"
 
 
-@pytest.fixture(scope="module")
-def exe():
+def build(name, tsan=False):
     if not Path("/usr/local/cuda/include/cuda_runtime.h").exists():
         pytest.skip("CUDA headers not found (uint4, host types of common.cuh)")
     inc = OUT / "scan_inc"
@@ -31,12 +30,21 @@ def exe():
     body = extract(text, "body")
     assert "blockIdx.x" in body and "atomicAdd(&state->ticket, 1u)" in body and "st_relaxed_u64" in body
     (inc / "scan_chained_body.inc").write_text(body)
-    out = OUT / "scan_emulation"
+    out = OUT / name
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-Wall", "-Wno-unknown-pragmas", "-Wno-attributes", "-Wno-unused-variable", "-pthread",
            "-I/usr/local/cuda/include", f"-I{inc}", str(ROOT / "tests" / "cpp" / "scan_emulation.cpp"), "-o", str(out)]
+    if tsan:
+        cmd.insert(1, "-fsanitize=thread")
     r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and tsan and ("tsan" in r.stderr or "sanitize" in r.stderr):
+        pytest.skip("ThreadSanitizer runtime not available")
     assert r.returncode == 0, r.stderr
     return out
+
+
+@pytest.fixture(scope="module")
+def exe():
+    return build("scan_emulation")
 
 
 def run(exe, ticket, order, misalign, sizes):
@@ -60,3 +68,9 @@ def test_ticket_tile_ids_give_the_scan_in_any_cta_order(exe, order):
 def test_block_index_tile_ids_in_order(exe):
     rc, out = run(exe, False, "forward", 0, SIZES)
     assert rc == 0 and f"ALL PASS {len(SIZES)} cases" in out, out
+
+
+def test_ticket_form_is_race_free_under_thread_sanitizer():
+    """the ticket prologue (thread 0 takes the ticket, barrier, everybody reads it) and the rest of the body under ThreadSanitizer"""
+    rc, out = run(build("scan_emulation_tsan", tsan=True), True, "shuffle", 0, [3 * 8192 + 5])
+    assert rc == 0 and "ALL PASS 1 cases" in out and "ThreadSanitizer" not in out, out[-3000:]
