@@ -159,3 +159,24 @@ def test_python_callers_match_the_declared_signatures(handle):
             assert len(fn.argtypes) == len(node.args), f"{path.name}:{node.lineno}: {name} called with {len(node.args)} arguments, declared {len(fn.argtypes)}"
             checked += 1
     assert checked > 100
+
+
+def test_header_is_plain_c_and_links_from_c(handle, tmp_path):
+    """the boundary is a C ABI: include/vrenb200.h compiles as C11 (no C++ in the signatures) and a C program links against the
+    library and calls host-side entry points (sizing helpers: no device needed)"""
+    src = tmp_path / "cabi.c"
+    src.write_text('#include <stdio.h>\n#include "vrenb200.h"\n'
+                   "int main(void) {\n"
+                   "    vrenb200_sort_config cfg = {VRENB200_RANKING_AUTO, VRENB200_TILE_IDS_AUTO, VRENB200_SORT_VARIANT_SINGLE_CTA};\n"
+                   "    (void) cfg;\n"
+                   '    printf("%u %u %zu\\n", vrenb200_calc_bvh_buffer_length(1024), vrenb200_round_to_next_power_of_2(1000), vrenb200_scan_scratch_bytes(1u << 20));\n'
+                   "    return 0;\n}\n")
+    exe = tmp_path / "cabi"
+    libdir = build.LIB.parent
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(src), "-o", str(exe), f"-L{libdir}", "-lvrenb200",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    length, pow2, scratch = r.stdout.split()
+    assert int(length) == 32 * 32 + 32 + 1 and int(pow2) == 1024 and int(scratch) >= 8 * ((1 << 20) // 8192)
