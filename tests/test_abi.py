@@ -180,3 +180,14 @@ def test_header_is_plain_c_and_links_from_c(handle, tmp_path):
     assert r.returncode == 0, r.stderr
     length, pow2, scratch = r.stdout.split()
     assert int(length) == 32 * 32 + 32 + 1 and int(pow2) == 1024 and int(scratch) >= 8 * ((1 << 20) // 8192)
+
+
+def test_library_exports_exactly_the_c_abi(handle):
+    """dynamic symbols of libvrenb200.so == the functions include/vrenb200.h declares (linker version script csrc/exports.map):
+    no internal C++ symbol leaks out, nothing declared is missing"""
+    if os.environ.get("VRENB200_TUNING") == "1":
+        pytest.skip("tuning build")
+    r = subprocess.run(["nm", "-D", "--defined-only", str(build.LIB)], capture_output=True, text=True, check=True)
+    exported = {line.split()[-1] for line in r.stdout.splitlines() if line.strip()}
+    declared = set(lib.declared_symbols())
+    assert exported == declared, (sorted(exported - declared), sorted(declared - exported))

@@ -44,7 +44,7 @@ def _newer(target: Path, sources) -> bool:
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     sources = sorted(CSRC.glob("*.cu"))
-    deps = sources + sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").glob("*.h"))
+    deps = sources + sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").glob("*.h")) + [CSRC / "exports.map"]
     if not force and _newer(LIB, deps):
         return LIB
     objs = []
@@ -70,7 +70,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("CUDA build failed")
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + [str(o) for o in objs] + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", f"--version-script={CSRC / 'exports.map'}",
+           "-o", str(LIB)] + [str(o) for o in objs] + ["-lcudart"]
     subprocess.run(cmd, check=True)
     return LIB
 
