@@ -215,9 +215,10 @@ def cpu_secondary_baselines(small: bool = False):
     return out
 
 
-def secondary_metrics(lib, vlib, dev, out=None):
+def secondary_metrics(lib, vlib, dev, out=None, big_log2=28):
     """the other BASELINE.json configs, each timed with CUDA events after 3 warm-ups (inputs larger than L2):
-    C2 scan + reduce over 2^28 u32, C4 BuildBVH over 2^20 leaves, C5 clustered light assignment at 4K / 65 536 lights"""
+    C2 scan + reduce over 2^28 u32, C4 BuildBVH over 2^20 leaves, C5 clustered light assignment at 4K / 65 536 lights.
+    big_log2: the size of the 2^28 rows (28 always, except in tests/bench_dry_run.py, which walks this code without a GPU)"""
     import math
 
     import numpy as np
@@ -241,7 +242,7 @@ def secondary_metrics(lib, vlib, dev, out=None):
             ts.append(e0.elapsed_time(e1))
         return float(np.median(ts))
 
-    n = 1 << 28
+    n = 1 << big_log2
     x = torch.ones(n, dtype=torch.int32, device=dev)
     y = torch.empty_like(x)
     sb = lib.vrenb200_scan_scratch_bytes(n)
@@ -306,7 +307,7 @@ def secondary_metrics(lib, vlib, dev, out=None):
             del src, work, scr_s
     except Exception as exc:  # noqa: BLE001 - rows added without a GPU at hand: they must not take the other rows with them
         out["radix_sort_keys_small"] = {"error": f"{type(exc).__name__}: {exc}"}
-    nb = 1 << 26
+    nb = 1 << max(big_log2 - 2, 10)
     pairs = torch.randint(0, 1 << 16, (nb, 2), dtype=torch.int32, device=dev, generator=g)
     ob = lib.vrenb200_bucket_sort_output_bytes(nb)
     bout = torch.empty(ob, dtype=torch.uint8, device=dev)
@@ -410,7 +411,7 @@ def secondary_metrics(lib, vlib, dev, out=None):
     # ... and the scan's opt-in safe mode (ticket tile ids, vrenb200_exclusive_scan_u32_ex): the chained register-tile kernel at
     # every size; tests/test_scan_safe_mode.py is its parity check
     try:
-        n = 1 << 28
+        n = 1 << big_log2
         x = torch.ones(n, dtype=torch.int32, device=dev)
         y = torch.empty_like(x)
         sb = lib.vrenb200_scan_scratch_bytes(n)
@@ -860,7 +861,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def secondary_metrics_multi(lib, vlib, dev, sorter, rank, world, out=None):
+def secondary_metrics_multi(lib, vlib, dev, sorter, rank, world, out=None, big_log2=28):
     """N > 1: the other sharded paths of SURVEY 8e, device-timed (max over ranks): sharded exclusive scan and reduce over
     2^28 u32 per GPU, sharded bucket sort (16-bit key) of 2^26 pairs per GPU, clustered shading of 8 views at 4K over the ranks"""
     import math
@@ -889,7 +890,7 @@ def secondary_metrics_multi(lib, vlib, dev, sorter, rank, world, out=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    n = 1 << 28
+    n = 1 << big_log2                      # 28 always, except in tests/bench_dry_run.py
     ops = vdist.CudaOps()
     x = torch.ones(n, dtype=torch.int32, device=dev)
     ms = timed(lambda: vdist.sharded_exclusive_scan(x, ops=ops))
@@ -898,7 +899,7 @@ def secondary_metrics_multi(lib, vlib, dev, sorter, rank, world, out=None):
     ms = timed(lambda: vdist.sharded_reduce_add(x, ops=ops))
     out["sharded_reduce_u32_2p28_per_gpu"] = {"ms": ms, "GB/s_per_gpu": 4 * n / ms / 1e6, "frac_hbm": 4 * n / ms / 1e6 / peak, "bytes_per_elt": 4}
     del x
-    nb = 1 << 26
+    nb = 1 << max(big_log2 - 2, 10)
     g = torch.Generator(device=dev)
     g.manual_seed(77 + rank)
     bk = torch.randint(0, 1 << 16, (nb,), dtype=torch.int32, device=dev, generator=g)
