@@ -6,6 +6,7 @@ Python control flow of the bench (the timed loop, the e2e legs, the secondary ro
 assembly of the JSON line, the watchdog) is executed before the driver executes it on the GPU box.
 
     python tests/bench_dry_run.py [bench.py arguments]      prints bench.py's line; run by tests/test_bench_contract.py
+    python tests/bench_dry_run.py --script tests/run_small_sort.py      walks another GPU script the same way (exact fakes at any size)
 """
 import contextlib
 import ctypes as C
@@ -21,6 +22,7 @@ import torch  # noqa: E402
 from torch.overrides import TorchFunctionMode  # noqa: E402
 
 CPU = torch.device("cpu")
+EXACT_BELOW = 1 << 21        # the fakes really sort / scan below this many elements (--script: always)
 
 
 def is_cuda(d):
@@ -90,7 +92,7 @@ class FakeLib:
 
     # ---- sorts (small ones really sort; the 2^28-sized secondary rows are not worth minutes of numpy)
     def _sort(self, keys, vals, n):
-        if n > (1 << 21):
+        if n > EXACT_BELOW:
             return
         k = u32(keys, n)
         if vals:
@@ -126,7 +128,7 @@ class FakeLib:
 
     # ---- scans
     def _scan(self, src, dst, n, base):
-        if n > (1 << 21):                       # input is all ones in the bench: the closed form at the ends is all that is looked at
+        if n > EXACT_BELOW:                     # input is all ones in the bench: the closed form at the ends is all that is looked at
             u32(dst, 1)[0] = base
             u32(dst + 4 * (n - 4), 4)[:] = np.arange(n - 4, n, dtype=np.uint32) + np.uint32(base)
             return
@@ -139,6 +141,8 @@ class FakeLib:
         return 0
 
     def vrenb200_exclusive_scan_u32_ex(self, stream, src, dst, n, base, scratch, nbytes, flags):
+        if flags & ~1:
+            return 5                            # VRENB200_EINVAL_ARG, as the library answers an unknown flag
         self._scan(src, dst, n, base)
         return 0
 
@@ -208,6 +212,16 @@ def main():
     real = vlib.load()
     fake = FakeLib(real)
     vlib.load = lambda: fake
+    if len(sys.argv) > 2 and sys.argv[1] == "--script":
+        import runpy
+
+        global EXACT_BELOW
+        EXACT_BELOW = 1 << 40
+        script = sys.argv[2]
+        sys.argv = [script] + sys.argv[3:]
+        with OnCpu():
+            runpy.run_path(script, run_name="__main__")
+        return
     import functools
 
     import bench

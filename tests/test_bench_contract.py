@@ -7,6 +7,8 @@ import subprocess
 import sys
 from pathlib import Path
 
+import pytest
+
 ROOT = Path(__file__).resolve().parent.parent
 
 
@@ -133,3 +135,12 @@ def test_watchdog_prints_the_line_without_the_secondary_rows():
     assert r.returncode == 0, r.stderr[-3000:]
     d = _line(r.stdout)
     assert d["value"] > 0 and d["e2e"]["value"] > 0 and "abandoned" in d["secondary"]["error"]
+
+
+@pytest.mark.parametrize("script,expect", [("run_small_sort.py", "ok 75 cases"), ("run_scan_safe_mode.py", "ok 8 cases")])
+def test_first_hardware_run_scripts_walk_without_a_gpu(script, expect):
+    """the scripts behind the non-gating first-hardware-run tests (tests/test_small_sort.py, tests/test_scan_safe_mode.py) executed
+    with the stand-ins: if one of them fails on the GPU box, it is the kernel, not the script"""
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "bench_dry_run.py"), "--script", str(ROOT / "tests" / script)],
+                       capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert r.returncode == 0 and expect in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
