@@ -1,14 +1,31 @@
-// The device-side plan of the multi-GPU sort (vren_b200/csrc/sharded_plan.cuh::plan_body, the body of sharded_sort.cu's
-// plan_kernel) executed on the host by cta_emulator.hpp; built as a shared library and driven through ctypes by
-// tests/test_plan_emulation.py, which compares every output with the numpy mirror (vren_b200/dist.py::exchange_plan).
+// The device-side plan of the multi-GPU sort (the body of vren_b200/csrc/sharded_sort.cu::plan_kernel) executed on the host by
+// cta_emulator.hpp.  The kernel's text and the tables it fills are taken from sharded_sort.cu itself: tests/test_plan_emulation.py
+// extracts what lies between the [[plan-*]] markers into plan_defs.inc / plan_body.inc.  Built as a shared library and driven
+// through ctypes by that test, which compares every output with the numpy mirror (vren_b200/dist.py::exchange_plan).
 #include <cuda_runtime.h>      // host types only (cudaStream_t in radix_internal.cuh); nothing of the CUDA runtime is called
 
 #include "cta_emulator.hpp"
 
-#include "../../vren_b200/csrc/sharded_plan.cuh"
+#include "../../vren_b200/csrc/radix_internal.cuh"
 
 #include <cstring>
 #include <memory>
+
+namespace vrenb200 {
+namespace {
+
+#include "plan_defs.inc"
+
+// the kernel first waits for the histograms of all sources (an acquire load in a spin loop on the device); here they are in place
+inline void wait_epoch(const uint32_t*, uint32_t) {}
+
+void plan_body(sym_header* mine, sort_control* ctl_part, shard_params sp, seg_plan* plan, xfer_plan* xp, uint16_t* tile_seg, uint32_t* status)
+{
+#include "plan_body.inc"
+}
+
+} // namespace
+} // namespace vrenb200
 
 using namespace vrenb200;
 

@@ -1,9 +1,10 @@
-"""The DEVICE plan of the multi-GPU sort (csrc/sharded_plan.cuh::plan_body = the body of sharded_sort.cu's plan_kernel) executed
-on the host, thread for thread (tests/cpp/cta_emulator.hpp, 256 OS threads), against its numpy mirror
+"""The DEVICE plan of the multi-GPU sort (the body of csrc/sharded_sort.cu::plan_kernel, taken from that file between its
+[[plan-*]] markers) executed on the host, thread for thread (tests/cpp/cta_emulator.hpp, 256 OS threads), against its numpy mirror
 vren_b200.dist.exchange_plan — the mirror that tests/test_dist_cpu.py simulates the whole sort with.  So the chain
 "device plan == mirror == globally stable sort" holds on CPU too, for 1-8 ranks, 1-8 rounds, skewed and empty shards, narrow key
 ranges, 16-bit keys and plans that do not fit."""
 import ctypes as C
+import re
 import subprocess
 from pathlib import Path
 
@@ -16,6 +17,22 @@ ROOT = Path(__file__).resolve().parent.parent
 OUT = ROOT / "build" / "emulation"
 
 
+def extract_plan_sources():
+    """plan_defs.inc / plan_body.inc from sharded_sort.cu (comment markers: the compiled kernel is untouched)"""
+    text = (ROOT / "vren_b200" / "csrc" / "sharded_sort.cu").read_text()
+    inc = OUT / "plan_inc"
+    inc.mkdir(parents=True, exist_ok=True)
+    first = re.search(r"^(constexpr int kMaxRanks = \d+;)[^\n]*\[\[plan-defs-a\]\]", text, flags=re.M)
+    defs = re.search(r"\[\[plan-defs-b-begin\]\][^\n]*\n(.*?)\n[^\n]*\[\[plan-defs-b-end\]\]", text, flags=re.S)
+    body = re.search(r"\[\[plan-body-begin\]\][^\n]*\n(.*?)\n[^\n]*\[\[plan-body-end\]\]", text, flags=re.S)
+    assert first and defs and body
+    defs_text = re.sub(r"^size_t sym_", "inline size_t sym_", defs.group(1), flags=re.M)
+    (inc / "plan_defs.inc").write_text(first.group(1) + "\n" + defs_text + "\n")
+    assert "wait_epoch(&mine->hist_ready[d], sp.epoch)" in body.group(1) and "__syncthreads_count" in body.group(1)
+    (inc / "plan_body.inc").write_text(body.group(1) + "\n")
+    return inc
+
+
 @pytest.fixture(scope="module")
 def emu():
     OUT.mkdir(parents=True, exist_ok=True)
@@ -23,8 +40,9 @@ def emu():
     cuda_inc = "/usr/local/cuda/include"
     if not Path(cuda_inc, "cuda_runtime.h").exists():
         pytest.skip("CUDA headers not found (host types of radix_internal.cuh)")
+    inc = extract_plan_sources()
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-Wall", "-Wno-unknown-pragmas", "-Wno-attributes", "-Wno-unused-variable", "-Wno-unused-but-set-variable",
-           "-pthread", "-fPIC", "-shared", f"-I{cuda_inc}", str(ROOT / "tests" / "cpp" / "plan_emulation.cpp"), "-o", str(so)]
+           "-Wno-unused-function", "-pthread", "-fPIC", "-shared", f"-I{cuda_inc}", f"-I{inc}", str(ROOT / "tests" / "cpp" / "plan_emulation.cpp"), "-o", str(so)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     lib = C.CDLL(str(so))
@@ -149,8 +167,11 @@ def test_device_plan_is_race_free_under_thread_sanitizer():
     """barriers of plan_body: a ThreadSanitizer build of the same emulation (stand-alone driver) reports no data race"""
     OUT.mkdir(parents=True, exist_ok=True)
     exe = OUT / "plan_emulation_tsan"
+    if not Path("/usr/local/cuda/include/cuda_runtime.h").exists():
+        pytest.skip("CUDA headers not found")
+    inc = extract_plan_sources()
     cmd = ["g++", "-fsanitize=thread", "-DPLAN_EMULATION_MAIN", "-std=c++17", "-O1", "-g", "-Wno-unknown-pragmas", "-Wno-attributes", "-pthread",
-           "-I/usr/local/cuda/include", str(ROOT / "tests" / "cpp" / "plan_emulation.cpp"), "-o", str(exe)]
+           "-I/usr/local/cuda/include", f"-I{inc}", str(ROOT / "tests" / "cpp" / "plan_emulation.cpp"), "-o", str(exe)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0 and ("tsan" in r.stderr or "sanitize" in r.stderr or "cuda_runtime.h" in r.stderr):
         pytest.skip("ThreadSanitizer runtime or CUDA headers not available")
