@@ -281,6 +281,39 @@ def secondary_metrics(lib, vlib, dev, out=None, big_log2=28):
     out["radix_sort_keys_2p28"] = {"ms": ms, "Gkeys/s": n / ms / 1e6, "GB/s": 36 * n / ms / 1e6, "frac_hbm": 36 * n / ms / 1e6 / peak,
                                    "bytes_per_key": 36, "note": "time of (restore + sort) minus time of restore"}
     del keys, shuffled, kscr
+    # the headline sort under every ranking / tile-id configuration of vrenb200_sort_config (all of them kernels the GPU suite
+    # verifies), on this box, so that the cost of the checked default is in the same line as the headline
+    try:
+        pk = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+        pv = torch.arange(n, dtype=torch.int32, device=dev)
+        wk, wv = torch.empty_like(pk), torch.empty_like(pv)
+        pb = lib.vrenb200_radix_sort_scratch_bytes(n, 1)
+        pscr = torch.empty(pb, dtype=torch.uint8, device=dev)
+
+        def restore_pairs():
+            wk.copy_(pk)
+            wv.copy_(pv)
+
+        t_restore = timed(restore_pairs, iters=10)
+        row = {}
+        for label, ranking, tile_ids in (("sampled_ticket (default)", vlib.RANKING_ATOMIC_SAMPLED, vlib.TILE_IDS_TICKET),
+                                         ("sampled_block", vlib.RANKING_ATOMIC_SAMPLED, vlib.TILE_IDS_BLOCK_INDEX),
+                                         ("unverified_block", vlib.RANKING_ATOMIC_UNVERIFIED, vlib.TILE_IDS_BLOCK_INDEX),
+                                         ("verified_ticket", vlib.RANKING_ATOMIC_VERIFIED, vlib.TILE_IDS_TICKET),
+                                         ("match_ticket", vlib.RANKING_MATCH, vlib.TILE_IDS_TICKET)):
+            cfg_r = vlib.SortConfig(ranking, tile_ids, 0)
+
+            def sort_cfg():
+                restore_pairs()
+                vlib.check(lib.vrenb200_radix_sort_ex(stream, wk.data_ptr(), wv.data_ptr(), n, pscr.data_ptr(), pb, C.addressof(cfg_r), None), "radix_sort_ex")
+
+            ms_cfg = timed(sort_cfg, iters=10) - t_restore
+            row[label] = {"ms": ms_cfg, "Gpairs/s": n / ms_cfg / 1e6, "frac_hbm_68B": 68 * n / ms_cfg / 1e6 / peak}
+        row["note"] = "key-value pairs, time of (restore + sort) minus time of restore; CUDA events around the whole call"
+        out["radix_sort_pairs_2p28_by_config"] = row
+        del pk, pv, wk, wv, pscr
+    except Exception as exc:  # noqa: BLE001
+        out["radix_sort_pairs_2p28_by_config"] = {"error": f"{type(exc).__name__}: {exc}"}
     # C1 (BASELINE configs[0]: the reference's own radix-sort sizes, vren_test radix_sort.cpp:82-143): launch-bound small sorts.
     # "auto" is what a caller gets (ballot-match passes below 2^21 elements: no repeat kernel behind a pass); "sampled" is the
     # large-input default forced onto the same size, for comparison

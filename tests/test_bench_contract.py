@@ -93,7 +93,7 @@ def test_gpu_arm_control_flow_without_a_gpu_single():
     assert d["e2e"]["h2d_bytes_per_step"] == 8 << 14 and d["e2e"]["d2h_bytes_per_step"] == 8 << 14 and d["e2e"]["value"] > 0
     sec = d["secondary"]
     assert "error" not in sec, sec.get("error")
-    for name in ("scan_u32_2p28", "reduce_u32_add_final_2p28", "radix_sort_keys_2p28", "radix_sort_keys_2p10", "radix_sort_keys_2p20", "bucket_sort_2p26_uvec2",
+    for name in ("scan_u32_2p28", "reduce_u32_add_final_2p28", "radix_sort_keys_2p28", "radix_sort_pairs_2p28_by_config", "radix_sort_keys_2p10", "radix_sort_keys_2p20", "bucket_sort_2p26_uvec2",
                  "build_bvh_2p20_leaves", "light_assign_4k_65536_lights", "light_list_consumer_4k", "depth_pyramid_4k", "bounce_point_lights_65536",
                  "visualize_bvh_2p20_leaves", "radix_sort_single_cta", "scan_u32_2p28_safe_mode"):
         assert name in sec and "error" not in sec[name], (name, sec.get(name))
