@@ -970,6 +970,28 @@ def secondary_metrics_multi(lib, vlib, dev, sorter, rank, world, out=None, big_l
                                                    "clusters_per_view": [per_view[v][0] for v in sorted(per_view)],
                                                    "assigned_lights_per_view": [per_view[v][4] for v in sorted(per_view)],
                                                    "note": "lights broadcast once per frame (NCCL, inside the timed region), view v on rank v % world"}
+    # LAST: the headline multi-GPU sort cut into other numbers of rounds (each of them ran on hardware in round 2: profiles/r2e_, r2g_,
+    # r2j_), on this box: how much the overlap of transfers and passes is worth at this N
+    try:
+        ns = 1 << big_log2
+        g2 = torch.Generator(device=dev)
+        g2.manual_seed(4321 + rank)
+        sk = torch.randint(-(1 << 31), (1 << 31) - 1, (ns,), dtype=torch.int64, device=dev, generator=g2).to(torch.int32)
+        sv = torch.arange(ns, dtype=torch.int32, device=dev)
+        row = {}
+        for rounds in (1, 2, 4, 8):
+            ctx = vdist.ShardedSort.for_process_group(ns, None, rounds)
+            ms = timed(lambda: ctx.sort(sk, sv), iters=3)
+            torch.cuda.synchronize()
+            ctx.result()                         # raises (on every rank alike) if the plan did not fit
+            row[f"rounds_{rounds}"] = {"ms": ms, "Gpairs/s": world * ns / ms / 1e6}
+            ctx.close()
+            del ctx
+            torch.cuda.empty_cache()
+        out["sharded_sort_by_rounds"] = row
+        del sk, sv
+    except Exception as exc:  # noqa: BLE001
+        out["sharded_sort_by_rounds"] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
 
 

@@ -123,7 +123,9 @@ def test_gpu_arm_control_flow_without_a_gpu_two_ranks():
     assert d["phases_rank0_last_step"] is not None
     sec = d["secondary"]
     assert "error" not in sec, sec.get("error")
-    assert set(sec) == {"sharded_scan_u32_2p28_per_gpu", "sharded_reduce_u32_2p28_per_gpu", "sharded_bucket_sort_2p26_per_gpu", "light_assign_4k_65536_lights_8_views"}
+    assert set(sec) == {"sharded_scan_u32_2p28_per_gpu", "sharded_reduce_u32_2p28_per_gpu", "sharded_bucket_sort_2p26_per_gpu", "light_assign_4k_65536_lights_8_views",
+                        "sharded_sort_by_rounds"}
+    assert set(sec["sharded_sort_by_rounds"]) == {"rounds_1", "rounds_2", "rounds_4", "rounds_8"}
     assert sec["light_assign_4k_65536_lights_8_views"]["views"] == 8 and len(sec["light_assign_4k_65536_lights_8_views"]["clusters_per_view"]) == 8
 
 
