@@ -984,7 +984,7 @@ def secondary_metrics_multi(lib, vlib, dev, sorter, rank, world, out=None, big_l
             ms = timed(lambda: ctx.sort(sk, sv), iters=3)
             torch.cuda.synchronize()
             ctx.result()                         # raises (on every rank alike) if the plan did not fit
-            row[f"rounds_{rounds}"] = {"ms": ms, "Gpairs/s": world * ns / ms / 1e6}
+            row[f"rounds_{rounds}"] = {"ms": ms, "Gpairs/s": world * ns / ms / 1e6, "phases_this_rank_last_sort": ctx.phases()}
             ctx.close()
             del ctx
             torch.cuda.empty_cache()
